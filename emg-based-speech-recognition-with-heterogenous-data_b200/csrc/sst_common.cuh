@@ -1,0 +1,85 @@
+// Shared device/host helpers for libsst.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/sst.h"
+
+namespace sst {
+
+// ---- error plumbing (thread-local message, negative return codes; include/sst.h) ----------------
+void set_error(const char* fmt, ...);
+int  check_launch(const char* what);          // cudaPeekAtLastError -> SST_E_LAUNCH
+
+#define SST_REQUIRE(cond, code, ...)                         \
+  do { if (!(cond)) { ::sst::set_error(__VA_ARGS__); return (code); } } while (0)
+
+inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+int num_sms();
+
+// ---- dtype helpers --------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float ld_as_f32(const void* p, long i, int dtype) {
+  return dtype == SST_F32 ? ((const float*)p)[i] : __bfloat162float(((const __nv_bfloat16*)p)[i]);
+}
+__device__ __forceinline__ void st_from_f32(void* p, long i, int dtype, float v) {
+  if (dtype == SST_F32) ((float*)p)[i] = v; else ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
+}
+
+// ---- warp / block reductions ----------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- Philox4x32-10 counter RNG: the one dropout stream shared by every kernel ---------------------
+// keep(seed, idx) is a pure function of (seed, element index) so forward and backward kernels (and the
+// SIMT and tensor-core variants of one op) regenerate identical masks without storing them.
+struct Philox4 { uint32_t x, y, z, w; };
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint64_t seed, uint64_t ctr) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x5353542du, c3 = 0x62323030u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+// keep-threshold: element kept iff rnd >= thr, thr = p * 2^32
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
+  double t = (double)p * 4294967296.0;
+  return t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+}
+__host__ __device__ __forceinline__ bool philox_keep(uint64_t seed, uint64_t idx, uint32_t thr) {
+  Philox4 r = philox4x32_10(seed, idx >> 2);
+  uint32_t v = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
+  return v >= thr;
+}
+
+}  // namespace sst
