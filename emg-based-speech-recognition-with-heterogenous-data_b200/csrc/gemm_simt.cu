@@ -53,11 +53,14 @@ gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, const SimtPar
   __shared__ float sB[TK][TN + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
-  float acc[4][4];
+  // Two-level accumulation: each 16-deep K tile is summed into `part`, which is then folded into `acc` with Kahan
+  // compensation.  Weight gradients contract over thousands of tokens with heavy sign cancellation; a plain running
+  // fp32 sum there loses ~sqrt(K) more digits than the blocked sums of the reference's CPU BLAS.
+  float acc[4][4], comp[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; comp[i][j] = 0.f; }
 
   for (int k0 = 0; k0 < p.K; k0 += TK) {
     // 64x16 elements per operand, 256 threads -> 4 each.  In TN mode k is the contiguous index, in MN mode m/n is.
@@ -70,6 +73,11 @@ gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, const SimtPar
       sB[kk][mm] = load_b(B, p, n0 + mm, k0 + kk);
     }
     __syncthreads();
+    float part[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
       float a[4], b[4];
@@ -80,8 +88,17 @@ gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, const SimtPar
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(a[i], b[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float y = __fsub_rn(part[i][j], comp[i][j]);
+        const float t = __fadd_rn(acc[i][j], y);
+        comp[i][j] = __fsub_rn(__fsub_rn(t, acc[i][j]), y);
+        acc[i][j] = t;
+      }
     __syncthreads();
   }
 

@@ -1,0 +1,281 @@
+// Small data-movement / optimiser kernels around the hot path:
+//   shift_left        in-place time shift augmentation               (architecture.py:104-108)
+//   im2col_first      raw 8-channel EMG -> (rows, 32) patch matrix so the first ResBlock's k=3 s=2 conv and its 1x1
+//                     s=2 residual conv run as ONE tensor-core GEMM   (architecture.py:26,32,55)
+//   gather_rows_pad / scatter_rows   decollate_tensor + pad_sequence(42.0) and its adjoint
+//                                                                    (data_utils.py:176-185, architecture.py:116-117)
+//   embed_posenc fwd/bwd   nn.Embedding(padding_idx) + batch-indexed sinusoid/768 + dropout
+//                                                                    (architecture.py:126-127, transformer.py:431-435, Q10)
+//   permute3_cast     weight packing / gradient unpacking between the reference's parameter layouts and GEMM operands
+//   adamw             fused AdamW over a flat fp32 parameter buffer  (recognition_model.py:293; torch defaults)
+#include "vec.cuh"
+
+namespace sst {
+
+__global__ void shift_left_kernel(float* __restrict__ x, long n_chunks, int Tlen, int Cc, int r) {
+  const long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n_chunks * Cc) return;
+  float* p = x + (id / Cc) * (long)Tlen * Cc + (id % Cc);
+  for (int t = 0; t < Tlen - r; ++t) p[(long)t * Cc] = p[(long)(t + r) * Cc];
+  for (int t = Tlen - r; t < Tlen; ++t) p[(long)t * Cc] = 0.f;
+}
+
+// x: (n, Tin, 8) fp32 -> col: (n*Tin/2, 32):  [k*8 + c] = x[2t+k-1][c] (zero outside), [24 + c] = x[2t][c]
+template <typename T>
+__global__ void im2col_first_kernel(const float* __restrict__ x, T* __restrict__ col, long n_chunks, int Tin) {
+  const int To = Tin / 2;
+  const long total = n_chunks * To * 4;      // one thread per (row, 8-wide group)
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int grp = (int)(i & 3);
+    const long row = i >> 2;
+    const long chunk = row / To;
+    const int t = (int)(row - chunk * To);
+    const int tin = grp < 3 ? 2 * t + grp - 1 : 2 * t;
+    float v[8];
+    if (tin < 0 || tin >= Tin) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    } else {
+      load8_f32(x + (chunk * Tin + tin) * 8, v);
+    }
+    Vec8<T>::store(col + row * 32 + grp * 8, v);
+  }
+}
+
+// out[(b, t), :] = t < lens[b] ? in[(offs[b] + t), :] : fill
+template <typename T>
+__global__ void gather_rows_pad_kernel(const T* __restrict__ in, T* __restrict__ out, const long* __restrict__ offs,
+                                       const int* __restrict__ lens, int B, int Lmax, int D, float fill) {
+  const int dv = D / 8;
+  const long total = (long)B * Lmax * dv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dv) * 8;
+    const long row = i / dv;
+    const int b = (int)(row / Lmax), t = (int)(row % Lmax);
+    float v[8];
+    if (t < lens[b]) Vec8<T>::load(in + (offs[b] + t) * D + c, v);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fill;
+    }
+    Vec8<T>::store(out + row * D + c, v);
+  }
+}
+
+// adjoint: din[(offs[b] + t), :] = dout[(b, t), :] for t < lens[b]   (din pre-zeroed by the caller)
+template <typename T>
+__global__ void scatter_rows_kernel(const T* __restrict__ dout, T* __restrict__ din, const long* __restrict__ offs,
+                                    const int* __restrict__ lens, int B, int Lmax, int D) {
+  const int dv = D / 8;
+  const long total = (long)B * Lmax * dv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dv) * 8;
+    const long row = i / dv;
+    const int b = (int)(row / Lmax), t = (int)(row % Lmax);
+    if (t < lens[b]) {
+      float v[8];
+      Vec8<T>::load(dout + row * D + c, v);
+      Vec8<T>::store(din + (offs[b] + t) * D + c, v);
+    }
+  }
+}
+
+// out[(b,s), :] = dropout( W[y[b,s], :] + pe[b, :] / D )
+template <typename T>
+__global__ void embed_posenc_kernel(const long* __restrict__ y, const float* __restrict__ W, const float* __restrict__ pe,
+                                    T* __restrict__ out, int B, int S, int D, uint32_t thr, float dscale, unsigned long long seed) {
+  const int dv = D / 8;
+  const long total = (long)B * S * dv;
+  const float invD = 1.f / (float)D;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dv) * 8;
+    const long row = i / dv;
+    const int b = (int)(row / S);
+    float w[8], p[8], o[8];
+    load8_f32(W + y[row] * D + c, w);
+    load8_f32(pe + (long)b * D + c, p);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = w[j] + invD * p[j];
+    if (thr) {
+      bool k[8];
+      keep8(seed, (unsigned long long)row * D + c, thr, k);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = k[j] ? o[j] * dscale : 0.f;
+    }
+    Vec8<T>::store(out + row * D + c, o);
+  }
+}
+
+// dW[y[row], :] += keep * dout[row, :]   (rows with y == pad_idx skipped: nn.Embedding padding_idx)
+template <typename T>
+__global__ void embed_bwd_kernel(const long* __restrict__ y, const T* __restrict__ dout, float* __restrict__ dW, int B, int S, int D,
+                                 int pad_idx, uint32_t thr, float dscale, unsigned long long seed) {
+  const int dv = D / 8;
+  const long total = (long)B * S * dv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dv) * 8;
+    const long row = i / dv;
+    const long tok = y[row];
+    if (tok == pad_idx) continue;
+    float g[8];
+    Vec8<T>::load(dout + row * D + c, g);
+    if (thr) {
+      bool k[8];
+      keep8(seed, (unsigned long long)row * D + c, thr, k);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = k[j] ? g[j] * dscale : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(dW + tok * D + c + j, g[j]);
+  }
+}
+
+// out[i*o0 + j*o1 + k*o2] (+)= in[i*s0 + j*s1 + k*s2]   for (i,j,k) in d0 x d1 x d2
+template <typename TI, typename TO>
+__global__ void permute3_cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, long d0, long d1, long d2, long s0, long s1,
+                                     long s2, long o0, long o1, long o2, int accumulate) {
+  const long total = d0 * d1 * d2;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long k = i % d2, j = (i / d2) % d1, a = i / (d2 * d1);
+    const long oi = a * o0 + j * o1 + k * o2;
+    float v = to_f32(in[a * s0 + j * s1 + k * s2]);
+    if (accumulate) v += to_f32(out[oi]);
+    out[oi] = from_f32<TO>(v);
+  }
+}
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
+                             float lr, float beta1, float beta2, float eps, float wd, float bc1, float sqrt_bc2) {
+  for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long)gridDim.x * blockDim.x * 4) {
+    if (i + 4 <= n) {
+      float4 pp = *reinterpret_cast<float4*>(p + i), gg = *reinterpret_cast<const float4*>(g + i);
+      float4 mm = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
+      float* P = &pp.x; const float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        P[j] *= (1.f - lr * wd);
+        M[j] = beta1 * M[j] + (1.f - beta1) * G[j];
+        V[j] = beta2 * V[j] + (1.f - beta2) * G[j] * G[j];
+        const float denom = sqrtf(V[j]) / sqrt_bc2 + eps;
+        P[j] -= (lr / bc1) * (M[j] / denom);
+      }
+      *reinterpret_cast<float4*>(p + i) = pp; *reinterpret_cast<float4*>(m + i) = mm; *reinterpret_cast<float4*>(v + i) = vv;
+    } else {
+      for (long e = i; e < n; ++e) {
+        float P = p[e] * (1.f - lr * wd);
+        float M = beta1 * m[e] + (1.f - beta1) * g[e];
+        float V = beta2 * v[e] + (1.f - beta2) * g[e] * g[e];
+        P -= (lr / bc1) * (M / (sqrtf(V) / sqrt_bc2 + eps));
+        p[e] = P; m[e] = M; v[e] = V;
+      }
+    }
+  }
+}
+
+static int ew_grid2(long total, int threads) {
+  long blocks = (total + threads - 1) / threads;
+  long cap = (long)num_sms() * 16;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace sst
+
+using namespace sst;
+
+extern "C" {
+
+int sst_shift_left(float* x, int64_t n_chunks, int T, int Cc, int r, void* stream) {
+  SST_REQUIRE(r >= 0 && r < T, SST_E_ARG, "shift_left: bad shift %d", r);
+  if (r == 0 || n_chunks <= 0) return SST_OK;
+  const long ids = n_chunks * Cc;
+  shift_left_kernel<<<(int)((ids + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, n_chunks, T, Cc, r);
+  return check_launch("shift_left");
+}
+
+int sst_im2col_first(int out_dtype, const float* x, void* col, int64_t n_chunks, int Tin, void* stream) {
+  SST_REQUIRE(Tin % 2 == 0, SST_E_ARG, "im2col_first: Tin must be even");
+  if (n_chunks <= 0) return SST_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = ew_grid2(n_chunks * (Tin / 2) * 4, 256);
+  if (out_dtype == SST_F32) im2col_first_kernel<float><<<grid, 256, 0, st>>>(x, (float*)col, n_chunks, Tin);
+  else im2col_first_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)col, n_chunks, Tin);
+  return check_launch("im2col_first");
+}
+
+int sst_gather_rows_pad(int dtype, const void* in, void* out, const int64_t* offs, const int32_t* lens, int B, int Lmax, int D,
+                        float fill, void* stream) {
+  SST_REQUIRE(D % 8 == 0, SST_E_ARG, "gather_rows_pad: D must be a multiple of 8");
+  if (B <= 0 || Lmax <= 0) return SST_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = ew_grid2((long)B * Lmax * (D / 8), 256);
+  if (dtype == SST_F32) gather_rows_pad_kernel<float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, (const long*)offs, lens, B, Lmax, D, fill);
+  else gather_rows_pad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, (const long*)offs, lens, B, Lmax, D, fill);
+  return check_launch("gather_rows_pad");
+}
+
+int sst_scatter_rows(int dtype, const void* dout, void* din, const int64_t* offs, const int32_t* lens, int B, int Lmax, int D,
+                     void* stream) {
+  SST_REQUIRE(D % 8 == 0, SST_E_ARG, "scatter_rows: D must be a multiple of 8");
+  if (B <= 0 || Lmax <= 0) return SST_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = ew_grid2((long)B * Lmax * (D / 8), 256);
+  if (dtype == SST_F32) scatter_rows_kernel<float><<<grid, 256, 0, st>>>((const float*)dout, (float*)din, (const long*)offs, lens, B, Lmax, D);
+  else scatter_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)din, (const long*)offs, lens, B, Lmax, D);
+  return check_launch("scatter_rows");
+}
+
+int sst_embed_posenc_fwd(int out_dtype, const int64_t* y, const float* W, const float* pe, void* out, int B, int S, int D,
+                         float drop_p, uint64_t seed, void* stream) {
+  SST_REQUIRE(D % 8 == 0, SST_E_ARG, "embed_posenc: D must be a multiple of 8");
+  if (B <= 0 || S <= 0) return SST_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const uint32_t thr = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
+  const float ds = drop_p < 1.f ? 1.f / (1.f - drop_p) : 0.f;
+  const int grid = ew_grid2((long)B * S * (D / 8), 256);
+  if (out_dtype == SST_F32) embed_posenc_kernel<float><<<grid, 256, 0, st>>>((const long*)y, W, pe, (float*)out, B, S, D, thr, ds, seed);
+  else embed_posenc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const long*)y, W, pe, (__nv_bfloat16*)out, B, S, D, thr, ds, seed);
+  return check_launch("embed_posenc_fwd");
+}
+
+int sst_embed_bwd(int dtype, const int64_t* y, const void* dout, float* dW, int B, int S, int D, int pad_idx, float drop_p,
+                  uint64_t seed, void* stream) {
+  SST_REQUIRE(D % 8 == 0, SST_E_ARG, "embed_bwd: D must be a multiple of 8");
+  if (B <= 0 || S <= 0) return SST_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const uint32_t thr = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
+  const float ds = drop_p < 1.f ? 1.f / (1.f - drop_p) : 0.f;
+  const int grid = ew_grid2((long)B * S * (D / 8), 256);
+  if (dtype == SST_F32) embed_bwd_kernel<float><<<grid, 256, 0, st>>>((const long*)y, (const float*)dout, dW, B, S, D, pad_idx, thr, ds, seed);
+  else embed_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const long*)y, (const __nv_bfloat16*)dout, dW, B, S, D, pad_idx, thr, ds, seed);
+  return check_launch("embed_bwd");
+}
+
+int sst_permute3_cast(int in_dtype, int out_dtype, const void* in, void* out, int64_t d0, int64_t d1, int64_t d2, int64_t s0,
+                      int64_t s1, int64_t s2, int64_t o0, int64_t o1, int64_t o2, int accumulate, void* stream) {
+  const long total = d0 * d1 * d2;
+  if (total <= 0) return SST_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = ew_grid2(total, 256);
+  typedef __nv_bfloat16 bf;
+  if (in_dtype == SST_F32 && out_dtype == SST_F32) permute3_cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, d0, d1, d2, s0, s1, s2, o0, o1, o2, accumulate);
+  else if (in_dtype == SST_F32) permute3_cast_kernel<float, bf><<<grid, 256, 0, st>>>((const float*)in, (bf*)out, d0, d1, d2, s0, s1, s2, o0, o1, o2, accumulate);
+  else if (out_dtype == SST_F32) permute3_cast_kernel<bf, float><<<grid, 256, 0, st>>>((const bf*)in, (float*)out, d0, d1, d2, s0, s1, s2, o0, o1, o2, accumulate);
+  else permute3_cast_kernel<bf, bf><<<grid, 256, 0, st>>>((const bf*)in, (bf*)out, d0, d1, d2, s0, s1, s2, o0, o1, o2, accumulate);
+  return check_launch("permute3_cast");
+}
+
+int sst_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, float wd,
+              int64_t step, void* stream) {
+  SST_REQUIRE(step >= 1, SST_E_ARG, "adamw: step is 1-based");
+  SST_REQUIRE(((uintptr_t)p & 15) == 0 && ((uintptr_t)g & 15) == 0 && ((uintptr_t)m & 15) == 0 && ((uintptr_t)v & 15) == 0, SST_E_ARG,
+              "adamw: buffers must be 16-byte aligned");
+  if (n <= 0) return SST_OK;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const int grid = ew_grid2((n + 3) / 4, 256);
+  adamw_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, (float)bc1,
+                                                                         (float)sqrt(bc2));
+  return check_launch("adamw");
+}
+
+}  // extern "C"

@@ -1,0 +1,570 @@
+"""Host-side orchestration of the hot path: explicit forward AND backward over libsst.so kernels.
+
+Mirrors, op for op, the reference modules it replaces (paths relative to /root/reference/speech_recognition/):
+  ResBlock x3 + w_raw_in          architecture.py:22-48, :54-59, :109-112
+  decollate / pad(42) / masks     architecture.py:116-121, data_utils.py:176-185
+  TransformerEncoderLayer         transformer.py:47-64   (post-LN, ReLU FFN, rel-pos MHA :162-210, :260-403)
+  TransformerDecoderLayer         transformer.py:108-134 (causal self-attn + cross-attn, no rel-pos)
+  embedding_tgt + pos_decoder     architecture.py:126-127, transformer.py:431-435
+  w_aux / w_out heads             architecture.py:139
+  CTC + label-smoothed CE mix     recognition_model.py:93-107, LabelSmoothingLoss.py:13-15
+PyTorch supplies device memory (torch.empty) and the current stream only; there is no autograd in here and no
+torch math op on an activation.  Activation layout: token-major rows (b*L + t, D), compute dtype fp32 (parity
+mode) or bf16 (tensor-core mode); conv activations are channels-last with one zero halo row on each side of every
+1600-sample chunk so that a k=3 convolution is a row-shifted GEMM (include/sst.h).
+"""
+import math
+
+import torch
+
+from . import lib as L
+
+PAD = 42
+
+
+class Ctx(dict):
+    """Saved-for-backward tensors of one forward pass (plain attribute dict)."""
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+class Engine:
+    def __init__(self, params, buffers, cfg, dtype=torch.float32, device="cuda"):
+        """params: name -> fp32 CUDA tensor (reference names); buffers: BN running stats + pos_decoder.pe."""
+        L.require_device()
+        self.P = params
+        self.Bf = buffers
+        self.cfg = dict(cfg)
+        self.dtype = dtype
+        self.dt = L.F32 if dtype == torch.float32 else L.BF16
+        self.dev = torch.device(device)
+        self.D = cfg["d_model"]
+        self.F = cfg["d_ff"]
+        self.H = cfg["n_heads"]
+        self.dh = self.D // self.H
+        self.R = cfg["rel_dist"]
+        self.n_enc = cfg["n_enc"]
+        self.n_dec = cfg["n_dec"]
+        self.n_out_enc = params["w_aux.weight"].shape[0]
+        self.n_out_dec = params["w_out.weight"].shape[0]
+        self.LDH = 64                      # pitch of the (padded) head-logit matrices
+        self.pk = {}
+        self.force_simt = False
+        self._packed_version = None
+        self._bn_scratch = torch.empty(3 * self.D, dtype=torch.float64, device=self.dev)
+        assert self.D % 64 == 0 and self.dh % 8 == 0
+
+    # ------------------------------------------------------------------------------------------------ utils
+    def empty(self, *shape, dtype=None):
+        return torch.empty(*shape, dtype=dtype or self.dtype, device=self.dev)
+
+    def zeros(self, *shape, dtype=None):
+        return torch.zeros(*shape, dtype=dtype or self.dtype, device=self.dev)
+
+    def gemm(self, A, B, C, M, N, K, lda, ldb, ldc, **kw):
+        L.gemm(A, B, C, M, N, K, lda, ldb, ldc, force_simt=self.force_simt, **kw)
+
+    # ------------------------------------------------------------------------------------------------ packing
+    def _cast2d(self, w2d, transpose=False):
+        N, K = w2d.shape
+        if transpose:
+            Np = N if N % 8 == 0 else (N + 63) // 64 * 64      # TMA needs 16-byte row pitches (44/43-class heads)
+            out = self.zeros(K, Np)[:, :N]
+            L.permute3_cast(w2d, out, (1, K, N), (0, 1, K), (0, Np, 1))
+        else:
+            if self.dtype == torch.float32:
+                return w2d
+            out = self.empty(N, K)
+            L.permute3_cast(w2d, out, (1, N, K), (0, K, 1), (0, K, 1))
+        return out
+
+    def _pack_linear(self, key, w2d):
+        self.pk[key] = self._cast2d(w2d)
+        self.pk[key + ".T"] = self._cast2d(w2d, transpose=True)
+
+    def _pack_heads_in(self, key, ws):
+        """ws: list of (H, D, dh) per-head projection weights -> W (len*H*dh, D) and its transpose."""
+        H, D, dh = ws[0].shape
+        HD = H * dh
+        n = len(ws)
+        W = self.empty(n * HD, D)
+        for s, w in enumerate(ws):
+            L.permute3_cast(w, W[s * HD:], (H, dh, D), (D * dh, 1, dh), (dh * D, D, 1))
+        WT = self.empty(D, n * HD)
+        L.permute3_cast(W, WT, (1, D, n * HD), (0, 1, D), (0, n * HD, 1))
+        self.pk[key] = W
+        self.pk[key + ".T"] = WT
+
+    def _pack_conv3(self, key, w, stride):
+        Co, Ci, _ = w.shape
+        W = self.empty(Co, 3 * Ci)
+        L.permute3_cast(w, W, (Co, 3, Ci), (Ci * 3, 1, 3), (3 * Ci, Ci, 1))
+        self.pk[key] = W
+        flat = w.reshape(-1)
+        if stride == 1:
+            Wd = self.empty(Ci, 3 * Co)           # segment s = tap k, read with row shift 1-k
+            L.permute3_cast(w, Wd, (Ci, 3, Co), (3, 1, Ci * 3), (3 * Co, Co, 1))
+            self.pk[key + ".d"] = Wd
+        else:
+            We = self.empty(Ci, Co)               # even input positions: tap 1
+            L.permute3_cast(flat[1:], We, (1, Ci, Co), (0, 3, Ci * 3), (0, Co, 1))
+            Wo = self.empty(Ci, 2 * Co)           # odd positions: [tap 2 | tap 0], the latter read from the next row
+            L.permute3_cast(flat[2:], Wo, (1, Ci, Co), (0, 3, Ci * 3), (0, 2 * Co, 1))
+            L.permute3_cast(flat, Wo[:, Co:], (1, Ci, Co), (0, 3, Ci * 3), (0, 2 * Co, 1))
+            self.pk[key + ".de"] = We
+            self.pk[key + ".do"] = Wo
+
+    def pack(self, version=None):
+        """(Re)build the GEMM-operand forms of every weight.  Call after the weights change."""
+        if version is not None and version == self._packed_version:
+            return
+        P, D, C = self.P, self.D, self.D
+        self.pk = {}
+        # first ResBlock: conv1 (k3) and residual_path (k1) over 8 channels as one (2C, 32) operand
+        wcat = self.zeros(2 * C, 32)
+        L.permute3_cast(P["conv_blocks.0.conv1.weight"], wcat, (C, 3, 8), (24, 1, 3), (32, 8, 1))
+        L.permute3_cast(P["conv_blocks.0.residual_path.weight"], wcat[C:, 24:], (1, C, 8), (0, 8, 1), (0, 32, 1))
+        self.pk["first.W"] = wcat
+        bcat = torch.empty(2 * C, dtype=torch.float32, device=self.dev)
+        L.permute3_cast(P["conv_blocks.0.conv1.bias"], bcat, (1, 1, C), (0, 0, 1), (0, 0, 1))
+        L.permute3_cast(P["conv_blocks.0.residual_path.bias"], bcat[C:], (1, 1, C), (0, 0, 1), (0, 0, 1))
+        self.pk["first.b"] = bcat
+        self._pack_conv3("conv_blocks.0.conv2", P["conv_blocks.0.conv2.weight"], 1)
+        for i in (1, 2):
+            p = "conv_blocks.%d" % i
+            self._pack_conv3(p + ".conv1", P[p + ".conv1.weight"], 2)
+            self._pack_conv3(p + ".conv2", P[p + ".conv2.weight"], 1)
+            self._pack_linear(p + ".res", P[p + ".residual_path.weight"].view(C, C))
+        self._pack_linear("w_raw_in", P["w_raw_in.weight"])
+        for i in range(self.n_enc):
+            p = "transformerEncoder.layers.%d" % i
+            a = p + ".self_attn"
+            self._pack_heads_in(a + ".qkv", [P[a + ".w_q"], P[a + ".w_k"], P[a + ".w_v"]])
+            self._pack_linear(a + ".o", P[a + ".w_o"].view(D, D))       # (H*dh, D): this IS W_o^T; ".T" is W_o
+            E = P[a + ".relative_positional.embeddings"]
+            self.pk[a + ".E"] = self._cast2d(E.view(-1, self.dh))
+            self._pack_linear(p + ".linear1", P[p + ".linear1.weight"])
+            self._pack_linear(p + ".linear2", P[p + ".linear2.weight"])
+        for i in range(self.n_dec):
+            p = "transformerDecoder.layers.%d" % i
+            a = p + ".self_attn"
+            self._pack_heads_in(a + ".qkv", [P[a + ".w_q"], P[a + ".w_k"], P[a + ".w_v"]])
+            self._pack_linear(a + ".o", P[a + ".w_o"].view(D, D))
+            m = p + ".multihead_attn"
+            self._pack_heads_in(m + ".q", [P[m + ".w_q"]])
+            self._pack_heads_in(m + ".kv", [P[m + ".w_k"], P[m + ".w_v"]])
+            self._pack_linear(m + ".o", P[m + ".w_o"].view(D, D))
+            self._pack_linear(p + ".linear1", P[p + ".linear1.weight"])
+            self._pack_linear(p + ".linear2", P[p + ".linear2.weight"])
+        self._pack_linear("w_aux", P["w_aux.weight"])
+        self._pack_linear("w_out", P["w_out.weight"])
+        self._packed_version = version
+
+    # ------------------------------------------------------------------------------------------------ building blocks
+    def _linear_fwd(self, x, M, key, bias=None, relu=False, drop_p=0.0, seed=0, out=None, out_dtype=None, N=None, ldc=None):
+        W = self.pk[key]
+        Nw, K = W.shape
+        N = N or Nw
+        ldc = ldc or N
+        if out is None:
+            out = self.empty(M, ldc, dtype=out_dtype)
+        epi = (L.EPI_BIAS if bias is not None else 0) | (L.EPI_RELU if relu else 0) | (L.EPI_DROPOUT if drop_p > 0 else 0)
+        self.gemm(x, W, out, M, N, K, x.stride(0), K, ldc, bias=bias, epilogue=epi, drop_p=drop_p, seed=seed)
+        return out
+
+    def _linear_bwd(self, dy, x, M, key, G, wname, bname=None, dx_out=None, accum_dx=False, aux=None, mask_scale=1.0,
+                    need_dx=True, K_dy=None):
+        """dW (+)= dy^T x into G[wname] (reference layout (N,K)); db += colsum(dy); dx (+)= dy W (optional relu/dropout mask)."""
+        W = self.pk[key]
+        N, K = W.shape
+        if G is not None:
+            self.gemm(dy, x, G[wname], N, K, M, dy.stride(0), x.stride(0), K, layout=L.GEMM_NT_MN, epilogue=L.EPI_ACCUM,
+                      a_cols=dy.stride(0) if dy.stride(0) >= N else N, b_cols=K)
+            if bname is not None:
+                L.colsum_accum(self.dt, dy, M, N, dy.stride(0), G[bname])
+        if not need_dx:
+            return None
+        WT = self.pk[key + ".T"]                # (K, N)
+        if dx_out is None:
+            dx_out = self.empty(M, K)
+        epi = (L.EPI_ACCUM if accum_dx else 0) | (L.EPI_MULMASK if aux is not None else 0)
+        self.gemm(dy, WT, dx_out, M, K, N, dy.stride(0), WT.stride(0), dx_out.stride(0), aux=aux, ldaux=aux.stride(0) if aux is not None else 0,
+                  epilogue=epi, mask_scale=mask_scale, a_cols=N)
+        return dx_out
+
+    def _ln_fwd(self, x, r, M, prefix, p, seed):
+        """returns y; r's buffer is overwritten with the pre-norm sum s (saved for backward)."""
+        y = self.empty(M, self.D)
+        mean = self.empty(M, dtype=torch.float32)
+        rstd = self.empty(M, dtype=torch.float32)
+        L.layernorm_fwd(self.dt, M, self.D, x, r, p, seed, self.P[prefix + ".weight"], self.P[prefix + ".bias"], y, r, mean, rstd)
+        return y, (r, mean, rstd, p, seed)
+
+    def _ln_bwd(self, dy, saved, M, prefix, G):
+        s, mean, rstd, p, seed = saved
+        ds = self.empty(M, self.D)
+        dr = self.empty(M, self.D) if p > 0 else None
+        L.layernorm_bwd(self.dt, M, self.D, dy, s, mean, rstd, self.P[prefix + ".weight"], ds, dr, p, seed,
+                        G[prefix + ".weight"], G[prefix + ".bias"])
+        return ds, (dr if p > 0 else ds)
+
+    def _attn_desc(self, B, Lq, Lk, ldq, ldk, ldv, causal, mask_q_rows, R, p, seed):
+        return L.attn_desc(self.dt, B, self.H, Lq, Lk, self.dh, ldq, ldk, ldv, self.D, causal, mask_q_rows, R,
+                           1.0 / math.sqrt(self.dh), p, seed, self.force_simt)
+
+    # ------------------------------------------------------------------------------------------------ conv front-end
+    def _bn_stats(self, x, rows, ld, prefix, training):
+        C = self.D
+        mean = self.empty(C, dtype=torch.float32)
+        invstd = self.empty(C, dtype=torch.float32)
+        rm, rv = self.Bf[prefix + ".running_mean"], self.Bf[prefix + ".running_var"]
+        if training:
+            stats = self._bn_scratch
+            L.colstats(self.dt, x, rows, C, ld, stats)
+            L.bn_finalize(stats, rows, C, 1e-5, 0.1, mean, invstd, rm, rv, True)
+            self.Bf[prefix + ".num_batches_tracked"] += 1
+        else:
+            L.bn_finalize(None, rows, C, 1e-5, 0.1, mean, invstd, rm, rv, False)
+        return mean, invstd, self.P[prefix + ".weight"], self.P[prefix + ".bias"]
+
+    def _resblock_fwd(self, i, inp, n, T_in, training, last):
+        C = self.D
+        T = T_in // 2
+        rows = n * T
+        pfx = "conv_blocks.%d" % i
+        c = Ctx(i=i, n=n, T_in=T_in, T=T, inp=inp)
+        if i == 0:
+            col = self.empty(rows, 32)
+            L.im2col_first(self.dt, inp, col, n, T_in)
+            ycat = self.empty(rows, 2 * C)
+            self.gemm(col, self.pk["first.W"], ycat, rows, 2 * C, 32, 32, 32, 2 * C, bias=self.pk["first.b"], epilogue=L.EPI_BIAS)
+            yc1, ld1, yr, ldr = ycat, 2 * C, ycat[:, C:], 2 * C
+            c.col = col
+        else:
+            P = T + 1                                    # pair-rows per chunk of the (T_in + 2)-row padded input
+            yc1 = self.empty(rows, C)
+            self.gemm(inp, self.pk[pfx + ".conv1"], yc1, n * P, C, 3 * C, 2 * C, 3 * C, C, n_seg=3, a_row_shift=(0, 0, 1),
+                      a_col0=(0, C, 0), a_rows=n * P, a_cols=2 * C, remap=(P, T, 0), bias=self.P[pfx + ".conv1.bias"],
+                      epilogue=L.EPI_BIAS)
+            yr = self.empty(rows, C)
+            self.gemm(inp, self.pk[pfx + ".res"], yr, n * P, C, C, 2 * C, C, C, a_col0=(C, 0, 0), a_rows=n * P, a_cols=2 * C,
+                      remap=(P, T, 0), bias=self.P[pfx + ".residual_path.bias"], epilogue=L.EPI_BIAS)
+            ld1, ldr = C, C
+        bn1 = self._bn_stats(yc1, rows, ld1, pfx + ".bn1", training)
+        h1p = self.empty(n, T + 2, C)
+        L.bn_apply(self.dt, n, T, C, yc1, ld1, bn1, None, 0, None, True, h1p, 1, 1)
+        yc2 = self.empty(rows, C)
+        self.gemm(h1p, self.pk[pfx + ".conv2"], yc2, n * (T + 2), C, 3 * C, C, 3 * C, C, n_seg=3, a_row_shift=(-1, 0, 1),
+                  a_rows=n * (T + 2), a_cols=C, remap=(T + 2, T, 1), bias=self.P[pfx + ".conv2.bias"], epilogue=L.EPI_BIAS)
+        bn2 = self._bn_stats(yc2, rows, C, pfx + ".bn2", training)
+        bnr = self._bn_stats(yr, rows, ldr, pfx + ".res_norm", training)
+        lead = 0 if last else 1
+        out = self.empty(n, T + 2 * lead, C)
+        L.bn_apply(self.dt, n, T, C, yc2, C, bn2, yr, ldr, bnr, True, out, lead, lead)
+        c.update(yc1=yc1, ld1=ld1, yr=yr, ldr=ldr, bn1=bn1, h1p=h1p, yc2=yc2, bn2=bn2, bnr=bnr, out=out, lead=lead)
+        return out, c
+
+    def _resblock_bwd(self, c, dout, G):
+        """dout: compact (n*T, C) gradient of the block output.  Returns the compact gradient of the block input (None for block 0)."""
+        C, n, T, i = self.D, c.n, c.T, c.i
+        rows = n * T
+        pfx = "conv_blocks.%d" % i
+        red = self._bn_scratch
+        # out = relu(bn2(yc2) + res_norm(yr))
+        dyc2p = self.empty(n, T + 2, C)
+        if i == 0:
+            dycat = self.empty(rows, 2 * C)
+            dyr, ld_dyr, lr, tr = dycat[:, C:], 2 * C, 0, 0
+        else:
+            dyr = self.empty(n, T + 1, C)
+            ld_dyr, lr, tr = C, 0, 1
+        L.bn_bwd(self.dt, n, T, C, dout, C, c.out, c.lead, c.lead, True,
+                 c.yc2, C, c.bn2[0], c.bn2[1], c.bn2[2], dyc2p, C, 1, 1, G[pfx + ".bn2.weight"], G[pfx + ".bn2.bias"],
+                 c.yr, c.ldr, c.bnr[0], c.bnr[1], c.bnr[2], dyr, ld_dyr, lr, tr, G[pfx + ".res_norm.weight"], G[pfx + ".res_norm.bias"], red)
+        # conv2 (k3, s1): weight gradient in packed (C, 3C) form, then unpack-accumulate into (C, C, 3)
+        Pp = T + 2
+        dW = self.empty(C, 3 * C, dtype=torch.float32)
+        self.gemm(dyc2p, c.h1p, dW, C, 3 * C, n * Pp, C, C, 3 * C, layout=L.GEMM_NT_MN, n_seg=3, b_row_shift=(-1, 0, 1),
+                  a_rows=n * Pp, a_cols=C, b_rows=n * Pp, b_cols=C)
+        L.permute3_cast(dW, G[pfx + ".conv2.weight"], (C, C, 3), (3 * C, 1, C), (3 * C, 3, 1), accumulate=True)
+        dh1 = self.empty(rows, C)
+        self.gemm(dyc2p, self.pk[pfx + ".conv2.d"], dh1, n * Pp, C, 3 * C, C, 3 * C, C, n_seg=3, a_row_shift=(1, 0, -1),
+                  a_rows=n * Pp, a_cols=C, remap=(Pp, T, 1))
+        # h1p = relu(bn1(yc1))
+        if i == 0:
+            dyc1, ld_dyc1, l1, t1 = dycat, 2 * C, 0, 0
+        else:
+            dyc1 = self.empty(n, T + 1, C)
+            ld_dyc1, l1, t1 = C, 0, 1
+        L.bn_bwd(self.dt, n, T, C, dh1, C, c.h1p, 1, 1, True,
+                 c.yc1, c.ld1, c.bn1[0], c.bn1[1], c.bn1[2], dyc1, ld_dyc1, l1, t1, G[pfx + ".bn1.weight"], G[pfx + ".bn1.bias"],
+                 None, 0, None, None, None, None, 0, 0, 0, None, None, red)
+        if i == 0:
+            dWc = self.empty(2 * C, 32, dtype=torch.float32)
+            self.gemm(dycat, c.col, dWc, 2 * C, 32, rows, 2 * C, 32, 32, layout=L.GEMM_NT_MN, a_rows=rows, a_cols=2 * C,
+                      b_rows=rows, b_cols=32)
+            L.permute3_cast(dWc, G[pfx + ".conv1.weight"], (C, 8, 3), (32, 1, 8), (24, 3, 1), accumulate=True)
+            L.permute3_cast(dWc[C:, 24:], G[pfx + ".residual_path.weight"], (1, C, 8), (0, 32, 1), (0, 8, 1), accumulate=True)
+            return None
+        P = T + 1
+        inp = c.inp                                        # (n, T_in + 2, C) == pair view (n*P, 2C)
+        dW = self.empty(C, 3 * C, dtype=torch.float32)
+        self.gemm(dyc1, inp, dW, C, 3 * C, n * P, C, 2 * C, 3 * C, layout=L.GEMM_NT_MN, n_seg=3, b_row_shift=(0, 0, 1),
+                  b_col0=(0, C, 0), a_rows=n * P, a_cols=C, b_rows=n * P, b_cols=2 * C)
+        L.permute3_cast(dW, G[pfx + ".conv1.weight"], (C, C, 3), (3 * C, 1, C), (3 * C, 3, 1), accumulate=True)
+        self.gemm(dyr, inp, G[pfx + ".residual_path.weight"], C, C, n * P, C, 2 * C, C, layout=L.GEMM_NT_MN, b_col0=(C, 0, 0),
+                  a_rows=n * P, a_cols=C, b_rows=n * P, b_cols=2 * C, epilogue=L.EPI_ACCUM)
+        dinp = self.empty(n * c.T_in, C)                   # compact; as pair view (n*T, 2C): [even | odd] input positions
+        self.gemm(dyc1, self.pk[pfx + ".conv1.de"], dinp, n * P, C, C, C, C, 2 * C, a_rows=n * P, a_cols=C, remap=(P, T, 0))
+        self.gemm(dyr, self.pk[pfx + ".res.T"], dinp, n * P, C, C, C, C, 2 * C, a_rows=n * P, a_cols=C, remap=(P, T, 0),
+                  epilogue=L.EPI_ACCUM)
+        self.gemm(dyc1, self.pk[pfx + ".conv1.do"], dinp.view(-1)[C:], n * P, C, 2 * C, C, 2 * C, 2 * C, n_seg=2,
+                  a_row_shift=(0, 1, 0), a_rows=n * P, a_cols=C, remap=(P, T, 0))
+        return dinp
+
+    # ------------------------------------------------------------------------------------------------ encoder
+    def _enc_layer_fwd(self, x, B, Lx, lens, i, training, seeds):
+        D, M = self.D, B * Lx
+        p = self.cfg["dropout"] if training else 0.0
+        pfx = "transformerEncoder.layers.%d" % i
+        a = pfx + ".self_attn"
+        qkv = self._linear_fwd(x, M, a + ".qkv")
+        o = self.empty(M, D)
+        lse = self.empty(2 * B * self.H * Lx, dtype=torch.float32)
+        ad = self._attn_desc(B, Lx, Lx, 3 * D, 3 * D, 3 * D, False, True, self.R, p, seeds())
+        L.attn_fwd(ad, qkv, qkv[:, D:], qkv[:, 2 * D:], self.pk[a + ".E"], lens, lens, o, lse)
+        y = self._linear_fwd(o, M, a + ".o.T")
+        x1, ln1 = self._ln_fwd(x, y, M, pfx + ".norm1", p, seeds())
+        s_ffn = seeds()
+        h = self._linear_fwd(x1, M, pfx + ".linear1", bias=self.P[pfx + ".linear1.bias"], relu=True, drop_p=p, seed=s_ffn)
+        y2 = self._linear_fwd(h, M, pfx + ".linear2", bias=self.P[pfx + ".linear2.bias"])
+        x2, ln2 = self._ln_fwd(x1, y2, M, pfx + ".norm2", p, seeds())
+        c = Ctx(x=x, qkv=qkv, o=o, lse=lse, ad=ad, ln1=ln1, x1=x1, h=h, ln2=ln2, p=p)
+        return x2, c
+
+    def _enc_layer_bwd(self, c, dx2, B, Lx, lens, i, G):
+        D, M = self.D, B * Lx
+        pfx = "transformerEncoder.layers.%d" % i
+        a = pfx + ".self_attn"
+        keep_scale = 1.0 / (1.0 - c.p) if c.p > 0 else 1.0
+        ds2, dy2 = self._ln_bwd(dx2, c.ln2, M, pfx + ".norm2", G)
+        dh = self._linear_bwd(dy2, c.h, M, pfx + ".linear2", G, pfx + ".linear2.weight", pfx + ".linear2.bias",
+                              aux=c.h, mask_scale=keep_scale)
+        # dx1 = ds2 + dh W1   (accumulated in place into ds2)
+        self._linear_bwd(dh, c.x1, M, pfx + ".linear1", G, pfx + ".linear1.weight", pfx + ".linear1.bias", dx_out=ds2, accum_dx=True)
+        ds1, dy = self._ln_bwd(ds2, c.ln1, M, pfx + ".norm1", G)
+        # out-projection y = o W_o^T-form: packed key ".o" holds (H*dh, D) = w_o itself, ".o.T" holds (D, H*dh)
+        # weight gradient directly in the parameter layout: d w_o (H*dh, D) = o^T dy
+        self.gemm(c.o, dy, G[a + ".w_o"], D, D, M, D, D, D, layout=L.GEMM_NT_MN, epilogue=L.EPI_ACCUM)
+        dO = self.empty(M, D)
+        self.gemm(dy, self.pk[a + ".o"], dO, M, D, D, D, D, D)
+        dqkv = self.empty(M, 3 * D)
+        delta = self.empty(B * self.H * Lx, dtype=torch.float32)
+        L.attn_bwd(c.ad, c.qkv, c.qkv[:, D:], c.qkv[:, 2 * D:], self.pk[a + ".E"], lens, lens, c.o, c.lse, dO,
+                   dqkv, dqkv[:, D:], dqkv[:, 2 * D:], delta)
+        self._qkv_wgrad(dqkv, c.x, M, [a + ".w_q", a + ".w_k", a + ".w_v"], G)
+        self.gemm(dqkv, self.pk[a + ".qkv.T"], ds1, M, D, 3 * D, 3 * D, 3 * D, D, epilogue=L.EPI_ACCUM)
+        return ds1
+
+    def _qkv_wgrad(self, dproj, x, M, names, G):
+        """dW packed (len*H*dh, D) = dproj^T x, then accumulate into the per-head (H, D, dh) parameter gradients."""
+        D, H, dh = self.D, self.H, self.dh
+        n = len(names)
+        dW = self.empty(n * D, D, dtype=torch.float32)
+        self.gemm(dproj, x, dW, n * D, D, M, dproj.stride(0), x.stride(0), D, layout=L.GEMM_NT_MN, a_cols=n * D, b_cols=D)
+        for s, name in enumerate(names):
+            L.permute3_cast(dW[s * D:], G[name], (H, D, dh), (dh * D, 1, D), (D * dh, dh, 1), accumulate=True)
+
+    # ------------------------------------------------------------------------------------------------ decoder
+    def _dec_layer_fwd(self, t, mem, B, S, Lm, tgt_lens, mem_lens, i, training, seeds):
+        D, M, Mm = self.D, B * S, B * Lm
+        p = self.cfg["dropout"] if training else 0.0
+        pfx = "transformerDecoder.layers.%d" % i
+        a, m = pfx + ".self_attn", pfx + ".multihead_attn"
+        qkv = self._linear_fwd(t, M, a + ".qkv")
+        o1 = self.empty(M, D)
+        lse1 = self.empty(2 * B * self.H * S, dtype=torch.float32)
+        ad1 = self._attn_desc(B, S, S, 3 * D, 3 * D, 3 * D, True, True, 0, p, seeds())
+        L.attn_fwd(ad1, qkv, qkv[:, D:], qkv[:, 2 * D:], None, tgt_lens, tgt_lens, o1, lse1)
+        y = self._linear_fwd(o1, M, a + ".o.T")
+        t1, ln1 = self._ln_fwd(t, y, M, pfx + ".norm1", p, seeds())
+        q = self._linear_fwd(t1, M, m + ".q")
+        kv = self._linear_fwd(mem, Mm, m + ".kv")
+        o2 = self.empty(M, D)
+        lse2 = self.empty(2 * B * self.H * S, dtype=torch.float32)
+        ad2 = self._attn_desc(B, S, Lm, D, 2 * D, 2 * D, False, False, 0, p, seeds())
+        L.attn_fwd(ad2, q, kv, kv[:, D:], None, None, mem_lens, o2, lse2)
+        y2 = self._linear_fwd(o2, M, m + ".o.T")
+        t2, ln2 = self._ln_fwd(t1, y2, M, pfx + ".norm2", p, seeds())
+        h = self._linear_fwd(t2, M, pfx + ".linear1", bias=self.P[pfx + ".linear1.bias"], relu=True, drop_p=p, seed=seeds())
+        y3 = self._linear_fwd(h, M, pfx + ".linear2", bias=self.P[pfx + ".linear2.bias"])
+        t3, ln3 = self._ln_fwd(t2, y3, M, pfx + ".norm3", p, seeds())
+        c = Ctx(t=t, qkv=qkv, o1=o1, lse1=lse1, ad1=ad1, ln1=ln1, t1=t1, q=q, kv=kv, o2=o2, lse2=lse2, ad2=ad2, ln2=ln2, t2=t2,
+                h=h, ln3=ln3, p=p)
+        return t3, c
+
+    def _dec_layer_bwd(self, c, dt3, mem, dmem, B, S, Lm, tgt_lens, mem_lens, i, G):
+        D, M, Mm = self.D, B * S, B * Lm
+        pfx = "transformerDecoder.layers.%d" % i
+        a, m = pfx + ".self_attn", pfx + ".multihead_attn"
+        keep_scale = 1.0 / (1.0 - c.p) if c.p > 0 else 1.0
+        ds3, dy3 = self._ln_bwd(dt3, c.ln3, M, pfx + ".norm3", G)
+        dh = self._linear_bwd(dy3, c.h, M, pfx + ".linear2", G, pfx + ".linear2.weight", pfx + ".linear2.bias", aux=c.h,
+                              mask_scale=keep_scale)
+        self._linear_bwd(dh, c.t2, M, pfx + ".linear1", G, pfx + ".linear1.weight", pfx + ".linear1.bias", dx_out=ds3, accum_dx=True)
+        ds2, dy2 = self._ln_bwd(ds3, c.ln2, M, pfx + ".norm2", G)
+        # cross attention
+        self.gemm(c.o2, dy2, G[m + ".w_o"], D, D, M, D, D, D, layout=L.GEMM_NT_MN, epilogue=L.EPI_ACCUM)
+        dO2 = self.empty(M, D)
+        self.gemm(dy2, self.pk[m + ".o"], dO2, M, D, D, D, D, D)
+        dq = self.empty(M, D)
+        dkv = self.empty(Mm, 2 * D)
+        delta = self.empty(B * self.H * S, dtype=torch.float32)
+        L.attn_bwd(c.ad2, c.q, c.kv, c.kv[:, D:], None, None, mem_lens, c.o2, c.lse2, dO2, dq, dkv, dkv[:, D:], delta)
+        self._qkv_wgrad(dq, c.t1, M, [m + ".w_q"], G)
+        self.gemm(dq, self.pk[m + ".q.T"], ds2, M, D, D, D, D, D, epilogue=L.EPI_ACCUM)
+        self._qkv_wgrad(dkv, mem, Mm, [m + ".w_k", m + ".w_v"], G)
+        self.gemm(dkv, self.pk[m + ".kv.T"], dmem, Mm, D, 2 * D, 2 * D, 2 * D, D, epilogue=L.EPI_ACCUM)
+        ds1, dy1 = self._ln_bwd(ds2, c.ln1, M, pfx + ".norm1", G)
+        # self attention
+        self.gemm(c.o1, dy1, G[a + ".w_o"], D, D, M, D, D, D, layout=L.GEMM_NT_MN, epilogue=L.EPI_ACCUM)
+        dO1 = self.empty(M, D)
+        self.gemm(dy1, self.pk[a + ".o"], dO1, M, D, D, D, D, D)
+        dqkv = self.empty(M, 3 * D)
+        L.attn_bwd(c.ad1, c.qkv, c.qkv[:, D:], c.qkv[:, 2 * D:], None, tgt_lens, tgt_lens, c.o1, c.lse1, dO1,
+                   dqkv, dqkv[:, D:], dqkv[:, 2 * D:], delta)
+        self._qkv_wgrad(dqkv, c.t, M, [a + ".w_q", a + ".w_k", a + ".w_v"], G)
+        self.gemm(dqkv, self.pk[a + ".qkv.T"], ds1, M, D, 3 * D, 3 * D, 3 * D, D, epilogue=L.EPI_ACCUM)
+        return ds1
+
+    # ------------------------------------------------------------------------------------------------ whole model
+    class _Seeds:
+        def __init__(self, base):
+            self.base, self.n = int(base), 0
+
+        def __call__(self):
+            self.n += 1
+            return (self.base * 1000003 + self.n * 7919) & 0xFFFFFFFFFFFFFFFF
+
+    def encode(self, x_raw, lengths, training, seed=0, save=True):
+        """x_raw: (n, 1600, 8) fp32 CUDA (already shifted); lengths: list[int] frames per utterance.
+        Returns (x_enc (B*Lmax, D), ctx)."""
+        assert x_raw.dtype == torch.float32 and x_raw.is_cuda and x_raw.is_contiguous()
+        n, T0, Cc = x_raw.shape
+        assert Cc == 8 and T0 % 8 == 0
+        seeds = Engine._Seeds(seed)
+        ctx = Ctx(n=n, blocks=[], layers=[], training=training)
+        a, T = x_raw, T0
+        for i in range(3):
+            a, c = self._resblock_fwd(i, a, n, T, training, last=(i == 2))
+            T //= 2
+            ctx.blocks.append(c)
+        rows3 = n * T
+        a3 = a.view(rows3, self.D)
+        xlin = self._linear_fwd(a3, rows3, "w_raw_in", bias=self.P["w_raw_in.bias"])
+        B, Lmax, total = len(lengths), max(lengths), sum(lengths)
+        assert total <= rows3, "lengths exceed the available frames (data_utils.py:182)"
+        lens_dev = torch.tensor(lengths, dtype=torch.int32).to(self.dev, non_blocking=True)
+        ragged = not (all(l == Lmax for l in lengths) and total == rows3)
+        if ragged:
+            offs = [0]
+            for l in lengths[:-1]:
+                offs.append(offs[-1] + l)
+            offs_dev = torch.tensor(offs, dtype=torch.int64).to(self.dev, non_blocking=True)
+            x = self.empty(B * Lmax, self.D)
+            L.gather_rows_pad(self.dt, xlin, x, offs_dev, lens_dev, B, Lmax, self.D, float(PAD))
+            ctx.offs = offs_dev
+        else:
+            x = xlin
+        ctx.update(a3=a3, rows3=rows3, B=B, Lmax=Lmax, lens=lens_dev, ragged=ragged, lengths=list(lengths))
+        for i in range(self.n_enc):
+            x, c = self._enc_layer_fwd(x, B, Lmax, lens_dev, i, training, seeds)
+            ctx.layers.append(c)
+        ctx.x_enc = x
+        ctx.seeds = seeds
+        return x, ctx
+
+    def enc_head(self, x_enc, M):
+        """w_aux: fp32 logits in a pitch-64 matrix (columns >= 44 undefined)."""
+        return self._linear_fwd(x_enc, M, "w_aux", bias=self.P["w_aux.bias"], out_dtype=torch.float32, ldc=self.LDH)
+
+    def decode(self, y, tgt_lens, mem, mem_lens, B, Lm, training, seeds, ctx=None):
+        """y: (B, S) int64 CUDA; returns x_dec (B*S, D)."""
+        S = y.shape[1]
+        p_pos = self.cfg["dropout_pos"] if training else 0.0
+        t = self.empty(B * S, self.D)
+        s_emb = seeds()
+        L.embed_posenc_fwd(self.dt, y, self.P["embedding_tgt.weight"], self.Bf["pos_decoder.pe"], t, B, S, self.D, p_pos, s_emb)
+        layers = []
+        for i in range(self.n_dec):
+            t, c = self._dec_layer_fwd(t, mem, B, S, Lm, tgt_lens, mem_lens, i, training, seeds)
+            layers.append(c)
+        if ctx is not None:
+            ctx.update(y=y, S=S, tgt_lens=tgt_lens, dec_layers=layers, p_pos=p_pos, s_emb=s_emb, x_dec=t)
+        return t
+
+    def dec_head(self, x_dec, M):
+        return self._linear_fwd(x_dec, M, "w_out", bias=self.P["w_out.bias"], out_dtype=torch.float32, ldc=self.LDH)
+
+    def forward(self, x_raw, lengths, y=None, tgt_lens=None, training=True, seed=0):
+        """Model.forward_training (architecture.py:101-139).  Returns (enc_logits (B*L, 64) fp32, dec_logits (B*S, 64) fp32 | None, ctx)."""
+        x_enc, ctx = self.encode(x_raw, lengths, training, seed)
+        B, Lmax = ctx.B, ctx.Lmax
+        ctx.enc_logits = self.enc_head(x_enc, B * Lmax)
+        ctx.dec_logits = None
+        if y is not None and self.n_dec >= 0 and y.numel() > 0:
+            if tgt_lens is None:
+                tgt_lens = (y != PAD).sum(1).to(torch.int32)
+            x_dec = self.decode(y, tgt_lens, x_enc, ctx.lens, B, Lmax, training, ctx.seeds, ctx)
+            ctx.dec_logits = self.dec_head(x_dec, B * y.shape[1])
+        return ctx.enc_logits, ctx.dec_logits, ctx
+
+    def losses(self, ctx, ctc_targets, ctc_tgt_lens, dec_target, n_valid, alpha, eps_ls=0.1, want_grad=True):
+        """recognition_model.py:93-107 on the saved logits.  Writes d(loss)/d(logits) (compute dtype, pitch 64) into ctx and
+        returns a float32[3] device tensor (loss, loss_dec, loss_enc)."""
+        B, Lx = ctx.B, ctx.Lmax
+        out = torch.zeros(3, dtype=torch.float32, device=self.dev)
+        Smax = ctc_targets.shape[1]
+        lp_ws = self.empty(B * Lx * self.n_out_enc, dtype=torch.float32)
+        a_ws = self.empty(B * Lx * (2 * Smax + 1), dtype=torch.float32)
+        nll = self.empty(B, dtype=torch.float32)
+        has_dec = ctx.dec_logits is not None
+        c_enc = alpha if has_dec else 1.0
+        ctx.d_enc_logits = self.empty(B * Lx, self.LDH)
+        L.ctc_loss(L.F32, self.dt, B, Lx, self.n_out_enc, self.n_out_enc - 1, ctx.enc_logits, self.LDH, ctc_targets, Smax, ctx.lens,
+                   ctc_tgt_lens, c_enc, lp_ws, a_ws, nll, ctx.d_enc_logits, self.LDH, out[2:])
+        if has_dec:
+            S = ctx.S
+            rows = B * S
+            ws = self.empty(2 * rows, dtype=torch.float32)
+            ctx.d_dec_logits = self.empty(rows, self.LDH)
+            L.ce_sumexp_loss(L.F32, self.dt, rows, S, self.n_out_dec, ctx.dec_logits, self.LDH, dec_target, PAD, eps_ls, n_valid,
+                             1.0 - alpha, ws, ctx.d_dec_logits, self.LDH, out[1:])
+        ctx.loss_mix = (alpha, has_dec)
+        return out
+
+    def backward(self, ctx, G, d_enc_logits=None, d_dec_logits=None):
+        """Accumulates every parameter gradient into G[name] (fp32, reference layout)."""
+        B, Lx, D = ctx.B, ctx.Lmax, self.D
+        M = B * Lx
+        d_enc_logits = d_enc_logits if d_enc_logits is not None else ctx.d_enc_logits
+        d_dec_logits = d_dec_logits if d_dec_logits is not None else ctx.get("d_dec_logits")
+        # CTC head
+        dx = self._linear_bwd(d_enc_logits, ctx.x_enc, M, "w_aux", G, "w_aux.weight", "w_aux.bias")
+        if ctx.dec_logits is not None and d_dec_logits is not None:
+            S = ctx.S
+            Md = B * S
+            dt_ = self._linear_bwd(d_dec_logits, ctx.x_dec, Md, "w_out", G, "w_out.weight", "w_out.bias")
+            for i in reversed(range(self.n_dec)):
+                dt_ = self._dec_layer_bwd(ctx.dec_layers[i], dt_, ctx.x_enc, dx, B, S, Lx, ctx.tgt_lens, ctx.lens, i, G)
+            L.embed_bwd(self.dt, ctx.y, dt_, G["embedding_tgt.weight"], B, S, D, PAD, ctx.p_pos, ctx.s_emb)
+        for i in reversed(range(self.n_enc)):
+            dx = self._enc_layer_bwd(ctx.layers[i], dx, B, Lx, ctx.lens, i, G)
+        if ctx.ragged:
+            dxlin = self.zeros(ctx.rows3, D)
+            L.scatter_rows(self.dt, dx, dxlin, ctx.offs, ctx.lens, B, Lx, D)
+        else:
+            dxlin = dx
+        da = self._linear_bwd(dxlin, ctx.a3, ctx.rows3, "w_raw_in", G, "w_raw_in.weight", "w_raw_in.bias")
+        for c in reversed(ctx.blocks):
+            da = self._resblock_bwd(c, da, G)

@@ -93,3 +93,136 @@ def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, layout=GEMM_TN, bias=None, aux=None
     d.remap_P, d.remap_T, d.remap_j0 = remap
     d.force_simt = 1 if force_simt else 0
     check(lib().sst_gemm(C.byref(d), ptr(A), ptr(B), ptr(Cout), ptr(bias), ptr(aux), stream()), "sst_gemm")
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("Lq", C.c_int32), ("Lk", C.c_int32),
+                ("dh", C.c_int32), ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64), ("ldo", C.c_int64),
+                ("causal", C.c_int32), ("mask_q_rows", C.c_int32), ("rel_dist", C.c_int32), ("scale", C.c_float),
+                ("drop_p", C.c_float), ("seed", C.c_uint64), ("force_simt", C.c_int32)]
+
+
+def _i64(v):
+    return C.c_int64(int(v))
+
+
+def _f(v):
+    return C.c_float(float(v))
+
+
+def _u64(v):
+    return C.c_uint64(int(v) & 0xFFFFFFFFFFFFFFFF)
+
+
+def attn_desc(dtype, B, H, Lq, Lk, dh, ldq, ldk, ldv, ldo, causal, mask_q_rows, rel_dist, scale, drop_p, seed,
+              force_simt=False):
+    d = AttnDesc()
+    d.dtype, d.B, d.H, d.Lq, d.Lk, d.dh = dtype, B, H, Lq, Lk, dh
+    d.ldq, d.ldk, d.ldv, d.ldo = ldq, ldk, ldv, ldo
+    d.causal, d.mask_q_rows, d.rel_dist = int(causal), int(mask_q_rows), int(rel_dist)
+    d.scale, d.drop_p, d.seed, d.force_simt = scale, drop_p, seed & 0xFFFFFFFFFFFFFFFF, int(force_simt)
+    return d
+
+
+def attn_fwd(d, q, k, v, E, q_lens, k_lens, o, lse):
+    check(lib().sst_attn_fwd(C.byref(d), ptr(q), ptr(k), ptr(v), ptr(E), ptr(q_lens), ptr(k_lens), ptr(o), ptr(lse),
+                             stream()), "sst_attn_fwd")
+
+
+def attn_bwd(d, q, k, v, E, q_lens, k_lens, o, lse, dO, dq, dk, dv, delta):
+    check(lib().sst_attn_bwd(C.byref(d), ptr(q), ptr(k), ptr(v), ptr(E), ptr(q_lens), ptr(k_lens), ptr(o), ptr(lse),
+                             ptr(dO), ptr(dq), ptr(dk), ptr(dv), ptr(delta), stream()), "sst_attn_bwd")
+
+
+def layernorm_fwd(dtype, rows, D, x, r, drop_p, seed, gamma, beta, y, s_out, mean, rstd, eps=1e-5):
+    check(lib().sst_layernorm_fwd(dtype, _i64(rows), D, ptr(x), ptr(r), _f(drop_p), _u64(seed), ptr(gamma), ptr(beta),
+                                  ptr(y), ptr(s_out), ptr(mean), ptr(rstd), _f(eps), stream()), "sst_layernorm_fwd")
+
+
+def layernorm_bwd(dtype, rows, D, dy, s, mean, rstd, gamma, ds, dr, drop_p, seed, dgamma, dbeta):
+    check(lib().sst_layernorm_bwd(dtype, _i64(rows), D, ptr(dy), ptr(s), ptr(mean), ptr(rstd), ptr(gamma), ptr(ds),
+                                  ptr(dr), _f(drop_p), _u64(seed), ptr(dgamma), ptr(dbeta), stream()), "sst_layernorm_bwd")
+
+
+def colstats(dtype, x, rows, Cc, ld, stats):
+    check(lib().sst_colstats(dtype, ptr(x), _i64(rows), Cc, _i64(ld), ptr(stats), stream()), "sst_colstats")
+
+
+def colsum_accum(dtype, x, rows, Cc, ld, out):
+    check(lib().sst_colsum_accum(dtype, ptr(x), _i64(rows), Cc, _i64(ld), ptr(out), stream()), "sst_colsum_accum")
+
+
+def bn_finalize(stats, count, Cc, eps, momentum, mean, invstd, running_mean, running_var, training):
+    check(lib().sst_bn_finalize(ptr(stats), _i64(count), Cc, _f(eps), _f(momentum), ptr(mean), ptr(invstd),
+                                ptr(running_mean), ptr(running_var), int(training), stream()), "sst_bn_finalize")
+
+
+def bn_apply(dtype, n_chunks, T, Cc, xa, lda, sa, xb, ldb, sb, relu, out, lead, trail):
+    """sa / sb = (mean, invstd, gamma, beta) tuples; xb / sb may be None."""
+    nb = (None, None, None, None) if sb is None else sb
+    check(lib().sst_bn_apply(dtype, _i64(n_chunks), T, Cc, ptr(xa), _i64(lda), ptr(sa[0]), ptr(sa[1]), ptr(sa[2]), ptr(sa[3]),
+                             ptr(xb), _i64(ldb), ptr(nb[0]), ptr(nb[1]), ptr(nb[2]), ptr(nb[3]), int(relu), ptr(out),
+                             lead, trail, stream()), "sst_bn_apply")
+
+
+def bn_bwd(dtype, n_chunks, T, Cc, dout, ld_dout, y, y_lead, y_trail, relu,
+           xa, lda, mean_a, invstd_a, gamma_a, dxa, ld_dxa, lead_a, trail_a, dgamma_a, dbeta_a,
+           xb, ldb, mean_b, invstd_b, gamma_b, dxb, ld_dxb, lead_b, trail_b, dgamma_b, dbeta_b, red):
+    check(lib().sst_bn_bwd(dtype, _i64(n_chunks), T, Cc, ptr(dout), _i64(ld_dout), ptr(y), y_lead, y_trail, int(relu),
+                           ptr(xa), _i64(lda), ptr(mean_a), ptr(invstd_a), ptr(gamma_a), ptr(dxa), _i64(ld_dxa), lead_a, trail_a,
+                           ptr(dgamma_a), ptr(dbeta_a),
+                           ptr(xb), _i64(ldb), ptr(mean_b), ptr(invstd_b), ptr(gamma_b), ptr(dxb), _i64(ld_dxb), lead_b, trail_b,
+                           ptr(dgamma_b), ptr(dbeta_b), ptr(red), stream()), "sst_bn_bwd")
+
+
+def ctc_loss(logits_dtype, grad_dtype, B, L, Cc, blank, logits, ld, targets, Smax, in_lens, tgt_lens, gcoef, lp_ws, alpha_ws,
+             nll, grad, ldg, loss_out):
+    check(lib().sst_ctc_loss(logits_dtype, grad_dtype, B, L, Cc, blank, ptr(logits), _i64(ld), ptr(targets), Smax, ptr(in_lens),
+                             ptr(tgt_lens), _f(gcoef), ptr(lp_ws), ptr(alpha_ws), ptr(nll), ptr(grad), _i64(ldg), ptr(loss_out),
+                             stream()), "sst_ctc_loss")
+
+
+def ce_sumexp_loss(logits_dtype, grad_dtype, rows, S, Cc, logits, ld, target, ignore, eps, n_valid, gcoef, row_ws, grad, ldg,
+                   loss_out):
+    check(lib().sst_ce_sumexp_loss(logits_dtype, grad_dtype, _i64(rows), S, Cc, ptr(logits), _i64(ld), ptr(target), ignore,
+                                   _f(eps), _i64(n_valid), _f(gcoef), ptr(row_ws), ptr(grad), _i64(ldg), ptr(loss_out),
+                                   stream()), "sst_ce_sumexp_loss")
+
+
+def shift_left(x, n_chunks, T, Cc, r):
+    check(lib().sst_shift_left(ptr(x), _i64(n_chunks), T, Cc, r, stream()), "sst_shift_left")
+
+
+def im2col_first(out_dtype, x, col, n_chunks, Tin):
+    check(lib().sst_im2col_first(out_dtype, ptr(x), ptr(col), _i64(n_chunks), Tin, stream()), "sst_im2col_first")
+
+
+def gather_rows_pad(dtype, inp, out, offs, lens, B, Lmax, D, fill):
+    check(lib().sst_gather_rows_pad(dtype, ptr(inp), ptr(out), ptr(offs), ptr(lens), B, Lmax, D, _f(fill), stream()),
+          "sst_gather_rows_pad")
+
+
+def scatter_rows(dtype, dout, din, offs, lens, B, Lmax, D):
+    check(lib().sst_scatter_rows(dtype, ptr(dout), ptr(din), ptr(offs), ptr(lens), B, Lmax, D, stream()), "sst_scatter_rows")
+
+
+def embed_posenc_fwd(out_dtype, y, W, pe, out, B, S, D, drop_p, seed):
+    check(lib().sst_embed_posenc_fwd(out_dtype, ptr(y), ptr(W), ptr(pe), ptr(out), B, S, D, _f(drop_p), _u64(seed), stream()),
+          "sst_embed_posenc_fwd")
+
+
+def embed_bwd(dtype, y, dout, dW, B, S, D, pad_idx, drop_p, seed):
+    check(lib().sst_embed_bwd(dtype, ptr(y), ptr(dout), ptr(dW), B, S, D, pad_idx, _f(drop_p), _u64(seed), stream()),
+          "sst_embed_bwd")
+
+
+def permute3_cast(inp, out, dims, in_strides, out_strides, accumulate=False):
+    check(lib().sst_permute3_cast(dt(inp), dt(out), ptr(inp), ptr(out), _i64(dims[0]), _i64(dims[1]), _i64(dims[2]),
+                                  _i64(in_strides[0]), _i64(in_strides[1]), _i64(in_strides[2]),
+                                  _i64(out_strides[0]), _i64(out_strides[1]), _i64(out_strides[2]), int(accumulate), stream()),
+          "sst_permute3_cast")
+
+
+def adamw(p, g, m, v, n, lr, beta1, beta2, eps, wd, step):
+    check(lib().sst_adamw(ptr(p), ptr(g), ptr(m), ptr(v), _i64(n), _f(lr), _f(beta1), _f(beta2), _f(eps), _f(wd), _i64(step),
+                          stream()), "sst_adamw")

@@ -90,6 +90,116 @@ typedef struct SstGemmDesc {
 int sst_gemm(const SstGemmDesc* d, const void* A, const void* B, void* C, const void* bias /*fp32[N]*/,
              const void* aux, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Normalisation (HBM-bound, 128-bit vectorised; all statistics fp32/fp64).
+ *  sst_layernorm_fwd/bwd : y = LN(x + dropout(r)) * gamma + beta, eps 1e-5, post-LN residual form of
+ *      transformer.py:59-60,62-63,124-133.  `s_out` receives the pre-norm sum (may alias r); backward takes it
+ *      back as `s`, returns ds (gradient of both x and the undropped r) and, when drop_p > 0, dr = ds*keep/(1-p).
+ *      dgamma/dbeta are ACCUMULATED (+=) in fp32.
+ *  sst_colstats / sst_bn_finalize / sst_bn_apply / sst_bn_bwd : training-mode nn.BatchNorm1d of ResBlock
+ *      (architecture.py:27,29,33,40-48) over channels-last conv outputs (rows = chunk*T + t, pitch ld):
+ *      per-channel sum / sum of squares in double, mean / invstd (+ running-stat update, momentum 0.1, unbiased
+ *      variance), then out = relu?(bnA(xa) [+ bnB(xb)]) written into the time-padded layout
+ *      (chunk, lead + t, C) with zero halo rows that the next implicit-GEMM convolution reads.
+ * ---------------------------------------------------------------------------------------------------------- */
+int sst_layernorm_fwd(int dtype, int64_t rows, int D, const void* x, const void* r, float drop_p, uint64_t seed,
+                      const float* gamma, const float* beta, void* y, void* s_out, float* mean, float* rstd, float eps,
+                      void* stream);
+int sst_layernorm_bwd(int dtype, int64_t rows, int D, const void* dy, const void* s, const float* mean, const float* rstd,
+                      const float* gamma, void* ds, void* dr, float drop_p, uint64_t seed, float* dgamma, float* dbeta,
+                      void* stream);
+int sst_colstats(int dtype, const void* x, int64_t rows, int C, int64_t ld, double* stats /*[2*C]*/, void* stream);
+/* out[c] += sum_rows x[r, c]  (bias gradients; fp32 accumulate) */
+int sst_colsum_accum(int dtype, const void* x, int64_t rows, int C, int64_t ld, float* out, void* stream);
+int sst_bn_finalize(const double* stats, int64_t count, int C, float eps, float momentum, float* mean, float* invstd,
+                    float* running_mean, float* running_var, int training, void* stream);
+int sst_bn_apply(int dtype, int64_t n_chunks, int T, int C, const void* xa, int64_t lda, const float* mean_a,
+                 const float* invstd_a, const float* gamma_a, const float* beta_a, const void* xb, int64_t ldb,
+                 const float* mean_b, const float* invstd_b, const float* gamma_b, const float* beta_b, int relu, void* out,
+                 int lead, int trail, void* stream);
+int sst_bn_bwd(int dtype, int64_t n_chunks, int T, int C, const void* dout, int64_t ld_dout, const void* y, int y_lead,
+               int y_trail, int relu, const void* xa, int64_t lda, const float* mean_a, const float* invstd_a,
+               const float* gamma_a, void* dxa, int64_t ld_dxa, int lead_a, int trail_a, float* dgamma_a, float* dbeta_a,
+               const void* xb, int64_t ldb, const float* mean_b, const float* invstd_b, const float* gamma_b, void* dxb,
+               int64_t ld_dxb, int lead_b, int trail_b, float* dgamma_b, float* dbeta_b, double* red /*[3*C]*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Attention.  Replaces MultiHeadAttention.forward between the projections (transformer.py:177-208) together
+ * with LearnedRelativePositionalEmbedding (transformer.py:260-403): logits = mask(q.k * scale) + relpos(q),
+ * softmax, dropout on the probabilities, probs.v -- without materialising (B,H,L,L).
+ *   q/k/v/o are token matrices: row = b*L + t (pitch ld*), head h occupies columns [h*dh, (h+1)*dh).
+ *   masks are SET to -1e8 exactly as masked_fill does: causal (j > i), keys j >= k_lens[b], and, with mask_q_rows,
+ *   whole rows i >= q_lens[b]; fully masked rows therefore give the reference's uniform softmax.
+ *   rel_dist R > 0 adds bias[i][j] = q_i . E[h][j-i+R-1] for |j-i| < R and -1e8 otherwise; E is
+ *   (H, 2R-1, dh) in the compute dtype and receives no gradient (Q2).
+ *   lse is float[2*B*H*Lq]: row maximum at [(b*H+h)*Lq + i] and log(sum exp(logit - max)) at [B*H*Lq + ...] (kept apart
+ *   because a fully masked row has max = -1e8, where max + log(sum) would round the sum away); saved for backward.
+ *   dtype SST_F32: CUDA-core kernels; SST_BF16: tensor-core flash kernels.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct SstAttnDesc {
+  int32_t dtype;
+  int32_t B, H, Lq, Lk, dh;
+  int64_t ldq, ldk, ldv, ldo;
+  int32_t causal;
+  int32_t mask_q_rows;
+  int32_t rel_dist;
+  float scale;
+  float drop_p;
+  uint64_t seed;
+  int32_t force_simt;
+} SstAttnDesc;
+
+int sst_attn_fwd(const SstAttnDesc* d, const void* q, const void* k, const void* v, const void* E, const int32_t* q_lens,
+                 const int32_t* k_lens, void* o, float* lse, void* stream);
+/* dq/dk/dv use the pitches of q/k/v; delta is a caller-provided float[B*H*Lq] scratch. */
+int sst_attn_bwd(const SstAttnDesc* d, const void* q, const void* k, const void* v, const void* E, const int32_t* q_lens,
+                 const int32_t* k_lens, const void* o, const float* lse, const void* dO, void* dq, void* dk, void* dv,
+                 float* delta, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Losses (recognition_model.py:93-107).
+ *  sst_ctc_loss : log_softmax over C classes + CTC (blank = `blank`, reduction 'mean' = mean_b nll_b / max(len_b,1),
+ *      zero_infinity False).  One warp per utterance runs the alpha and beta recursions in log space; the gradient is
+ *      written directly w.r.t. the raw logits (softmax - occupancy), scaled by gcoef, zero for t >= in_lens[b].
+ *      Workspaces: lp_ws float[B*L*C], alpha_ws float[B*L*(2*Smax+1)], nll float[B].  targets: int64 (B, Smax).
+ *  sst_ce_sumexp_loss : LabelSmoothingLoss.py:13-15 -- (1-eps)*CE(ignore_index, mean over kept) + eps/S*sum(exp(logits)),
+ *      the sum running over every row including ignored ones; S = target length; gradient scaled by gcoef.
+ *      row_ws float[2*rows].
+ * ---------------------------------------------------------------------------------------------------------- */
+int sst_ctc_loss(int logits_dtype, int grad_dtype, int B, int L, int C, int blank, const void* logits, int64_t ld,
+                 const int64_t* targets, int Smax, const int32_t* in_lens, const int32_t* tgt_lens, float gcoef, float* lp_ws,
+                 float* alpha_ws, float* nll, void* grad, int64_t ldg, float* loss_out, void* stream);
+int sst_ce_sumexp_loss(int logits_dtype, int grad_dtype, int64_t rows, int S, int C, const void* logits, int64_t ld,
+                       const int64_t* target, int ignore, float eps, int64_t n_valid, float gcoef, float* row_ws, void* grad,
+                       int64_t ldg, float* loss_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Data movement and optimiser.
+ *  sst_shift_left       : x[:, :-r] = x[:, r:]; x[:, -r:] = 0 per chunk, in place        (architecture.py:104-108)
+ *  sst_im2col_first     : (n, Tin, 8) fp32 EMG -> (n*Tin/2, 32) patches [3 taps x 8 | centre tap x 8] so that the first
+ *                         ResBlock's conv1 (k3,s2) and residual_path (k1,s2) are one GEMM (architecture.py:26,32,55)
+ *  sst_gather_rows_pad  : decollate_tensor + pad_sequence(padding_value=fill)             (data_utils.py:176-185,
+ *                         architecture.py:116-117);  sst_scatter_rows is its adjoint (din pre-zeroed)
+ *  sst_embed_posenc_fwd : embedding_tgt(y) + pe[b]/D, dropout                             (architecture.py:126-127, Q10)
+ *  sst_embed_bwd        : dW[y] += dout, skipping padding_idx rows (fp32 atomics)
+ *  sst_permute3_cast    : out[i*o0+j*o1+k*o2] (+)= in[i*s0+j*s1+k*s2] with dtype conversion (weight packing / grad unpacking)
+ *  sst_adamw            : torch.optim.AdamW step over a flat fp32 buffer, `step` 1-based  (recognition_model.py:293)
+ * ---------------------------------------------------------------------------------------------------------- */
+int sst_shift_left(float* x, int64_t n_chunks, int T, int Cc, int r, void* stream);
+int sst_im2col_first(int out_dtype, const float* x, void* col, int64_t n_chunks, int Tin, void* stream);
+int sst_gather_rows_pad(int dtype, const void* in, void* out, const int64_t* offs, const int32_t* lens, int B, int Lmax, int D,
+                        float fill, void* stream);
+int sst_scatter_rows(int dtype, const void* dout, void* din, const int64_t* offs, const int32_t* lens, int B, int Lmax, int D,
+                     void* stream);
+int sst_embed_posenc_fwd(int out_dtype, const int64_t* y, const float* W, const float* pe, void* out, int B, int S, int D,
+                         float drop_p, uint64_t seed, void* stream);
+int sst_embed_bwd(int dtype, const int64_t* y, const void* dout, float* dW, int B, int S, int D, int pad_idx, float drop_p,
+                  uint64_t seed, void* stream);
+int sst_permute3_cast(int in_dtype, int out_dtype, const void* in, void* out, int64_t d0, int64_t d1, int64_t d2, int64_t s0,
+                      int64_t s1, int64_t s2, int64_t o0, int64_t o1, int64_t o2, int accumulate, void* stream);
+int sst_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, float wd,
+              int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,6 +105,19 @@ def run_case(name, case):
         out["gidx/" + pname] = idx.astype(np.int64)
         out["gval/" + pname] = g[idx].astype(np.float32)
         out["gstat/" + pname] = np.array([np.abs(g).max(), np.sqrt((g.astype(np.float64) ** 2).sum())])
+    # exact-arithmetic statement of the same step: the (reference-pinned) oracle evaluated in float64.  The reference's own
+    # fp32 rounding error against it is what bounds any fp32 re-implementation on ill-conditioned tensors (BatchNorm /
+    # LayerNorm backward cancellation), so the fixtures carry both.
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    b64 = dict(batch)
+    b64["raw_emg"] = [x.double() for x in batch["raw_emg"]]
+    r64, g64, _ = O.loss_and_grads(sd64, cfg, b64, True, 0)
+    for pname in names:
+        g = g64[pname].reshape(-1).numpy()
+        out["gtruth/" + pname] = g[out["gidx/" + pname]]
+        out["gtruthstat/" + pname] = np.array([np.abs(g).max()])
+    out["out_enc_truth"] = r64["out_enc"].numpy().astype(np.float32)
+    out["loss_truth"] = np.float64(r64["loss"].item())
     none_grad = [n for n, p in model.named_parameters() if p.grad is None]
     msd = model.state_dict()
     for k in msd:
