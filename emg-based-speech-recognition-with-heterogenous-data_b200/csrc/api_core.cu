@@ -1,5 +1,6 @@
 // extern "C" surface shared by every op: version, error reporting, device check, GEMM dispatch.
 #include <stdarg.h>
+#include <atomic>
 #include "sst_common.cuh"
 
 namespace sst {
@@ -13,7 +14,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int check_launch(const char* what) {
+static std::atomic<long long> g_launches{0};
+
+int check_launch(const char* what, int n_kernels) {
+  g_launches.fetch_add(n_kernels, std::memory_order_relaxed);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -42,6 +46,7 @@ extern "C" {
 
 const char* sst_version(void) { return "sst-b200 0.1 (sm_100a)"; }
 const char* sst_last_error(void) { return sst::g_err; }
+long long sst_launch_count(void) { return sst::g_launches.load(std::memory_order_relaxed); }
 
 int sst_device_check(void) {
   int dev = 0, major = 0;

@@ -281,7 +281,7 @@ int attn_bwd_simt_launch(const SstAttnDesc& d, const void* q, const void* k, con
     attn_bwd_dkv_simt<bf><<<(int)((rows_k + 3) / 4), 128, smem2, st>>>((const bf*)q, (const bf*)k, (const bf*)v, (const bf*)E,
         (const bf*)dO, lse, delta, (bf*)dk, (bf*)dv, p, maxq);
   }
-  return check_launch("attn_bwd_simt");
+  return check_launch("attn_bwd_simt", 2);
 }
 
 }  // namespace sst

@@ -255,7 +255,7 @@ int sst_ctc_loss(int logits_dtype, int grad_dtype, int B, int L, int C, int blan
     ctc_kernel<__nv_bfloat16><<<B, 32, C * sizeof(float), st>>>(lp_ws, (const long*)targets, Smax, in_lens, tgt_lens, L, C, blank, NS,
                                                                 alpha_ws, nll, (__nv_bfloat16*)grad, ldg, gcoef, B);
   ctc_finalize_kernel<<<1, 32, 0, st>>>(nll, tgt_lens, B, loss_out);
-  return check_launch("ctc_loss");
+  return check_launch("ctc_loss", 3);
 }
 
 /* logits (rows, ld) with rows = B*S; loss = (1-eps)*CE(ignore_index, mean over non-ignored) + eps/S * sum(exp(logits)).
@@ -278,7 +278,7 @@ int sst_ce_sumexp_loss(int logits_dtype, int grad_dtype, int64_t rows, int S, in
   else SST_CE_LAUNCH(bf, bf);
 #undef SST_CE_LAUNCH
   ce_finalize_kernel<<<1, 32, 0, st>>>(rce, rse, rows, eps, inv_nv, inv_S, loss_out);
-  return check_launch("ce_sumexp_loss");
+  return check_launch("ce_sumexp_loss", 2);
 }
 
 }  // extern "C"

@@ -543,7 +543,7 @@ int sst_bn_bwd(int dtype, int64_t n_chunks, int T, int C, const void* dout, int6
     bn_bwd_apply_kernel<__nv_bfloat16><<<grid2, 256, 0, st>>>((const __nv_bfloat16*)dout, ld_dout, (const __nv_bfloat16*)y, y_lead,
                                                               y_trail, relu, a, b, has_b, ga, gb, n_chunks, T, C, red);
   }
-  return check_launch("bn_bwd");
+  return check_launch("bn_bwd", 2);
 }
 
 }  // extern "C"

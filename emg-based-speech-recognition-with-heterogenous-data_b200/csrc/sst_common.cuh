@@ -12,7 +12,7 @@ namespace sst {
 
 // ---- error plumbing (thread-local message, negative return codes; include/sst.h) ----------------
 void set_error(const char* fmt, ...);
-int  check_launch(const char* what);          // cudaPeekAtLastError -> SST_E_LAUNCH
+int  check_launch(const char* what, int n_kernels = 1);   // counts launches; cudaPeekAtLastError -> SST_E_LAUNCH
 
 #define SST_REQUIRE(cond, code, ...)                         \
   do { if (!(cond)) { ::sst::set_error(__VA_ARGS__); return (code); } } while (0)

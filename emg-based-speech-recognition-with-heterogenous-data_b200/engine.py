@@ -543,8 +543,10 @@ class Engine:
         ctx.loss_mix = (alpha, has_dec)
         return out
 
-    def backward(self, ctx, G, d_enc_logits=None, d_dec_logits=None):
-        """Accumulates every parameter gradient into G[name] (fp32, reference layout)."""
+    def backward(self, ctx, G, d_enc_logits=None, d_dec_logits=None, on_stage=None):
+        """Accumulates every parameter gradient into G[name] (fp32, reference layout).  `on_stage(label)` is invoked when all
+        gradients of a stage are final ("decoder", "enc<i>", "w_raw_in", "conv") so that the caller can start reducing them."""
+        on_stage = on_stage or (lambda label: None)
         B, Lx, D = ctx.B, ctx.Lmax, self.D
         M = B * Lx
         d_enc_logits = d_enc_logits if d_enc_logits is not None else ctx.d_enc_logits
@@ -558,13 +560,17 @@ class Engine:
             for i in reversed(range(self.n_dec)):
                 dt_ = self._dec_layer_bwd(ctx.dec_layers[i], dt_, ctx.x_enc, dx, B, S, Lx, ctx.tgt_lens, ctx.lens, i, G)
             L.embed_bwd(self.dt, ctx.y, dt_, G["embedding_tgt.weight"], B, S, D, PAD, ctx.p_pos, ctx.s_emb)
+        on_stage("decoder")
         for i in reversed(range(self.n_enc)):
             dx = self._enc_layer_bwd(ctx.layers[i], dx, B, Lx, ctx.lens, i, G)
+            on_stage("enc%d" % i)
         if ctx.ragged:
             dxlin = self.zeros(ctx.rows3, D)
             L.scatter_rows(self.dt, dx, dxlin, ctx.offs, ctx.lens, B, Lx, D)
         else:
             dxlin = dx
         da = self._linear_bwd(dxlin, ctx.a3, ctx.rows3, "w_raw_in", G, "w_raw_in.weight", "w_raw_in.bias")
+        on_stage("w_raw_in")
         for c in reversed(ctx.blocks):
             da = self._resblock_bwd(c, da, G)
+        on_stage("conv")

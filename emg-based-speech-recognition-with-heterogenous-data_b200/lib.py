@@ -39,6 +39,7 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.sst_version.restype = C.c_char_p
         _lib.sst_last_error.restype = C.c_char_p
+        _lib.sst_launch_count.restype = C.c_longlong
     return _lib
 
 
@@ -226,3 +227,7 @@ def permute3_cast(inp, out, dims, in_strides, out_strides, accumulate=False):
 def adamw(p, g, m, v, n, lr, beta1, beta2, eps, wd, step):
     check(lib().sst_adamw(ptr(p), ptr(g), ptr(m), ptr(v), _i64(n), _f(lr), _f(beta1), _f(beta2), _f(eps), _f(wd), _i64(step),
                           stream()), "sst_adamw")
+
+
+def launch_count():
+    return int(lib().sst_launch_count())

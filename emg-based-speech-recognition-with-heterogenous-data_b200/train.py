@@ -1,0 +1,272 @@
+"""Training step of the reference loop (recognition_model.py:57-64, :76-118, :283-293) on the B200 path.
+
+  * `FlatState`   : every trainable parameter re-homed as a view into ONE fp32 buffer laid out in backward-completion
+                    order (heads, decoder N..0, embedding, encoder N..0, w_raw_in, conv 2..0), with matching flat
+                    gradient / Adam-moment buffers.  Parameters that never receive a gradient in the reference
+                    (rel-pos embeddings, emg_projection: SURVEY.md Q2/Q14) stay outside and are skipped by AdamW exactly
+                    as torch.optim.AdamW skips `grad is None`.
+  * `GradSync`    : data parallelism, one process per GPU: the flat gradient buffer is cut into ~25 MB buckets that are
+                    all-reduced (mean) on a side stream as soon as backward has produced them (NCCL over NVLink; gloo on
+                    CPU for the host-logic tests); replaces nn.DataParallel (recognition_model.py:284).
+  * `Trainer.step`: schedule_lr -> combine_fixed_length -> H2D -> forward -> CTC + label-smoothed CE -> backward ->
+                    summed gradient accumulation until `batch_size_grad` chunks -> fused AdamW.  The three `.item()`
+                    syncs of recognition_model.py:108-111 become one async D2H copy of a float[3].
+"""
+import torch
+
+from . import lib as L
+from .data_utils import combine_fixed_length
+
+PAD = 42
+
+
+def backward_order(names, n_enc, n_dec):
+    """Parameter names sorted by the moment their gradient is complete during Engine.backward."""
+    def key(n):
+        if n.startswith("w_aux"):
+            return (0, 0)
+        if n.startswith("w_out"):
+            return (1, 0)
+        if n.startswith("transformerDecoder.layers."):
+            return (2, n_dec - int(n.split(".")[2]))
+        if n.startswith("embedding_tgt"):
+            return (3, 0)
+        if n.startswith("transformerEncoder.layers."):
+            return (4, n_enc - int(n.split(".")[2]))
+        if n.startswith("w_raw_in"):
+            return (5, 0)
+        if n.startswith("conv_blocks."):
+            return (6, 3 - int(n.split(".")[1]))
+        return (7, 0)
+    return sorted(names, key=lambda n: (key(n), n))
+
+
+def stage_of(name, n_enc, n_dec):
+    """Backward stage label after which `name`'s gradient is final (matches Engine.backward's on_stage calls)."""
+    if name.startswith("w_aux") or name.startswith("w_out") or name.startswith("transformerDecoder") or name.startswith("embedding_tgt"):
+        return "decoder"
+    if name.startswith("transformerEncoder.layers."):
+        return "enc%d" % int(name.split(".")[2])
+    if name.startswith("w_raw_in"):
+        return "w_raw_in"
+    return "conv"
+
+
+class FlatState:
+    def __init__(self, model):
+        eng = model.engine()
+        names = [n for n in model._param_names if model._trainable[n]]
+        self.names = backward_order(names, eng.n_enc, eng.n_dec)
+        params = dict(model.named_parameters())
+        sizes = [(params[n].numel() + 3) // 4 * 4 for n in self.names]          # keep every view 16-byte aligned
+        self.offsets, off = {}, 0
+        for n, s in zip(self.names, sizes):
+            self.offsets[n] = off
+            off += s
+        self.numel = off
+        dev = params[self.names[0]].device
+        self.p = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.g = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.G = {}
+        for n in self.names:
+            prm = params[n]
+            o, k = self.offsets[n], prm.numel()
+            view = self.p[o:o + k].view(prm.shape)
+            view.copy_(prm.data)
+            prm.data = view
+            self.G[n] = self.g[o:o + k].view(prm.shape)
+            prm.grad = self.G[n]
+        model._engine = None                      # parameter storage moved: rebuild the engine's views
+        self.step_count = 0
+        # gradient sinks for the never-trained parameters (written by nobody, kept so Engine.backward can index them)
+        self.G_all = dict(self.G)
+        for n in model._param_names:
+            if n not in self.G_all:
+                self.G_all[n] = None
+
+    def zero_grad(self):
+        self.g.zero_()
+
+
+class GradSync:
+    def __init__(self, flat, n_enc, n_dec, bucket_bytes=25 << 20, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.flat = flat
+        self.backend = dist.get_backend(group) if dist.is_initialized() else None
+        # buckets = contiguous ranges of the flat gradient buffer, closed at stage boundaries once they reach bucket_bytes
+        self.buckets = []            # (start, end, stage after which the bucket is complete)
+        start, cur_stage = 0, None
+        per = bucket_bytes // 4
+        for n in flat.names:
+            st = stage_of(n, n_enc, n_dec)
+            off = flat.offsets[n]
+            if cur_stage is not None and st != cur_stage and off - start >= per:
+                self.buckets.append((start, off, cur_stage))
+                start = off
+            cur_stage = st
+        self.buckets.append((start, flat.numel, cur_stage))
+        self.stage_order = ["decoder"] + ["enc%d" % i for i in reversed(range(n_enc))] + ["w_raw_in", "conv"]
+        self.cuda = flat.g.is_cuda
+        self.stream = torch.cuda.Stream() if self.cuda else None
+        self._next = 0
+        self._pending = []
+
+    def begin(self):
+        self._next = 0
+        self._pending = []
+
+    def on_stage(self, stage):
+        """Called by Engine.backward when every gradient up to and including `stage` is final."""
+        if self.world == 1:
+            return
+        done = self.stage_order.index(stage)
+        while self._next < len(self.buckets) and self.stage_order.index(self.buckets[self._next][2]) <= done:
+            s, e, _ = self.buckets[self._next]
+            self._launch(self.flat.g[s:e])
+            self._next += 1
+
+    def _launch(self, t):
+        dist = self.dist
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self.stream.wait_event(ev)
+            with torch.cuda.stream(self.stream):
+                if self.backend == "nccl":
+                    dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+                else:
+                    dist.all_reduce(t, group=self.group)
+                    t.div_(self.world)
+        else:
+            dist.all_reduce(t, group=self.group)
+            t.div_(self.world)
+
+    def finish(self):
+        """All buckets reduced and visible to the compute stream."""
+        if self.world == 1:
+            return
+        self.on_stage("conv")
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.stream)
+
+
+class Trainer:
+    def __init__(self, model, learning_rate=3e-4, learning_rate_warmup=1500, alpha_loss=0.2, batch_size_grad=100,
+                 eps_ls=0.1, weight_decay=0.01, seed=0, distributed=False, bucket_bytes=25 << 20):
+        self.model = model
+        self.lr_target, self.warmup = learning_rate, learning_rate_warmup
+        self.lr = learning_rate
+        self.alpha, self.eps_ls = alpha_loss, eps_ls
+        self.batch_size_grad = batch_size_grad
+        self.wd = weight_decay
+        model.engine()
+        self.flat = FlatState(model)
+        self.eng = model.engine()
+        self.eng.pack()
+        self.sync = GradSync(self.flat, self.eng.n_enc, self.eng.n_dec, bucket_bytes) if distributed else None
+        self.batch_idx = 0
+        self.sum_batch_size = 0
+        self.seed = seed
+        self.dev = self.flat.p.device
+        self._host_loss = torch.zeros(3, dtype=torch.float32).pin_memory() if self.dev.type == "cuda" else torch.zeros(3)
+        self._loss_event = None
+        self.launch_count = 0
+
+    def schedule_lr(self, iteration):
+        """recognition_model.py:57-64."""
+        iteration = iteration + 1
+        if iteration <= self.warmup:
+            self.lr = iteration * self.lr_target / self.warmup
+
+    # ---- host-side batch preparation (recognition_model.py:77,85-87,95-97) ------------------------------------------
+    def prepare(self, example, pin=True):
+        """collate_raw dict -> host tensors (pinned) ready for an async H2D copy."""
+        pad_seq = torch.nn.utils.rnn.pad_sequence
+        X = combine_fixed_length(example['raw_emg'], 200 * 8)
+        target = pad_seq(example['phonemes_int'], batch_first=True, padding_value=PAD)
+        tgt_in = target[:, :-1].contiguous()
+        tgt_out = target[:, 1:].contiguous()
+        nmax = target.shape[1]
+        ctc_lens = [n - 2 for n in example['phonemes_int_lengths']]
+        ctc_tgt = pad_seq([p[1:-1] for p in example['phonemes_int']], batch_first=True, padding_value=PAD).contiguous()
+        if ctc_tgt.shape[1] == 0:
+            ctc_tgt = torch.full((len(ctc_lens), 1), PAD, dtype=torch.int64)
+        host = dict(X=X, tgt_in=tgt_in, tgt_out=tgt_out.view(-1), ctc_tgt=ctc_tgt,
+                    ctc_lens=torch.tensor(ctc_lens, dtype=torch.int32),
+                    tgt_lens=torch.tensor([min(n, nmax - 1) for n in example['phonemes_int_lengths']], dtype=torch.int32))
+        if pin and self.dev.type == "cuda":
+            host = {k: v.pin_memory() for k, v in host.items()}
+        host['lengths'] = list(example['lengths'])
+        host['n_valid'] = int(sum(min(n, nmax) - 1 for n in example['phonemes_int_lengths']))
+        return host
+
+    def to_device(self, host):
+        d = {k: (v.to(self.dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
+        d['h2d_bytes'] = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+        return d
+
+    # ---- one micro-batch (recognition_model.py:69-118) -----------------------------------------------------------------
+    def step_device(self, dev_batch, shift_r=None):
+        """forward + loss + backward (+ optimizer when the accumulation threshold is reached) on device-resident inputs.
+        Returns the float32[3] device tensor (loss, loss_dec, loss_enc)."""
+        import random
+        model, eng, flat = self.model, self.eng, self.flat
+        model.train()
+        self.schedule_lr(self.batch_idx)
+        X = dev_batch['X']
+        self.sum_batch_size += X.shape[0]
+        r = random.randrange(8) if shift_r is None else shift_r       # architecture.py:105
+        if r > 0:
+            L.shift_left(X, X.shape[0], X.shape[1], X.shape[2], r)
+        has_dec = eng.n_dec > 0
+        _, _, ctx = eng.forward(X, dev_batch['lengths'], dev_batch['tgt_in'] if has_dec else None,
+                                dev_batch['tgt_lens'] if has_dec else None, training=True,
+                                seed=self.seed * 1000003 + self.batch_idx)
+        losses = eng.losses(ctx, dev_batch['ctc_tgt'], dev_batch['ctc_lens'], dev_batch['tgt_out'] if has_dec else None,
+                            dev_batch['n_valid'], self.alpha, self.eps_ls)
+        will_step = self.sum_batch_size >= self.batch_size_grad
+        if self.sync is not None and will_step:
+            self.sync.begin()
+            eng.backward(ctx, flat.G_all, on_stage=self.sync.on_stage)
+            self.sync.finish()
+        else:
+            eng.backward(ctx, flat.G_all)
+        if will_step:                                               # recognition_model.py:115-118
+            flat.step_count += 1
+            L.adamw(flat.p, flat.g, flat.m, flat.v, flat.numel, self.lr, 0.9, 0.999, 1e-8, self.wd, flat.step_count)
+            flat.zero_grad()
+            self.sum_batch_size = 0
+            eng.pack()
+            model._weights_version += 1
+        self.batch_idx += 1
+        return losses
+
+    def step(self, example):
+        """Public entry: collate_raw dict on the host -> losses; one async D2H of float[3] replaces the three .item() calls."""
+        dev_batch = self.to_device(self.prepare(example))
+        losses = self.step_device(dev_batch)
+        return self.fetch_losses(losses)
+
+    def fetch_losses(self, losses):
+        if self.dev.type == "cuda":
+            self._host_loss.copy_(losses, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._loss_event = ev
+        else:
+            self._host_loss.copy_(losses)
+        return self._host_loss
+
+    def wait_losses(self):
+        if self._loss_event is not None:
+            self._loss_event.synchronize()
+        a = self._host_loss
+        loss_dec, loss_enc = float(a[1]), float(a[2])
+        if self.eng.n_dec > 0:
+            return (1 - self.alpha) * loss_dec + self.alpha * loss_enc, loss_dec, loss_enc
+        return loss_enc, 0.0, loss_enc

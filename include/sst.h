@@ -33,6 +33,8 @@ extern "C" {
 
 const char* sst_version(void);
 const char* sst_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+long long sst_launch_count(void);
 /* 0 when the current device is a Blackwell sm_100 part, SST_E_ARCH otherwise. */
 int sst_device_check(void);
 
