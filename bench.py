@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Headline benchmark: train EMG frames/s (forward + hybrid CTC/attention loss + backward + AdamW) of the Silent Speech
+Transformer hot path on B200, through libsst.so.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg1]
+
+Workload (BASELINE.json configs[1], "cfg2"): 6 encoder layers (d 768, 8 heads, FFN 3072, rel-pos distance 100) + the
+reference's default 6-layer decoder, bf16 compute, 64 utterances x 8000 raw EMG samples per GPU (-> 320 chunks of 1600,
+64 x 1000 encoder frames), targets of 80-120 phones, hybrid loss (alpha 0.2, label smoothing 0.1), dropout 0.2, one AdamW
+step per batch.  A "step" is one such batch; `value` = encoder frames of all ranks / device time with the batches
+resident in HBM; `e2e` = the same step driven from pinned HOST buffers (H2D of the batch and D2H of the losses inside
+the timed region).  N > 1 (torchrun): weak scaling, one process per GPU, bucketed NCCL all-reduce overlapped with backward.
+
+`--impl reference` times the reference's CPU implementation of the same step (the oracle port of the PyTorch-CPU
+reference: /root/reference does not exist on the GPU box) on the host cores, on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "train EMG frames/s (fwd+bwd+loss+AdamW)"
+UNIT = "frames/s"
+
+WORKLOADS = {
+    # name: (n_enc, n_dec, alpha, utterances per GPU, frames per utterance)
+    "cfg1": dict(n_enc=6, n_dec=0, alpha=0.2, n_utt=4, frames=200, tgt=(30, 30)),
+    "cfg2": dict(n_enc=6, n_dec=6, alpha=0.2, n_utt=64, frames=1000, tgt=(80, 120)),
+    "cfg3": dict(n_enc=8, n_dec=4, alpha=0.7, n_utt=64, frames=1000, tgt=(80, 120)),
+}
+
+
+def workload_name(w):
+    return ("%s: %d enc + %d dec layers, d768 h8 ffn3072 R100, %d utt x %d samples/GPU, hybrid CTC/label-smoothed CE alpha %.1f, "
+            "dropout 0.2, AdamW every step" % (w["name"], w["n_enc"], w["n_dec"], w["n_utt"], w["frames"] * 8, w["alpha"]))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor=d.get("bf16_tflops_sustained", d["bf16_tflops"]), tensor_burst=d["bf16_tflops"],
+                    source="measured (MEASURED_PEAKS.json; tensor = sustained cuBLAS bf16)")
+    return dict(hbm=6650.0, tensor=1400.0, tensor_burst=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), power_w_max=max(pw), samples=len(sm), reasons=sorted(reasons))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference's PyTorch-CPU step on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_step_rate(w, steps, warmup, n_utt_sample=2):
+    """Times the CPU oracle (oracle/sst_oracle.py, the restated reference step: forward_training + CTC + LabelSmoothingLoss +
+    backward + AdamW) on `n_utt_sample` utterances of the workload's length.  Returns (frames/s, ms/step, cores, sample str)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sst_oracle as O
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    cfg = O.make_cfg(n_enc=w["n_enc"], n_dec=w["n_dec"], rel_dist=100, alpha=w["alpha"], dropout=0.2, dropout_pos=0.2)
+    sd = O.synthetic_state_dict(cfg, 0)
+    names = O.trainable_names(sd, cfg)
+    for n in names:
+        sd[n].requires_grad_(True)
+    m = {n: torch.zeros_like(sd[n]) for n in names}
+    v = {n: torch.zeros_like(sd[n]) for n in names}
+    frames = w["frames"]
+    tl = (w["tgt"][0] + w["tgt"][1]) // 2
+    times = []
+    for it in range(warmup + steps):
+        batch = O.synthetic_batch(n_utt=n_utt_sample, frames=frames, tgt_len=tl, seed=100 + it)
+        t0 = time.perf_counter()
+        res = O.train_step_losses(sd, cfg, batch, training=True, shift_r=it % 8)
+        res["loss"].backward()
+        with torch.no_grad():
+            for n in names:
+                if sd[n].grad is not None:
+                    O.adamw_step(sd[n], sd[n].grad, m[n], v[n], it + 1, 3e-4 * (it + 1) / 1500)
+                    sd[n].grad = None
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    fps = n_utt_sample * frames / (ms / 1e3)
+    sample = "%d utterances x %d samples (same utterance length and model as the workload), %d warm-up + %d timed steps" % (
+        n_utt_sample, frames * 8, warmup, steps)
+    return fps, ms, cores, sample
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    fps, ms, cores, sample = cpu_reference_step_rate(w, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": workload_name(w), "note": "reference CPU path (PyTorch fp32, oracle port) on host cores"},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args, w):
+    import torch.distributed as dist
+    import sst_b200  # noqa: F401
+    from sst_b200 import lib as L
+    from sst_b200 import architecture as A
+    from sst_b200.synthetic import make_batch
+    from sst_b200.train import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L.require_device()
+
+    A.configure(model_size=768, feed_forward_layer_size=3072, num_layers_encoder=w["n_enc"], num_layers_decoder=w["n_dec"],
+                n_heads_encoder=8, n_heads_decoder=8, relative_distance=100, dropout_model=0.2, dropout_pos_emb=0.2,
+                sst_dtype=args.dtype)
+    torch.manual_seed(0)                                   # identical initial weights on every rank
+    model = A.Model(112, 44, 43, dev).to(dev)
+    trainer = Trainer(model, alpha_loss=w["alpha"], batch_size_grad=1, seed=rank, distributed=world > 1)
+
+    n_batches = 2
+    host = [trainer.prepare(make_batch(w["n_utt"], w["frames"], w["tgt"][0], w["tgt"][1], seed=1234 + rank * 100 + i))
+            for i in range(n_batches)]
+    resident = [trainer.to_device(h) for h in host]
+    pristine = [d["X"].clone() for d in resident]
+    frames_per_step = w["n_utt"] * w["frames"]
+    h2d = resident[0]["h2d_bytes"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+        return ms
+
+    def resident_step(i):
+        d = resident[i % n_batches]
+        d["X"].copy_(pristine[i % n_batches])              # the training-time shift mutates x_raw in place (architecture.py:104-108)
+        return trainer.step_device(d)
+
+    def e2e_step(i):
+        d = trainer.to_device(host[i % n_batches])         # pinned host -> device, async on the compute stream
+        losses = trainer.step_device(d)
+        trainer.fetch_losses(losses)
+        return trainer.wait_losses()                       # device -> host read of the step's result
+
+    # ---- device-resident throughput -----------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        resident_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        losses = resident_step(i)
+    e1.record()
+    barrier()
+    launches = L.launch_count() - n0
+    ms_res = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    loss_vals = [float(x) for x in losses.cpu()]
+
+    # ---- end to end from host buffers ---------------------------------------------------------------------------------
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), wall_ms)) / args.steps
+
+    # ---- per-kernel-family device times (CUDA events on the launching stream) -----------------------------------------
+    with L.Profiler() as prof:
+        resident_step(0)
+        fam = prof.summary()
+    tot_ms = sum(d["ms"] for d in fam.values())
+    pk = peaks()
+    kernels = {}
+    for k, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+        e = {"ms": round(d["ms"], 3), "share": round(d["ms"] / tot_ms, 4), "launches": d["launches"]}
+        if d["flops"] > 0:
+            e["tflops"] = round(d["flops"] / d["ms"] / 1e9, 1)
+        if d["bytes"] > 0:
+            e["gbs"] = round(d["bytes"] / d["ms"] / 1e6, 1)
+        kernels[k] = e
+    dom = max(fam.items(), key=lambda kv: kv[1]["ms"])
+    dk, dd = dom
+    if dd["flops"] > 0:
+        ach = dd["flops"] / dd["ms"] / 1e9
+        roof = {"kernel": dk, "bound": "tensor", "achieved": round(ach, 1), "peak": pk["tensor"], "unit": "TFLOP/s",
+                "frac": round(ach / pk["tensor"], 4), "traffic": None, "launches_per_step": dd["launches"],
+                "avg_launch_ms": round(dd["ms"] / dd["launches"], 4), "peak_source": pk["source"]}
+    else:
+        ach = dd["bytes"] / dd["ms"] / 1e6
+        roof = {"kernel": dk, "bound": "hbm", "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s",
+                "frac": round(ach / pk["hbm"], 4), "traffic": None, "launches_per_step": dd["launches"],
+                "avg_launch_ms": round(dd["ms"] / dd["launches"], 4), "peak_source": pk["source"]}
+    # whole-step tensor roofline: algorithmic flops of every GEMM/attention launch / step time
+    step_flops = sum(d["flops"] for d in fam.values())
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            fps, ms, cores, sample = cpu_reference_step_rate(w, 2, 1)
+            cpu = {"value": round(fps, 1), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_step": round(ms, 1)}
+        line = {
+            "metric": METRIC, "value": round(world * frames_per_step / (ms_res / 1e3), 1), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(w), "frames_per_step_per_gpu": frames_per_step,
+                       "l2": "no flush needed: a step streams >10 GB of activations, far above the 126 MB L2",
+                       "parallelism": "dp%d" % world, "loss_last_step": loss_vals},
+            "e2e": {"value": round(world * frames_per_step / (ms_e2e / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 12, "ms_per_step": round(ms_e2e, 3)},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+            "step_tensor_roofline": {"algorithmic_tflop_per_step": round(step_flops / 1e12, 3),
+                                     "achieved_tflops": round(step_flops / ms_res / 1e9, 1), "peak": pk["tensor"],
+                                     "frac": round(step_flops / ms_res / 1e9 / pk["tensor"], 4)},
+            "kernels": kernels, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload], name=args.workload)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, w)
+        return
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            # convenience: relaunch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+                   "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+    args.warmup = max(args.warmup, 3)
+    run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

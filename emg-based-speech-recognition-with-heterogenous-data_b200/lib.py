@@ -48,6 +48,57 @@ def check(rc, what=""):
         raise SstError("%s failed (%d): %s" % (what, rc, lib().sst_last_error().decode()))
 
 
+class Profiler:
+    """Per-kernel-family device timing with CUDA events on the launching stream (bench.py's roofline leg).
+    Every C-ABI wrapper below brackets its launch with `_scope(kind, flops=, bytes=)`; while a Profiler is
+    installed (`with Profiler() as prof:`) each scope records a start/stop event pair; `summary()` synchronises and
+    returns {kind: dict(ms, launches, flops, bytes)}.  With no profiler installed a scope is a no-op."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _profiler
+        self._prev, _profiler = _profiler, self
+        return self
+
+    def __exit__(self, *exc):
+        global _profiler
+        _profiler = self._prev
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for kind, flops, nbytes, e0, e1 in self.records:
+            d = out.setdefault(kind, dict(ms=0.0, launches=0, flops=0.0, bytes=0.0))
+            d["ms"] += e0.elapsed_time(e1)
+            d["launches"] += 1
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        return out
+
+
+_profiler = None
+
+
+class _scope:
+    __slots__ = ("kind", "flops", "bytes", "e0")
+
+    def __init__(self, kind, flops=0.0, bytes=0.0):
+        self.kind, self.flops, self.bytes = kind, flops, bytes
+
+    def __enter__(self):
+        if _profiler is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _profiler is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _profiler.records.append((self.kind, self.flops, self.bytes, self.e0, e1))
+
+
 def dt(t):
     if t.dtype == torch.float32:
         return F32
@@ -93,7 +144,11 @@ def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, layout=GEMM_TN, bias=None, aux=None
     d.epilogue, d.alpha, d.mask_scale, d.drop_p, d.seed = epilogue, alpha, mask_scale, drop_p, seed
     d.remap_P, d.remap_T, d.remap_j0 = remap
     d.force_simt = 1 if force_simt else 0
-    check(lib().sst_gemm(C.byref(d), ptr(A), ptr(B), ptr(Cout), ptr(bias), ptr(aux), stream()), "sst_gemm")
+    m_real = M * remap[1] / remap[0] if remap[0] > 0 else M        # halo rows of a remapped conv GEMM are not work
+    tc = d.dtype == BF16 and not force_simt
+    kind = ("gemm_tcgen05_wgrad" if layout == GEMM_NT_MN else "gemm_tcgen05") if tc else "gemm_cuda_core"
+    with _scope(kind, 2.0 * m_real * N * K, (m_real * K + N * K) * A.element_size() + m_real * N * Cout.element_size()):
+        check(lib().sst_gemm(C.byref(d), ptr(A), ptr(B), ptr(Cout), ptr(bias), ptr(aux), stream()), "sst_gemm")
 
 
 class AttnDesc(C.Structure):
@@ -125,32 +180,56 @@ def attn_desc(dtype, B, H, Lq, Lk, dh, ldq, ldk, ldv, ldo, causal, mask_q_rows, 
     return d
 
 
+def attn_work(d):
+    """Band-limited ALGORITHMIC flops of one attention call (SURVEY.md 8(a) flop model, Q3): per (b, h, query) 4*k*dh for
+    q.k and p.v plus 2*k*dh for the q.E bias, k = mean number of in-band keys; backward = 2x forward minus the absent dE."""
+    Lq, Lk, R = d.Lq, d.Lk, d.rel_dist
+    if R > 0 and Lk > R:
+        kbar = sum(min(Lk - 1, i + R - 1) - max(0, i - R + 1) + 1 for i in range(Lq)) / float(Lq)
+    elif d.causal:
+        kbar = (Lk + 1) / 2.0
+    else:
+        kbar = float(Lk)
+    rows = d.B * d.H * Lq
+    qk_pv = 4.0 * kbar * d.dh * rows
+    bias = 2.0 * kbar * d.dh * rows if R > 0 else 0.0
+    return qk_pv + bias, 2.0 * qk_pv + bias
+
+
 def attn_fwd(d, q, k, v, E, q_lens, k_lens, o, lse):
-    check(lib().sst_attn_fwd(C.byref(d), ptr(q), ptr(k), ptr(v), ptr(E), ptr(q_lens), ptr(k_lens), ptr(o), ptr(lse),
-                             stream()), "sst_attn_fwd")
+    with _scope("attn_fwd", attn_work(d)[0] if _profiler is not None else 0.0):
+        check(lib().sst_attn_fwd(C.byref(d), ptr(q), ptr(k), ptr(v), ptr(E), ptr(q_lens), ptr(k_lens), ptr(o), ptr(lse),
+                                 stream()), "sst_attn_fwd")
 
 
 def attn_bwd(d, q, k, v, E, q_lens, k_lens, o, lse, dO, dq, dk, dv, delta):
-    check(lib().sst_attn_bwd(C.byref(d), ptr(q), ptr(k), ptr(v), ptr(E), ptr(q_lens), ptr(k_lens), ptr(o), ptr(lse),
-                             ptr(dO), ptr(dq), ptr(dk), ptr(dv), ptr(delta), stream()), "sst_attn_bwd")
+    with _scope("attn_bwd", attn_work(d)[1] if _profiler is not None else 0.0):
+        check(lib().sst_attn_bwd(C.byref(d), ptr(q), ptr(k), ptr(v), ptr(E), ptr(q_lens), ptr(k_lens), ptr(o), ptr(lse),
+                                 ptr(dO), ptr(dq), ptr(dk), ptr(dv), ptr(delta), stream()), "sst_attn_bwd")
 
 
 def layernorm_fwd(dtype, rows, D, x, r, drop_p, seed, gamma, beta, y, s_out, mean, rstd, eps=1e-5):
-    check(lib().sst_layernorm_fwd(dtype, _i64(rows), D, ptr(x), ptr(r), _f(drop_p), _u64(seed), ptr(gamma), ptr(beta),
-                                  ptr(y), ptr(s_out), ptr(mean), ptr(rstd), _f(eps), stream()), "sst_layernorm_fwd")
+    # algorithmic bytes: read x, r; write y, s (saved pre-norm sum)
+    with _scope("layernorm_fwd", bytes=4.0 * rows * D * (2 if dtype == BF16 else 4)):
+        check(lib().sst_layernorm_fwd(dtype, _i64(rows), D, ptr(x), ptr(r), _f(drop_p), _u64(seed), ptr(gamma), ptr(beta),
+                                      ptr(y), ptr(s_out), ptr(mean), ptr(rstd), _f(eps), stream()), "sst_layernorm_fwd")
 
 
 def layernorm_bwd(dtype, rows, D, dy, s, mean, rstd, gamma, ds, dr, drop_p, seed, dgamma, dbeta):
-    check(lib().sst_layernorm_bwd(dtype, _i64(rows), D, ptr(dy), ptr(s), ptr(mean), ptr(rstd), ptr(gamma), ptr(ds),
-                                  ptr(dr), _f(drop_p), _u64(seed), ptr(dgamma), ptr(dbeta), stream()), "sst_layernorm_bwd")
+    # read dy, s; write ds (+ dr when dropout is on)
+    with _scope("layernorm_bwd", bytes=(3.0 + (1.0 if drop_p > 0 else 0.0)) * rows * D * (2 if dtype == BF16 else 4)):
+        check(lib().sst_layernorm_bwd(dtype, _i64(rows), D, ptr(dy), ptr(s), ptr(mean), ptr(rstd), ptr(gamma), ptr(ds),
+                                      ptr(dr), _f(drop_p), _u64(seed), ptr(dgamma), ptr(dbeta), stream()), "sst_layernorm_bwd")
 
 
 def colstats(dtype, x, rows, Cc, ld, stats):
-    check(lib().sst_colstats(dtype, ptr(x), _i64(rows), Cc, _i64(ld), ptr(stats), stream()), "sst_colstats")
+    with _scope("bn_colstats", bytes=1.0 * rows * Cc * (2 if dtype == BF16 else 4)):
+        check(lib().sst_colstats(dtype, ptr(x), _i64(rows), Cc, _i64(ld), ptr(stats), stream()), "sst_colstats")
 
 
 def colsum_accum(dtype, x, rows, Cc, ld, out):
-    check(lib().sst_colsum_accum(dtype, ptr(x), _i64(rows), Cc, _i64(ld), ptr(out), stream()), "sst_colsum_accum")
+    with _scope("bias_colsum", bytes=1.0 * rows * Cc * (2 if dtype == BF16 else 4)):
+        check(lib().sst_colsum_accum(dtype, ptr(x), _i64(rows), Cc, _i64(ld), ptr(out), stream()), "sst_colsum_accum")
 
 
 def bn_finalize(stats, count, Cc, eps, momentum, mean, invstd, running_mean, running_var, training):
@@ -161,33 +240,39 @@ def bn_finalize(stats, count, Cc, eps, momentum, mean, invstd, running_mean, run
 def bn_apply(dtype, n_chunks, T, Cc, xa, lda, sa, xb, ldb, sb, relu, out, lead, trail):
     """sa / sb = (mean, invstd, gamma, beta) tuples; xb / sb may be None."""
     nb = (None, None, None, None) if sb is None else sb
-    check(lib().sst_bn_apply(dtype, _i64(n_chunks), T, Cc, ptr(xa), _i64(lda), ptr(sa[0]), ptr(sa[1]), ptr(sa[2]), ptr(sa[3]),
-                             ptr(xb), _i64(ldb), ptr(nb[0]), ptr(nb[1]), ptr(nb[2]), ptr(nb[3]), int(relu), ptr(out),
-                             lead, trail, stream()), "sst_bn_apply")
+    with _scope("bn_apply", bytes=(2.0 + (1.0 if xb is not None else 0.0)) * n_chunks * T * Cc * (2 if dtype == BF16 else 4)):
+        check(lib().sst_bn_apply(dtype, _i64(n_chunks), T, Cc, ptr(xa), _i64(lda), ptr(sa[0]), ptr(sa[1]), ptr(sa[2]), ptr(sa[3]),
+                                 ptr(xb), _i64(ldb), ptr(nb[0]), ptr(nb[1]), ptr(nb[2]), ptr(nb[3]), int(relu), ptr(out),
+                                 lead, trail, stream()), "sst_bn_apply")
 
 
 def bn_bwd(dtype, n_chunks, T, Cc, dout, ld_dout, y, y_lead, y_trail, relu,
            xa, lda, mean_a, invstd_a, gamma_a, dxa, ld_dxa, lead_a, trail_a, dgamma_a, dbeta_a,
            xb, ldb, mean_b, invstd_b, gamma_b, dxb, ld_dxb, lead_b, trail_b, dgamma_b, dbeta_b, red):
-    check(lib().sst_bn_bwd(dtype, _i64(n_chunks), T, Cc, ptr(dout), _i64(ld_dout), ptr(y), y_lead, y_trail, int(relu),
-                           ptr(xa), _i64(lda), ptr(mean_a), ptr(invstd_a), ptr(gamma_a), ptr(dxa), _i64(ld_dxa), lead_a, trail_a,
-                           ptr(dgamma_a), ptr(dbeta_a),
-                           ptr(xb), _i64(ldb), ptr(mean_b), ptr(invstd_b), ptr(gamma_b), ptr(dxb), _i64(ld_dxb), lead_b, trail_b,
-                           ptr(dgamma_b), ptr(dbeta_b), ptr(red), stream()), "sst_bn_bwd")
+    # two passes (reduce, apply): dout, y, xa (+xb) read twice; dxa (+dxb) written
+    with _scope("bn_bwd", bytes=(2.0 * (3.0 + (1.0 if xb is not None else 0.0)) + 1.0 + (1.0 if xb is not None else 0.0))
+                * n_chunks * T * Cc * (2 if dtype == BF16 else 4)):
+        check(lib().sst_bn_bwd(dtype, _i64(n_chunks), T, Cc, ptr(dout), _i64(ld_dout), ptr(y), y_lead, y_trail, int(relu),
+                               ptr(xa), _i64(lda), ptr(mean_a), ptr(invstd_a), ptr(gamma_a), ptr(dxa), _i64(ld_dxa), lead_a, trail_a,
+                               ptr(dgamma_a), ptr(dbeta_a),
+                               ptr(xb), _i64(ldb), ptr(mean_b), ptr(invstd_b), ptr(gamma_b), ptr(dxb), _i64(ld_dxb), lead_b, trail_b,
+                               ptr(dgamma_b), ptr(dbeta_b), ptr(red), stream()), "sst_bn_bwd")
 
 
 def ctc_loss(logits_dtype, grad_dtype, B, L, Cc, blank, logits, ld, targets, Smax, in_lens, tgt_lens, gcoef, lp_ws, alpha_ws,
              nll, grad, ldg, loss_out):
-    check(lib().sst_ctc_loss(logits_dtype, grad_dtype, B, L, Cc, blank, ptr(logits), _i64(ld), ptr(targets), Smax, ptr(in_lens),
-                             ptr(tgt_lens), _f(gcoef), ptr(lp_ws), ptr(alpha_ws), ptr(nll), ptr(grad), _i64(ldg), ptr(loss_out),
-                             stream()), "sst_ctc_loss")
+    with _scope("ctc"):
+        check(lib().sst_ctc_loss(logits_dtype, grad_dtype, B, L, Cc, blank, ptr(logits), _i64(ld), ptr(targets), Smax, ptr(in_lens),
+                                 ptr(tgt_lens), _f(gcoef), ptr(lp_ws), ptr(alpha_ws), ptr(nll), ptr(grad), _i64(ldg), ptr(loss_out),
+                                 stream()), "sst_ctc_loss")
 
 
 def ce_sumexp_loss(logits_dtype, grad_dtype, rows, S, Cc, logits, ld, target, ignore, eps, n_valid, gcoef, row_ws, grad, ldg,
                    loss_out):
-    check(lib().sst_ce_sumexp_loss(logits_dtype, grad_dtype, _i64(rows), S, Cc, ptr(logits), _i64(ld), ptr(target), ignore,
-                                   _f(eps), _i64(n_valid), _f(gcoef), ptr(row_ws), ptr(grad), _i64(ldg), ptr(loss_out),
-                                   stream()), "sst_ce_sumexp_loss")
+    with _scope("ce_sumexp"):
+        check(lib().sst_ce_sumexp_loss(logits_dtype, grad_dtype, _i64(rows), S, Cc, ptr(logits), _i64(ld), ptr(target), ignore,
+                                       _f(eps), _i64(n_valid), _f(gcoef), ptr(row_ws), ptr(grad), _i64(ldg), ptr(loss_out),
+                                       stream()), "sst_ce_sumexp_loss")
 
 
 def shift_left(x, n_chunks, T, Cc, r):
@@ -225,8 +310,9 @@ def permute3_cast(inp, out, dims, in_strides, out_strides, accumulate=False):
 
 
 def adamw(p, g, m, v, n, lr, beta1, beta2, eps, wd, step):
-    check(lib().sst_adamw(ptr(p), ptr(g), ptr(m), ptr(v), _i64(n), _f(lr), _f(beta1), _f(beta2), _f(eps), _f(wd), _i64(step),
-                          stream()), "sst_adamw")
+    with _scope("adamw", bytes=28.0 * n):          # read p, g, m, v; write p, m, v (fp32)
+        check(lib().sst_adamw(ptr(p), ptr(g), ptr(m), ptr(v), _i64(n), _f(lr), _f(beta1), _f(beta2), _f(eps), _f(wd), _i64(step),
+                              stream()), "sst_adamw")
 
 
 def launch_count():
