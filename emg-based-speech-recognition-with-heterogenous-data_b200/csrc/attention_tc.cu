@@ -1,0 +1,253 @@
+// Tensor-core attention (bf16 operands, fp32 accumulation): the fused masked / banded relative-position attention of
+// include/sst.h on tcgen05, TMA-fed.  Replaces MultiHeadAttention.forward between the projections
+// (transformer.py:177-208) and LearnedRelativePositionalEmbedding (transformer.py:260-403).
+//
+// One CTA = 128 query rows of one (batch, head); key tiles of 64.  Per key tile, issued by one thread:
+//     S  (128 x 64)  = Q K^T            tcgen05.mma, accumulator in TMEM columns [0, 64)
+//     PB (128 x 192) = Q E_win^T        the relative-position logits against the 191 embedding rows the tile can touch
+//                                       (E_win = rows [j0-i0-127+R-1, +192) of E[h]); TMEM columns [64, 256)
+// then one thread per query row reads its S row and its PB window from TMEM.  The reference's pad/view "skew"
+// (transformer.py:383-395) becomes a per-lane register barrel shift: bias[i][j] = PB[i][(j-j0) - (i-i0) + 127]; the
+// warp-uniform part of the shift is folded into the tcgen05.ld column address, the lane part (0..31) is five
+// predicated select stages.  Masks are SET to -1e8 and the bias ADDED exactly as the reference does,
+// online softmax over key tiles, Philox dropout on the probabilities, P (bf16) goes to 128B-swizzled shared memory and
+//     O (128 x dh) += P V               accumulator in TMEM columns [256, 256+dh), rescaled in TMEM when a row max moves.
+// Only key tiles that intersect the band |i-j| < R are visited (exact: everything outside has probability 0 in fp32).
+// Backward = two kernels of the same shape (dQ per query tile; dK/dV per key tile), see attention_tc_bwd.cu.
+#include "attention_tc.cuh"
+
+namespace sst {
+
+template <int DH>
+__global__ void __launch_bounds__(128, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmE, const attn_tc::AttnTcParams p) {
+  using namespace attn_tc;
+  constexpr int KS = DH / 16;                    // k-steps of the q.k / q.E contractions
+  constexpr int NATOM = (DH + 63) / 64;          // 64-column (128-byte) swizzle atoms per row of q / k / E / v
+  constexpr int Q_ATOM = BM * 128, K_ATOM = BN * 128, E_ATOM = PBW * 128, V_GRP = BN * 128;
+  constexpr uint32_t TM_S = 0, TM_PB = 64, TM_O = 256;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + NATOM * Q_ATOM;
+  uint8_t* sE = sK + NATOM * K_ATOM;
+  uint8_t* sV = sE + NATOM * E_ATOM;             // two buffers
+  uint8_t* sP = sV + 2 * NATOM * V_GRP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + BM * 128);
+  uint64_t* bar_q = bars, *bar_ke = bars + 1, *bar_v = bars + 2 /* [2] */, *bar_s = bars + 4, *bar_o = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int li = threadIdx.x;
+  const int i0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
+  const int i = i0 + li;
+  const bool leader = threadIdx.x == 0;
+
+  if (w == 0) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
+      if (p.R > 0) ptx::prefetch_tmap(&tmE);
+      for (int k = 0; k < 6; ++k) ptx::mbar_init(&bars[k], 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = (uint32_t)(w * 32) << 16;
+
+  int t_lo, t_hi;
+  key_tile_range(p, i0, t_lo, t_hi);
+
+  const uint32_t ke_bytes = NATOM * K_ATOM + (p.R > 0 ? NATOM * E_ATOM : 0);
+  auto load_ke = [&](int t) {
+    ptx::mbar_arrive_expect_tx(bar_ke, ke_bytes);
+#pragma unroll
+    for (int a = 0; a < NATOM; ++a) ptx::tma_load_2d(sK + a * K_ATOM, &tmK, bar_ke, h * DH + a * 64, b * p.Lk + t * BN);
+    if (p.R > 0) {
+      const int e0 = (t * BN - i0) - (BM - 1) + (p.R - 1);
+#pragma unroll
+      for (int a = 0; a < NATOM; ++a) ptx::tma_load_2d(sE + a * E_ATOM, &tmE, bar_ke, a * 64, h * (2 * p.R - 1) + e0);
+    }
+  };
+  auto load_v = [&](int t) {
+    const int buf = (t - t_lo) & 1;
+    ptx::mbar_arrive_expect_tx(&bar_v[buf], NATOM * V_GRP);
+#pragma unroll
+    for (int a = 0; a < NATOM; ++a)
+      ptx::tma_load_2d(sV + (buf * NATOM + a) * V_GRP, &tmV, &bar_v[buf], h * DH + a * 64, b * p.Lk + t * BN);
+  };
+  auto issue_s = [&]() {          // S = Q K^T and PB = Q E_win^T for the tile whose K / E are in shared memory
+    const uint32_t qb = ptx::smem_u32(sQ), kb = ptx::smem_u32(sK), eb = ptx::smem_u32(sE);
+    const uint32_t id_s = ptx::make_idesc_bf16(BM, BN, 0, 0), id_pb = ptx::make_idesc_bf16(BM, PBW, 0, 0);
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const uint32_t off = (ks >> 2), in = (ks & 3) * 32;
+      ptx::umma_bf16(tmem + TM_S, ptx::make_smem_desc_sw128(qb + off * Q_ATOM + in, 0, 1024),
+                     ptx::make_smem_desc_sw128(kb + off * K_ATOM + in, 0, 1024), id_s, ks > 0);
+    }
+    if (p.R > 0) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t off = (ks >> 2), in = (ks & 3) * 32;
+        ptx::umma_bf16(tmem + TM_PB, ptx::make_smem_desc_sw128(qb + off * Q_ATOM + in, 0, 1024),
+                       ptx::make_smem_desc_sw128(eb + off * E_ATOM + in, 0, 1024), id_pb, ks > 0);
+      }
+    }
+    ptx::umma_commit(bar_s);
+  };
+
+  if (leader) {
+    ptx::mbar_arrive_expect_tx(bar_q, NATOM * Q_ATOM);
+#pragma unroll
+    for (int a = 0; a < NATOM; ++a) ptx::tma_load_2d(sQ + a * Q_ATOM, &tmQ, bar_q, h * DH + a * 64, b * p.Lq + i0);
+    load_ke(t_lo);
+    load_v(t_lo);
+    ptx::mbar_wait(bar_q, 0);
+    ptx::mbar_wait(bar_ke, 0);
+    ptx::tc_fence_after();
+    issue_s();
+  }
+  __syncwarp();
+
+  const RowCtx rc = make_row_ctx(p, b, h, i);
+  float m_run = NEG_BIG, l_run = 0.f;
+  uint32_t ph_s = 0, ph_ke = 1;
+
+  for (int t = t_lo; t <= t_hi; ++t) {
+    ptx::mbar_wait(bar_s, ph_s);
+    ph_s ^= 1u;
+    ptx::tc_fence_after();
+    if (leader && t < t_hi) { load_ke(t + 1); load_v(t + 1); }
+    __syncwarp();
+
+    float U[96];
+    tile_logits<false>(p, rc, tmem + TM_S + lane_base, tmem + TM_PB + lane_base, w, lane, t * BN, U);
+
+    float mt = U[0];
+#pragma unroll
+    for (int x = 1; x < BN; ++x) mt = fmaxf(mt, U[x]);
+    const float m_new = fmaxf(m_run, mt);
+    const float alpha = __expf(m_run - m_new);
+    float sum = 0.f;
+#pragma unroll
+    for (int x = 0; x < BN; ++x) { U[x] = __expf(U[x] - m_new); sum += U[x]; }
+    l_run = l_run * alpha + sum;
+    m_run = m_new;
+    if (p.thr) apply_dropout(p, rc, t * BN, U);
+    store_row_bf16_sw128(ptx::smem_u32(sP), li, U);
+
+    if (t > t_lo && __any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+      for (int c = 0; c < DH / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tmem + TM_O + c * 32 + lane_base, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int x = 0; x < 32; ++x) r[x] = __float_as_uint(__uint_as_float(r[x]) * alpha);
+        ptx::tmem_st_32x32b_x32(tmem + TM_O + c * 32 + lane_base, r);
+      }
+      ptx::tmem_st_wait();
+    }
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (leader) {
+      ptx::tc_fence_after();
+      const int buf = (t - t_lo) & 1;
+      ptx::mbar_wait(&bar_v[buf], ((t - t_lo) >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t pb = ptx::smem_u32(sP), vb = ptx::smem_u32(sV + buf * NATOM * V_GRP);
+      const uint32_t id_o = ptx::make_idesc_bf16(BM, DH, 0, 1);
+#pragma unroll
+      for (int ks = 0; ks < BN / 16; ++ks)
+        ptx::umma_bf16(tmem + TM_O, ptx::make_smem_desc_sw128(pb + ks * 32, 0, 1024),
+                       ptx::make_smem_desc_sw128(vb + ks * 2048, V_GRP, 1024), id_o, (t > t_lo || ks > 0) ? 1u : 0u);
+      if (t < t_hi) {
+        ptx::mbar_wait(bar_ke, ph_ke);
+        ph_ke ^= 1u;
+        ptx::tc_fence_after();
+        issue_s();
+      } else {
+        ptx::umma_commit(bar_o);
+      }
+    }
+    __syncwarp();
+  }
+
+  ptx::mbar_wait(bar_o, 0);
+  ptx::tc_fence_after();
+  {
+    // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only rows that exist store
+    const bool valid = i < p.Lq;
+    const float inv = 1.f / l_run;
+    __nv_bfloat16* orow = p.o + ((long)b * p.Lq + i) * p.ldo + h * DH;
+#pragma unroll
+    for (int c = 0; c < DH / 32; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(tmem + TM_O + c * 32 + lane_base, r);
+      ptx::tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o4;
+          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o4);
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+            o2[x] = __floats2bfloat162_rn(__uint_as_float(r[g * 8 + 2 * x]) * inv, __uint_as_float(r[g * 8 + 2 * x + 1]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = o4;
+        }
+      }
+      __syncwarp();
+    }
+    if (valid) {
+      const long nrows = (long)p.B * p.H * p.Lq;
+      p.lse[rc.row_id] = m_run;
+      p.lse[nrows + rc.row_id] = __logf(l_run);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (w == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
+int attn_fwd_tc_launch(const SstAttnDesc& d, const void* q, const void* k, const void* v, const void* E, const int* q_lens,
+                       const int* k_lens, void* o, float* lse, cudaStream_t st) {
+  using namespace attn_tc;
+  constexpr int DH = 96;
+  AttnTcParams p = make_tc_params(d, q_lens, k_lens);
+  p.o = reinterpret_cast<__nv_bfloat16*>(o); p.ldo = d.ldo; p.lse = lse;
+  CUtensorMap tmQ, tmK, tmV, tmE;
+  int rc;
+  const long HD = (long)d.H * d.dh;
+  if ((rc = make_tmap_bf16_2d(&tmQ, q, HD, (long)d.B * d.Lq, d.ldq, 64, BM))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmK, k, HD, (long)d.B * d.Lk, d.ldk, 64, BN))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmV, v, HD, (long)d.B * d.Lk, d.ldv, 64, BN))) return rc;
+  if (d.rel_dist > 0) {
+    if ((rc = make_tmap_bf16_2d(&tmE, E, d.dh, (long)d.H * (2 * d.rel_dist - 1), d.dh, 64, PBW))) return rc;
+  } else {
+    tmE = tmK;
+  }
+  constexpr int NATOM = (DH + 63) / 64;
+  constexpr int SMEM = NATOM * (BM * 128 + BN * 128 + PBW * 128 + 2 * BN * 128) + BM * 128 + 1024 + 128;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    SST_REQUIRE(e == cudaSuccess, SST_E_LAUNCH, "cudaFuncSetAttribute(attn_fwd_tc): %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  dim3 grid(cdiv(d.Lq, BM), d.H, d.B);
+  attn_fwd_tc_kernel<DH><<<grid, 128, SMEM, st>>>(tmQ, tmK, tmV, tmE, p);
+  return check_launch("attn_fwd_tc");
+}
+
+}  // namespace sst
