@@ -287,6 +287,10 @@ int attn_bwd_simt_launch(const SstAttnDesc& d, const void* q, const void* k, con
 int attn_fwd_tc_launch(const SstAttnDesc& d, const void* q, const void* k, const void* v, const void* E, const int* q_lens,
                        const int* k_lens, void* o, float* lse, cudaStream_t st);
 
+int attn_bwd_tc_launch(const SstAttnDesc& d, const void* q, const void* k, const void* v, const void* E, const int* q_lens,
+                       const int* k_lens, const void* o, const float* lse, const void* dO, void* dq, void* dk, void* dv,
+                       float* delta, cudaStream_t st);
+
 static bool use_tc(const SstAttnDesc& d) { return d.dtype == SST_BF16 && !d.force_simt && d.dh == 96; }
 
 }  // namespace sst
@@ -319,6 +323,8 @@ int sst_attn_bwd(const SstAttnDesc* d, const void* q, const void* k, const void*
   int rc = attn_check(d, q, k, v, E);
   if (rc) return rc;
   if (d->B * d->H * d->Lq == 0) return SST_OK;
+  if (use_tc(*d))
+    return attn_bwd_tc_launch(*d, q, k, v, E, q_lens, k_lens, o, lse, dO, dq, dk, dv, delta, reinterpret_cast<cudaStream_t>(stream));
   return attn_bwd_simt_launch(*d, q, k, v, E, q_lens, k_lens, o, lse, dO, dq, dk, dv, delta, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -26,6 +26,10 @@ struct AttnTcParams {
   const int* q_lens; const int* k_lens;
   __nv_bfloat16* o; long ldo;
   float* lse;
+  // backward only
+  const __nv_bfloat16* dO;                 // pitch ldo
+  float* delta;                            // [B*H*Lq]  dO_i . O_i   (written by the dQ kernel, read by the dK/dV kernel)
+  __nv_bfloat16 *dq, *dk, *dv; long ldq, ldk, ldv;
 };
 
 inline AttnTcParams make_tc_params(const SstAttnDesc& d, const int* q_lens, const int* k_lens) {
@@ -157,7 +161,9 @@ __device__ __forceinline__ void apply_dropout(const AttnTcParams& p, const RowCt
 
 // One 64-element row (128 bytes of bf16) into a K-major SWIZZLE_128B operand tile: 16-byte chunk c of row r lives at
 // chunk c ^ (r & 7).  `sbase` must be 1024-byte aligned.
-__device__ __forceinline__ void store_row_bf16_sw128(uint32_t sbase, int row, const float (&U)[96]) {
+template <int N>
+__device__ __forceinline__ void store_row_bf16_sw128(uint32_t sbase, int row, const float (&U)[N]) {
+  static_assert(N >= BN, "row array too short");
   const uint32_t rbase = sbase + row * 128;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
