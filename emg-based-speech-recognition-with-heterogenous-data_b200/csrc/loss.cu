@@ -37,141 +37,158 @@ __global__ void log_softmax_kernel(const T* __restrict__ x, long ld, float* __re
 
 constexpr int CTC_MAXSPL = 16;   // states per lane -> 2S+1 <= 512
 
-// lp: (B, L, C) fp32 log-probs.  alpha_ws: (B, L, NS) fp32.  grad: (B*L, ldg) in T.  One warp per utterance.
-template <typename T>
-__global__ void __launch_bounds__(32)
-ctc_kernel(const float* __restrict__ lp, const long* __restrict__ targets, int tgt_pitch, const int* __restrict__ in_lens,
-           const int* __restrict__ tgt_lens, int L, int C, int blank, int NS, float* __restrict__ alpha_ws,
-           float* __restrict__ nll, T* __restrict__ grad, long ldg, float gcoef, int B) {
-  extern __shared__ float occ[];   // [C]
-  const int b = blockIdx.x, lane = threadIdx.x;
+// CTC forward-backward lattice of one utterance per CTA, log space (Graves 2006 eq. 6-11): warp 0 runs the alpha recursion
+// over t = 0 .. T-1, warp 1 the beta recursion over t = T-1 .. 0, concurrently; the 2S+1 lattice states are spread over
+// the 32 lanes (SPL consecutive states per lane, neighbours by warp shuffle).  The utterance's log-probabilities are
+// staged once in shared memory (all threads) so that the serial loops never wait on HBM.  alpha and beta (each already
+// containing the emission at t) go to the workspace; ctc_grad_kernel turns them into the gradient in parallel over (b, t).
+template <int SPL, bool SMEM_LP>
+__global__ void __launch_bounds__(128)
+ctc_lattice_kernel(const float* __restrict__ lp, const long* __restrict__ targets, int tgt_pitch, const int* __restrict__ in_lens,
+                   const int* __restrict__ tgt_lens, int L, int C, int blank, int NS, float* __restrict__ alpha_ws,
+                   float* __restrict__ beta_ws, float* __restrict__ nll) {
+  extern __shared__ float slp[];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Tn = min(in_lens[b], L);
   const int S = tgt_lens[b];
   const int n = 2 * S + 1;
-  int spl = (NS + 31) / 32;
-  if (spl < 2) spl = 2;
   const float* lpb = lp + (long)b * L * C;
-  float* aw = alpha_ws + (long)b * L * NS;
-  int lab[CTC_MAXSPL];
-  bool skip_a[CTC_MAXSPL], skip_b[CTC_MAXSPL];
+  if (SMEM_LP) {
+    const long tot = (long)Tn * C;
+    if ((((uintptr_t)lpb) & 15) == 0) {
+      const float4* src = reinterpret_cast<const float4*>(lpb);
+      float4* dst = reinterpret_cast<float4*>(slp);
+      for (long k = threadIdx.x; k < tot / 4; k += blockDim.x) dst[k] = __ldg(src + k);
+      for (long k = (tot & ~3L) + threadIdx.x; k < tot; k += blockDim.x) slp[k] = __ldg(lpb + k);
+    } else {
+      for (long k = threadIdx.x; k < tot; k += blockDim.x) slp[k] = __ldg(lpb + k);
+    }
+    __syncthreads();
+  }
+  if (warp > 1) return;
+  if (Tn <= 0) { if (warp == 0 && lane == 0) nll[b] = INFINITY; return; }
+  const float* LP = SMEM_LP ? slp : lpb;
+  int lab[SPL];
+  bool skip[SPL];      // alpha warp: transition from s-2 allowed; beta warp: transition to s+2 allowed
 #pragma unroll
-  for (int u = 0; u < CTC_MAXSPL; ++u) {
-    const int s = lane * spl + u;
-    lab[u] = blank; skip_a[u] = false; skip_b[u] = false;
-    if (u < spl && s < n && (s & 1)) {
+  for (int u = 0; u < SPL; ++u) {
+    const int s = lane * SPL + u;
+    lab[u] = blank; skip[u] = false;
+    if (s < n && (s & 1)) {
       const int l = (int)targets[(long)b * tgt_pitch + (s >> 1)];
       lab[u] = l;
-      skip_a[u] = s >= 2 && l != (int)targets[(long)b * tgt_pitch + (s >> 1) - 1];
-      skip_b[u] = s + 2 < n && l != (int)targets[(long)b * tgt_pitch + (s >> 1) + 1];
+      if (warp == 0) skip[u] = s >= 2 && l != (int)targets[(long)b * tgt_pitch + (s >> 1) - 1];
+      else skip[u] = s + 2 < n && l != (int)targets[(long)b * tgt_pitch + (s >> 1) + 1];
     }
   }
-  float a[CTC_MAXSPL];
-  float ll = -INFINITY;
-  if (Tn > 0) {
-    // ---- alpha ----
+  float a[SPL];
+  if (warp == 0) {
+    float* aw = alpha_ws + (long)b * L * NS;
 #pragma unroll
-    for (int u = 0; u < CTC_MAXSPL; ++u) {
-      const int s = lane * spl + u;
-      a[u] = -INFINITY;
-      if (u < spl && s < n && s <= 1) a[u] = lpb[lab[u]];
-      if (u < spl && s < n) aw[s] = a[u];
+    for (int u = 0; u < SPL; ++u) {
+      const int s = lane * SPL + u;
+      a[u] = (s < n && s <= 1) ? LP[lab[u]] : -INFINITY;
+      if (s < n) aw[s] = a[u];
     }
     for (int t = 1; t < Tn; ++t) {
-      float emit[CTC_MAXSPL];
+      float emit[SPL];
 #pragma unroll
-      for (int u = 0; u < CTC_MAXSPL; ++u) emit[u] = (u < spl) ? __ldg(lpb + (long)t * C + lab[u]) : 0.f;
-      // neighbours from the previous lane: its last and second-to-last state
-      float last = a[0], last2 = a[0];
-#pragma unroll
-      for (int u = 0; u < CTC_MAXSPL; ++u) { if (u == spl - 1) last = a[u]; if (u == spl - 2) last2 = a[u]; }
-      float p1 = __shfl_up_sync(0xffffffffu, last, 1), p2 = __shfl_up_sync(0xffffffffu, last2, 1);
+      for (int u = 0; u < SPL; ++u) emit[u] = LP[(long)t * C + lab[u]];
+      float p1 = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1), p2 = __shfl_up_sync(0xffffffffu, a[SPL - 2], 1);
       if (lane == 0) { p1 = -INFINITY; p2 = -INFINITY; }
-      float na[CTC_MAXSPL];
+      float na[SPL];
 #pragma unroll
-      for (int u = 0; u < CTC_MAXSPL; ++u) {
-        if (u < spl) {
-          const float m1 = u >= 1 ? a[u >= 1 ? u - 1 : 0] : p1;
-          const float m2 = u >= 2 ? a[u >= 2 ? u - 2 : 0] : (u == 1 ? p1 : p2);
-          na[u] = (skip_a[u] ? lse3(a[u], m1, m2) : lse2(a[u], m1)) + emit[u];
-        }
+      for (int u = 0; u < SPL; ++u) {
+        const float m1 = u >= 1 ? a[u >= 1 ? u - 1 : 0] : p1;
+        const float m2 = u >= 2 ? a[u >= 2 ? u - 2 : 0] : (u == 1 ? p1 : p2);
+        na[u] = (skip[u] ? lse3(a[u], m1, m2) : lse2(a[u], m1)) + emit[u];
       }
 #pragma unroll
-      for (int u = 0; u < CTC_MAXSPL; ++u) {
-        const int s = lane * spl + u;
-        if (u < spl) {
-          a[u] = s < n ? na[u] : -INFINITY;
-          if (s < n) aw[(long)t * NS + s] = a[u];
-        }
+      for (int u = 0; u < SPL; ++u) {
+        const int s = lane * SPL + u;
+        a[u] = s < n ? na[u] : -INFINITY;
+        if (s < n) aw[(long)t * NS + s] = a[u];
       }
     }
     // log-likelihood = lse(alpha[T-1][n-1], alpha[T-1][n-2])
     float mine = -INFINITY;
 #pragma unroll
-    for (int u = 0; u < CTC_MAXSPL; ++u) {
-      const int s = lane * spl + u;
-      if (u < spl && (s == n - 1 || s == n - 2)) mine = lse2(mine, a[u]);
+    for (int u = 0; u < SPL; ++u) {
+      const int s = lane * SPL + u;
+      if (s == n - 1 || s == n - 2) mine = lse2(mine, a[u]);
     }
-    // combine across lanes in log space
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mine = lse2(mine, __shfl_xor_sync(0xffffffffu, mine, o));
-    ll = mine;
-  }
-  if (lane == 0) nll[b] = -ll;
-  const float gscale = gcoef / (float)(max(S, 1)) / (float)B;
-
-  // ---- beta + gradient ----
-  float be[CTC_MAXSPL];
+    if (lane == 0) nll[b] = -mine;
+  } else {
+    float* bw = beta_ws + (long)b * L * NS;
 #pragma unroll
-  for (int u = 0; u < CTC_MAXSPL; ++u) {
-    const int s = lane * spl + u;
-    be[u] = -INFINITY;
-    if (Tn > 0 && u < spl && s < n && s >= n - 2) be[u] = lpb[(long)(Tn - 1) * C + lab[u]];
-  }
-  for (int t = L - 1; t >= 0; --t) {
-    T* grow = grad + ((long)b * L + t) * ldg;
-    if (t >= Tn) {
-      for (int c = lane; c < ldg; c += 32) grow[c] = from_f32<T>(0.f);
-      continue;
+    for (int u = 0; u < SPL; ++u) {
+      const int s = lane * SPL + u;
+      a[u] = (s < n && s >= n - 2) ? LP[(long)(Tn - 1) * C + lab[u]] : -INFINITY;
+      if (s < n) bw[(long)(Tn - 1) * NS + s] = a[u];
     }
-    for (int c = lane; c < C; c += 32) occ[c] = 0.f;
-    __syncwarp();
+    for (int t = Tn - 2; t >= 0; --t) {
+      float emit[SPL];
 #pragma unroll
-    for (int u = 0; u < CTC_MAXSPL; ++u) {
-      const int s = lane * spl + u;
-      if (u < spl && s < n) {
-        const float v = aw[(long)t * NS + s] + be[u];
-        if (v > -INFINITY) atomicAdd(&occ[lab[u]], __expf(v - __ldg(lpb + (long)t * C + lab[u]) - ll));
-      }
-    }
-    __syncwarp();
-    for (int c = lane; c < ldg; c += 32) {
-      float g = 0.f;
-      if (c < C) g = (__expf(lpb[(long)t * C + c]) - occ[c]) * gscale;
-      grow[c] = from_f32<T>(g);
-    }
-    __syncwarp();
-    if (t > 0) {
-      float emit[CTC_MAXSPL];
-#pragma unroll
-      for (int u = 0; u < CTC_MAXSPL; ++u) emit[u] = (u < spl) ? __ldg(lpb + (long)(t - 1) * C + lab[u]) : 0.f;
-      float first = be[0], second = be[1];
-      float n1 = __shfl_down_sync(0xffffffffu, first, 1), n2 = __shfl_down_sync(0xffffffffu, second, 1);
+      for (int u = 0; u < SPL; ++u) emit[u] = LP[(long)t * C + lab[u]];
+      float n1 = __shfl_down_sync(0xffffffffu, a[0], 1), n2 = __shfl_down_sync(0xffffffffu, a[1], 1);
       if (lane == 31) { n1 = -INFINITY; n2 = -INFINITY; }
-      float nb[CTC_MAXSPL];
+      float nb[SPL];
 #pragma unroll
-      for (int u = 0; u < CTC_MAXSPL; ++u) {
-        if (u < spl) {
-          const float m1 = (u + 1 < spl) ? be[u + 1 < CTC_MAXSPL ? u + 1 : 0] : n1;
-          const float m2 = (u + 2 < spl) ? be[u + 2 < CTC_MAXSPL ? u + 2 : 0] : (u + 1 < spl ? n1 : n2);
-          nb[u] = (skip_b[u] ? lse3(be[u], m1, m2) : lse2(be[u], m1)) + emit[u];
-        }
+      for (int u = 0; u < SPL; ++u) {
+        const float m1 = (u + 1 < SPL) ? a[u + 1 < SPL ? u + 1 : 0] : n1;
+        const float m2 = (u + 2 < SPL) ? a[u + 2 < SPL ? u + 2 : 0] : (u + 1 < SPL ? n1 : n2);
+        nb[u] = (skip[u] ? lse3(a[u], m1, m2) : lse2(a[u], m1)) + emit[u];
       }
 #pragma unroll
-      for (int u = 0; u < CTC_MAXSPL; ++u) {
-        const int s = lane * spl + u;
-        if (u < spl) be[u] = s < n ? nb[u] : -INFINITY;
+      for (int u = 0; u < SPL; ++u) {
+        const int s = lane * SPL + u;
+        a[u] = s < n ? nb[u] : -INFINITY;
+        if (s < n) bw[(long)t * NS + s] = a[u];
       }
     }
+  }
+}
+
+// gradient w.r.t. the raw logits, one warp per (utterance, frame):
+//   g[c] = gscale_b * ( softmax[c] - sum_{s: label(s) = c} exp(alpha[t][s] + beta[t][s] - lp[t][c] - ll) ),  0 for t >= T_b
+template <typename T>
+__global__ void __launch_bounds__(256)
+ctc_grad_kernel(const float* __restrict__ lp, const long* __restrict__ targets, int tgt_pitch, const int* __restrict__ in_lens,
+                const int* __restrict__ tgt_lens, int L, int C, int blank, int NS, const float* __restrict__ alpha_ws,
+                const float* __restrict__ beta_ws, const float* __restrict__ nll, T* __restrict__ grad, long ldg, float gcoef, int B) {
+  extern __shared__ float occ_all[];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  float* occ = occ_all + wi * C;
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + wi;
+  if (row >= (long)B * L) return;
+  const int b = (int)(row / L), t = (int)(row - (long)b * L);
+  T* grow = grad + row * ldg;
+  const int Tn = min(in_lens[b], L);
+  if (t >= Tn) {
+    for (int c = lane; c < ldg; c += 32) grow[c] = from_f32<T>(0.f);
+    return;
+  }
+  const int S = tgt_lens[b];
+  const int n = 2 * S + 1;
+  const float ll = -nll[b];
+  const float gscale = gcoef / (float)(max(S, 1)) / (float)B;
+  const float* lpr = lp + row * C;
+  for (int c = lane; c < C; c += 32) occ[c] = 0.f;
+  __syncwarp();
+  const float* ar = alpha_ws + row * NS;
+  const float* br = beta_ws + row * NS;
+  for (int s = lane; s < n; s += 32) {
+    const int l = (s & 1) ? (int)targets[(long)b * tgt_pitch + (s >> 1)] : blank;
+    const float v = ar[s] + br[s];
+    if (v > -INFINITY) atomicAdd(&occ[l], __expf(v - lpr[l] - ll));
+  }
+  __syncwarp();
+  for (int c = lane; c < ldg; c += 32) {
+    float g = 0.f;
+    if (c < C) g = (__expf(lpr[c]) - occ[c]) * gscale;
+    grow[c] = from_f32<T>(g);
   }
 }
 
@@ -235,7 +252,7 @@ using namespace sst;
 
 extern "C" {
 
-/* logits: (B*L, ld) in dtype; lp_ws: float[B*L*C]; alpha_ws: float[B*L*(2*Smax+1)]; nll: float[B];
+/* logits: (B*L, ld) in dtype; lp_ws: float[B*L*C]; alpha_ws: float[2*B*L*(2*Smax+1)] (alpha, then beta); nll: float[B];
  * grad: (B*L, ldg) in dtype (columns >= C zeroed) = gcoef * d(mean_b nll_b/len_b)/d logits;  loss_out: float[1]. */
 int sst_ctc_loss(int logits_dtype, int grad_dtype, int B, int L, int C, int blank, const void* logits, int64_t ld,
                  const int64_t* targets, int Smax, const int32_t* in_lens, const int32_t* tgt_lens, float gcoef, float* lp_ws,
@@ -248,14 +265,40 @@ int sst_ctc_loss(int logits_dtype, int grad_dtype, int B, int L, int C, int blan
   const int NS = 2 * Smax + 1;
   if (logits_dtype == SST_F32) log_softmax_kernel<float><<<(int)((rows + 7) / 8), 256, 0, st>>>((const float*)logits, ld, lp_ws, rows, C);
   else log_softmax_kernel<__nv_bfloat16><<<(int)((rows + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)logits, ld, lp_ws, rows, C);
-  if (grad_dtype == SST_F32)
-    ctc_kernel<float><<<B, 32, C * sizeof(float), st>>>(lp_ws, (const long*)targets, Smax, in_lens, tgt_lens, L, C, blank, NS, alpha_ws,
-                                                        nll, (float*)grad, ldg, gcoef, B);
-  else
-    ctc_kernel<__nv_bfloat16><<<B, 32, C * sizeof(float), st>>>(lp_ws, (const long*)targets, Smax, in_lens, tgt_lens, L, C, blank, NS,
-                                                                alpha_ws, nll, (__nv_bfloat16*)grad, ldg, gcoef, B);
+  float* beta_ws = alpha_ws + rows * NS;
+  {
+    const size_t lp_bytes = (size_t)L * C * sizeof(float);
+    const bool in_smem = lp_bytes <= 200 * 1024;
+    const size_t sm = in_smem ? lp_bytes : 0;
+    const int spl = NS <= 64 ? 2 : NS <= 128 ? 4 : NS <= 256 ? 8 : 16;
+#define SST_CTC_LAUNCH(SPL_, SM_)                                                                                          \
+    do {                                                                                                                   \
+      if (SM_) cudaFuncSetAttribute(ctc_lattice_kernel<SPL_, SM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      ctc_lattice_kernel<SPL_, SM_><<<B, 128, sm, st>>>(lp_ws, (const long*)targets, Smax, in_lens, tgt_lens, L, C, blank, NS, \
+                                                        alpha_ws, beta_ws, nll);                                           \
+    } while (0)
+    if (in_smem) {
+      if (spl == 2) SST_CTC_LAUNCH(2, true); else if (spl == 4) SST_CTC_LAUNCH(4, true);
+      else if (spl == 8) SST_CTC_LAUNCH(8, true); else SST_CTC_LAUNCH(16, true);
+    } else {
+      if (spl == 2) SST_CTC_LAUNCH(2, false); else if (spl == 4) SST_CTC_LAUNCH(4, false);
+      else if (spl == 8) SST_CTC_LAUNCH(8, false); else SST_CTC_LAUNCH(16, false);
+    }
+#undef SST_CTC_LAUNCH
+  }
+  {
+    const int wpb = 8;
+    const int grid = (int)((rows + wpb - 1) / wpb);
+    const size_t sm = (size_t)wpb * C * sizeof(float);
+    if (grad_dtype == SST_F32)
+      ctc_grad_kernel<float><<<grid, wpb * 32, sm, st>>>(lp_ws, (const long*)targets, Smax, in_lens, tgt_lens, L, C, blank, NS, alpha_ws,
+                                                         beta_ws, nll, (float*)grad, ldg, gcoef, B);
+    else
+      ctc_grad_kernel<__nv_bfloat16><<<grid, wpb * 32, sm, st>>>(lp_ws, (const long*)targets, Smax, in_lens, tgt_lens, L, C, blank, NS,
+                                                                 alpha_ws, beta_ws, nll, (__nv_bfloat16*)grad, ldg, gcoef, B);
+  }
   ctc_finalize_kernel<<<1, 32, 0, st>>>(nll, tgt_lens, B, loss_out);
-  return check_launch("ctc_loss", 3);
+  return check_launch("ctc_loss", 4);
 }
 
 /* logits (rows, ld) with rows = B*S; loss = (1-eps)*CE(ignore_index, mean over non-ignored) + eps/S * sum(exp(logits)).

@@ -526,7 +526,7 @@ class Engine:
         out = torch.zeros(3, dtype=torch.float32, device=self.dev)
         Smax = ctc_targets.shape[1]
         lp_ws = self.empty(B * Lx * self.n_out_enc, dtype=torch.float32)
-        a_ws = self.empty(B * Lx * (2 * Smax + 1), dtype=torch.float32)
+        a_ws = self.empty(2 * B * Lx * (2 * Smax + 1), dtype=torch.float32)      # alpha and beta lattices
         nll = self.empty(B, dtype=torch.float32)
         has_dec = ctx.dec_logits is not None
         c_enc = alpha if has_dec else 1.0

@@ -52,6 +52,28 @@ def stage_of(name, n_enc, n_dec):
     return "conv"
 
 
+def prepare_batch(example):
+    """The host half of one training step (recognition_model.py:77, :85-87, :95-97) on a `collate_raw` dict
+    (read_emg.py:463-504): X = combine_fixed_length(raw_emg, 1600); decoder input/target = phonemes[:, :-1] / [:, 1:] padded
+    with 42; CTC target = phonemes without <S>/</S>.  Returns plain host tensors plus the python-side scalars."""
+    pad_seq = torch.nn.utils.rnn.pad_sequence
+    X = combine_fixed_length(example['raw_emg'], 200 * 8)
+    target = pad_seq(example['phonemes_int'], batch_first=True, padding_value=PAD)
+    tgt_in = target[:, :-1].contiguous()
+    tgt_out = target[:, 1:].contiguous()
+    nmax = target.shape[1]
+    ctc_lens = [n - 2 for n in example['phonemes_int_lengths']]
+    ctc_tgt = pad_seq([p[1:-1] for p in example['phonemes_int']], batch_first=True, padding_value=PAD).contiguous()
+    if ctc_tgt.shape[1] == 0:
+        ctc_tgt = torch.full((len(ctc_lens), 1), PAD, dtype=torch.int64)
+    host = dict(X=X, tgt_in=tgt_in, tgt_out=tgt_out.view(-1), ctc_tgt=ctc_tgt,
+                ctc_lens=torch.tensor(ctc_lens, dtype=torch.int32),
+                tgt_lens=torch.tensor([min(n, nmax - 1) for n in example['phonemes_int_lengths']], dtype=torch.int32))
+    host['lengths'] = list(example['lengths'])
+    host['n_valid'] = int(sum(min(n, nmax) - 1 for n in example['phonemes_int_lengths']))
+    return host
+
+
 class FlatState:
     def __init__(self, model):
         eng = model.engine()
@@ -186,23 +208,9 @@ class Trainer:
     # ---- host-side batch preparation (recognition_model.py:77,85-87,95-97) ------------------------------------------
     def prepare(self, example, pin=True):
         """collate_raw dict -> host tensors (pinned) ready for an async H2D copy."""
-        pad_seq = torch.nn.utils.rnn.pad_sequence
-        X = combine_fixed_length(example['raw_emg'], 200 * 8)
-        target = pad_seq(example['phonemes_int'], batch_first=True, padding_value=PAD)
-        tgt_in = target[:, :-1].contiguous()
-        tgt_out = target[:, 1:].contiguous()
-        nmax = target.shape[1]
-        ctc_lens = [n - 2 for n in example['phonemes_int_lengths']]
-        ctc_tgt = pad_seq([p[1:-1] for p in example['phonemes_int']], batch_first=True, padding_value=PAD).contiguous()
-        if ctc_tgt.shape[1] == 0:
-            ctc_tgt = torch.full((len(ctc_lens), 1), PAD, dtype=torch.int64)
-        host = dict(X=X, tgt_in=tgt_in, tgt_out=tgt_out.view(-1), ctc_tgt=ctc_tgt,
-                    ctc_lens=torch.tensor(ctc_lens, dtype=torch.int32),
-                    tgt_lens=torch.tensor([min(n, nmax - 1) for n in example['phonemes_int_lengths']], dtype=torch.int32))
+        host = prepare_batch(example)
         if pin and self.dev.type == "cuda":
-            host = {k: v.pin_memory() for k, v in host.items()}
-        host['lengths'] = list(example['lengths'])
-        host['n_valid'] = int(sum(min(n, nmax) - 1 for n in example['phonemes_int_lengths']))
+            host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
         return host
 
     def to_device(self, host):

@@ -161,9 +161,11 @@ int sst_attn_bwd(const SstAttnDesc* d, const void* q, const void* k, const void*
 /* ------------------------------------------------------------------------------------------------------------
  * Losses (recognition_model.py:93-107).
  *  sst_ctc_loss : log_softmax over C classes + CTC (blank = `blank`, reduction 'mean' = mean_b nll_b / max(len_b,1),
- *      zero_infinity False).  One warp per utterance runs the alpha and beta recursions in log space; the gradient is
- *      written directly w.r.t. the raw logits (softmax - occupancy), scaled by gcoef, zero for t >= in_lens[b].
- *      Workspaces: lp_ws float[B*L*C], alpha_ws float[B*L*(2*Smax+1)], nll float[B].  targets: int64 (B, Smax).
+ *      zero_infinity False).  Per utterance one warp runs the alpha and one the beta recursion in log space (lattice
+ *      states spread over the lanes, the utterance's log-probs staged in shared memory); the gradient is written
+ *      directly w.r.t. the raw logits (softmax - occupancy), scaled by gcoef, zero for t >= in_lens[b].
+ *      Workspaces: lp_ws float[B*L*C], alpha_ws float[2*B*L*(2*Smax+1)] (alpha then beta lattice), nll float[B].
+ *      targets: int64 (B, Smax).
  *  sst_ce_sumexp_loss : LabelSmoothingLoss.py:13-15 -- (1-eps)*CE(ignore_index, mean over kept) + eps/S*sum(exp(logits)),
  *      the sum running over every row including ignored ones; S = target length; gradient scaled by gcoef.
  *      row_ws float[2*rows].

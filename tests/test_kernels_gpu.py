@@ -245,7 +245,7 @@ def test_ctc_loss_and_grad(L, gdtype):
     ref = F.ctc_loss(lp, targets.to(DEV), in_lens, tgt_lens, blank=43)
     (0.7 * ref).backward()
     il = torch.tensor(in_lens, dtype=torch.int32, device=DEV); tl = torch.tensor(tgt_lens, dtype=torch.int32, device=DEV)
-    lp_ws = torch.empty(B * Lx * C, device=DEV); a_ws = torch.empty(B * Lx * (2 * Smax + 1), device=DEV)
+    lp_ws = torch.empty(B * Lx * C, device=DEV); a_ws = torch.empty(2 * B * Lx * (2 * Smax + 1), device=DEV)
     nll = torch.empty(B, device=DEV); grad = torch.full((B * Lx, ld), 3.0, device=DEV, dtype=gdtype); loss = torch.zeros(1, device=DEV)
     L.ctc_loss(L.F32, L.dt(grad), B, Lx, C, 43, logits, ld, targets.to(DEV), Smax, il, tl, 0.7, lp_ws, a_ws, nll, grad, ld, loss)
     assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
