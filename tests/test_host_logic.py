@@ -1,0 +1,174 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol include/sst.h declares, the host half of the
+training step (batch preparation, warm-up schedule, flat parameter order, gradient buckets) and the data-parallel
+gradient exchange on a world_size-2 gloo group."""
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+import sst_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+import sst_b200  # noqa: E402,F401
+from sst_b200 import lib as L  # noqa: E402
+from sst_b200 import train as T  # noqa: E402
+from sst_b200.synthetic import make_batch, lognormal_lengths  # noqa: E402
+from sst_b200.data_utils import combine_fixed_length, decollate_tensor  # noqa: E402
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "sst.h")).read()
+    return re.findall(r"^(?:int|long long|const char\*) (sst_\w+)\(", src, re.M)
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    names = declared_symbols()
+    assert len(names) >= 24
+    lib = L.lib()                       # raises SstError when libsst.so has not been built: there is no fallback
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert b"sm_100a" in lib.sst_version()
+    assert lib.sst_launch_count() == 0  # nothing was launched by loading
+
+
+def test_missing_device_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(L.SstError):
+        L.require_device()
+
+
+def test_prepare_batch_matches_reference_step_arithmetic():
+    """train.prepare_batch == recognition_model.py:77,85-87,95-97 as restated by the oracle."""
+    batch = O.synthetic_batch(seed=7, ragged=[70, 100, 29], tgt_lens=[9, 14, 5])
+    host = T.prepare_batch(batch)
+    X = O.combine_fixed_length(batch["raw_emg"])
+    tgt_in, tgt_out, ctc_tgt, ctc_lens = O.make_targets(batch)
+    assert torch.equal(host["X"], X) and host["X"].shape == (1, 1600, 8)
+    assert float(host["X"][0, -1, 0]) == 42.0               # tail padded with the VALUE 42 (data_utils.py:170)
+    assert torch.equal(host["tgt_in"], tgt_in) and torch.equal(host["tgt_out"], tgt_out.reshape(-1))
+    assert torch.equal(host["ctc_tgt"], ctc_tgt) and host["ctc_lens"].tolist() == ctc_lens
+    assert host["n_valid"] == int((tgt_out != 42).sum())
+    assert host["lengths"] == [70, 100, 29]
+    # decoder key lengths: number of non-pad tokens in tgt_in
+    assert host["tgt_lens"].tolist() == (tgt_in != 42).sum(1).tolist()
+
+
+def test_combine_and_decollate_round_trip():
+    g = torch.Generator().manual_seed(0)
+    parts = [torch.randn(n, 8, generator=g) for n in (800, 1234, 66)]
+    X = combine_fixed_length(parts, 1600)
+    assert X.shape == (2, 1600, 8)
+    flat = X.view(-1, 8)
+    assert torch.equal(flat[:2100], torch.cat(parts)) and bool((flat[2100:] == 42).all())
+    back = decollate_tensor(X, [800, 1234, 66])
+    for a, b in zip(back, parts):
+        assert torch.equal(a, b)
+    with pytest.raises(AssertionError):
+        decollate_tensor(X, [3000, 1000])                   # data_utils.py:182
+
+
+def test_synthetic_batch_contract():
+    b = make_batch(n_utt=3, frames=50, tgt_min=5, tgt_max=9, seed=1)
+    assert set(b) == {"raw_emg", "lengths", "phonemes_int", "phonemes_int_lengths"}
+    assert [t.shape for t in b["raw_emg"]] == [(400, 8)] * 3
+    for p, n in zip(b["phonemes_int"], b["phonemes_int_lengths"]):
+        assert int(p[0]) == 41 and int(p[-1]) == 40 and p.numel() == n and int(p[1:-1].max()) < 40
+    lens = lognormal_lengths(1000, seed=3)
+    assert min(lens) >= 100 and max(lens) <= 1500 and 380 < sum(lens) / 1000 < 620
+
+
+def test_lr_warmup_schedule_matches_reference():
+    class Dummy(T.Trainer):
+        def __init__(self):
+            self.lr_target, self.warmup, self.lr = 3e-4, 1500, 3e-4
+    tr = Dummy()
+    for it in (0, 1, 10, 1499, 1500, 5000):
+        tr.schedule_lr(it)
+        ref = O.lr_schedule(it)
+        if ref is not None:
+            assert tr.lr == pytest.approx(ref, rel=1e-12)
+    assert tr.lr == pytest.approx(3e-4)
+
+
+def _names(n_enc, n_dec):
+    cfg = O.make_cfg(n_enc=n_enc, n_dec=n_dec)
+    sd = O.synthetic_state_dict(dict(cfg, d_model=64, d_ff=128, n_heads=2), 0)
+    return O.trainable_names(sd, cfg), sd
+
+
+def test_backward_order_follows_gradient_completion():
+    names, _ = _names(2, 2)
+    order = T.backward_order(names, 2, 2)
+    assert sorted(order) == sorted(names)
+    stages = [T.stage_of(n, 2, 2) for n in order]
+    seq = ["decoder", "enc1", "enc0", "w_raw_in", "conv"]
+    idx = [seq.index(s) for s in stages]
+    assert idx == sorted(idx), "flat buffer must be laid out in backward-completion order"
+    assert order[0].startswith("w_aux") and order[-1].startswith("conv_blocks.0")
+
+
+class _FakeFlat:
+    def __init__(self, names, sd):
+        self.names = names
+        self.offsets, off = {}, 0
+        for n in names:
+            self.offsets[n] = off
+            off += (sd[n].numel() + 3) // 4 * 4
+        self.numel = off
+        self.g = torch.zeros(off)
+
+
+def test_gradient_buckets_partition_the_flat_buffer():
+    names, sd = _names(3, 1)
+    flat = _FakeFlat(T.backward_order(names, 3, 1), sd)
+    sync = T.GradSync(flat, 3, 1, bucket_bytes=64 << 10)
+    assert sync.buckets[0][0] == 0 and sync.buckets[-1][1] == flat.numel
+    for (s0, e0, st0), (s1, e1, st1) in zip(sync.buckets, sync.buckets[1:]):
+        assert e0 == s1 and e0 > s0
+        assert sync.stage_order.index(st0) <= sync.stage_order.index(st1)
+    assert len(sync.buckets) > 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    names, sd = _names(2, 1)
+    flat = _FakeFlat(T.backward_order(names, 2, 1), sd)
+    sync = T.GradSync(flat, 2, 1, bucket_bytes=32 << 10)
+    g = torch.Generator().manual_seed(100 + rank)
+    flat.g.copy_(torch.randn(flat.numel, generator=g))
+    mine = flat.g.clone()
+    sync.begin()
+    launched = []
+    for st in sync.stage_order:                 # Engine.backward announces the stages in this order
+        sync.on_stage(st)
+        launched.append(sync._next)
+    sync.finish()
+    others = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(others, mine)
+    want = sum(others) / world
+    q.put((rank, float((flat.g - want).abs().max()), launched, len(sync.buckets)))
+    dist.destroy_process_group()
+
+
+def test_gradsync_world2_gloo_averages_every_bucket_once():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + os.getpid() % 200
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, launched, nb in res:
+        assert err < 1e-6, "rank %d: reduced gradient differs from the mean over ranks" % rank
+        assert launched == sorted(launched) and launched[-1] == nb   # buckets fire in order, all of them by the last stage
