@@ -7,7 +7,7 @@
 namespace sst {
 
 struct AttnP {
-  int B, H, Lq, Lk, Lkp, dh;      // Lkp = Lk rounded up to 4: pitch of the dropout counter space (shared with attention_tc)
+  int B, H, Lq, Lk, Lkp, dh;      // Lkp = Lk rounded up to 8: pitch of the dropout counter space (shared with attention_tc)
   long ldq, ldk, ldv, ldo;
   int causal, mask_q_rows, R;
   float scale;
@@ -84,7 +84,7 @@ attn_fwd_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __restr
   if (lane == 0) { lse[row_id] = mx; lse[nrows + row_id] = __logf(sum); }
   for (int jj = lane; jj < nk; jj += 32) {
     float pr = sc[jj] * inv;
-    if (p.thr) pr = philox_keep(p.seed, (unsigned long long)row_id * p.Lkp + (lo + jj), p.thr) ? pr * p.dscale : 0.f;
+    if (p.thr) pr = philox_keep16(p.seed, (unsigned long long)row_id * p.Lkp + (lo + jj), p.thr) ? pr * p.dscale : 0.f;
     sc[jj] = pr;
   }
   __syncwarp();
@@ -139,7 +139,7 @@ attn_bwd_dq_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     const float s = make_logit(p, b, i, j, qk, qe, masked);
     const float pr = __expf((s - Lm) - Ll);
     float dp = dot_row(dos, v + ((long)b * p.Lk + j) * p.ldv + h * p.dh, p.dh);
-    if (p.thr) dp = philox_keep(p.seed, (unsigned long long)row_id * p.Lkp + j, p.thr) ? dp * p.dscale : 0.f;
+    if (p.thr) dp = philox_keep16(p.seed, (unsigned long long)row_id * p.Lkp + j, p.thr) ? dp * p.dscale : 0.f;
     const float ds = pr * (dp - dl);
     dsq[jj] = masked ? 0.f : ds * p.scale;
     dsb[jj] = inband ? ds : 0.f;
@@ -202,7 +202,7 @@ attn_bwd_dkv_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __r
     const float pr = __expf((s - lse[rid]) - lse[(long)p.B * p.H * p.Lq + rid]);
     float dp = dot_row(vs, dO + tokq * p.ldo + h * p.dh, p.dh);
     float keep = 1.f;
-    if (p.thr) keep = philox_keep(p.seed, (unsigned long long)rid * p.Lkp + j, p.thr) ? p.dscale : 0.f;
+    if (p.thr) keep = philox_keep16(p.seed, (unsigned long long)rid * p.Lkp + j, p.thr) ? p.dscale : 0.f;
     dp *= keep;
     const float ds = pr * (dp - delta[rid]);
     pw[ii] = pr * keep;
@@ -224,11 +224,11 @@ attn_bwd_dkv_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __r
 
 static AttnP make_params(const SstAttnDesc& d, const int* q_lens, const int* k_lens) {
   AttnP p;
-  p.B = d.B; p.H = d.H; p.Lq = d.Lq; p.Lk = d.Lk; p.Lkp = (d.Lk + 3) & ~3; p.dh = d.dh;
+  p.B = d.B; p.H = d.H; p.Lq = d.Lq; p.Lk = d.Lk; p.Lkp = (d.Lk + 7) & ~7; p.dh = d.dh;
   p.ldq = d.ldq; p.ldk = d.ldk; p.ldv = d.ldv; p.ldo = d.ldo;
   p.causal = d.causal; p.mask_q_rows = d.mask_q_rows; p.R = d.rel_dist;
   p.scale = d.scale;
-  p.thr = d.drop_p > 0.f ? drop_threshold(d.drop_p) : 0u;
+  p.thr = d.drop_p > 0.f ? drop_threshold16(d.drop_p) : 0u;
   p.dscale = d.drop_p < 1.f ? 1.f / (1.f - d.drop_p) : 0.f;
   p.seed = d.seed;
   p.q_lens = q_lens; p.k_lens = k_lens;

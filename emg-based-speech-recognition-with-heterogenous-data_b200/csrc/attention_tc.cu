@@ -6,7 +6,7 @@
 //     S  (128 x 64)  = Q K^T            tcgen05.mma, accumulator in TMEM columns [0, 64)
 //     PB (128 x 192) = Q E_win^T        the relative-position logits against the 191 embedding rows the tile can touch
 //                                       (E_win = rows [j0-i0-127+R-1, +192) of E[h]); TMEM columns [64, 256)
-// then one thread per query row reads its S row and its PB window from TMEM.  The reference's pad/view "skew"
+// then the threads (one query row x CW keys each, attention_tc.cuh) read S and their PB window from TMEM.  The reference's pad/view "skew"
 // (transformer.py:383-395) becomes a per-lane register barrel shift: bias[i][j] = PB[i][(j-j0) - (i-i0) + 127]; the
 // warp-uniform part of the shift is folded into the tcgen05.ld column address, the lane part (0..31) is five
 // predicated select stages.  Masks are SET to -1e8 and the bias ADDED exactly as the reference does,
@@ -18,15 +18,19 @@
 
 namespace sst {
 
-template <int DH>
-__global__ void __launch_bounds__(128, 1)
+template <int DH, int NSPLIT>
+__global__ void __launch_bounds__(128 * NSPLIT, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmE, const attn_tc::AttnTcParams p) {
   using namespace attn_tc;
+  using SP = Split<NSPLIT>;
+  constexpr int CW = SP::CW;
   constexpr int KS = DH / 16;                    // k-steps of the q.k / q.E contractions
   constexpr int NATOM = (DH + 63) / 64;          // 64-column (128-byte) swizzle atoms per row of q / k / E / v
   constexpr int Q_ATOM = BM * 128, K_ATOM = BN * 128, E_ATOM = PBW * 128, V_GRP = BN * 128;
+  constexpr int OC = DH / NSPLIT;                // accumulator columns each thread of a row looks after
   constexpr uint32_t TM_S = 0, TM_PB = 64, TM_O = 256;
+  static_assert(OC % 8 == 0, "head dim must split into x8 TMEM granules");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -38,9 +42,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + BM * 128);
   uint64_t* bar_q = bars, *bar_ke = bars + 1, *bar_v = bars + 2 /* [2] */, *bar_s = bars + 4, *bar_o = bars + 5;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  float* sred = reinterpret_cast<float*>(bars + 8);          // [NSPLIT][128] row-statistic exchange between column groups
 
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int li = threadIdx.x;
+  const int q = w & 3, hf = w >> 2;
+  const int li = 32 * q + lane;
   const int i0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
   const int i = i0 + li;
   const bool leader = threadIdx.x == 0;
@@ -60,7 +66,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_base = (uint32_t)(w * 32) << 16;
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
 
   int t_lo, t_hi;
   key_tile_range(p, i0, t_lo, t_hi);
@@ -117,7 +123,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncwarp();
 
   const RowCtx rc = make_row_ctx(p, b, h, i);
-  float m_run = NEG_BIG, l_run = 0.f;
+  float m_run = NEG_BIG, l_run = 0.f;             // l_run: this thread's share (its CW columns) of the row sum
   uint32_t ph_s = 0, ph_ke = 1;
 
   for (int t = t_lo; t <= t_hi; ++t) {
@@ -127,31 +133,43 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (leader && t < t_hi) { load_ke(t + 1); load_v(t + 1); }
     __syncwarp();
 
-    float U[96];
-    tile_logits<false>(p, rc, tmem + TM_S + lane_base, tmem + TM_PB + lane_base, w, lane, t * BN, U);
+    float U[SP::WIN_LD];
+    uint32_t mbits;
+    const bool simple = tile_is_simple(p, rc, t * BN);
+    tile_logits<NSPLIT>(p, rc, tmem + TM_S + lane_base, tmem + TM_PB + lane_base, q, hf, lane, t * BN, simple, U, mbits);
 
     float mt = U[0];
 #pragma unroll
-    for (int x = 1; x < BN; ++x) mt = fmaxf(mt, U[x]);
+    for (int x = 1; x < CW; ++x) mt = fmaxf(mt, U[x]);
+    sred[hf * 128 + li] = mt;
+    ptx::named_bar_sync(1 + q, 32 * NSPLIT);       // the NSPLIT warps that share this lane quarter
+#pragma unroll
+    for (int g = 0; g < NSPLIT; ++g) mt = fmaxf(mt, sred[g * 128 + li]);
     const float m_new = fmaxf(m_run, mt);
     const float alpha = __expf(m_run - m_new);
     float sum = 0.f;
 #pragma unroll
-    for (int x = 0; x < BN; ++x) { U[x] = __expf(U[x] - m_new); sum += U[x]; }
+    for (int x = 0; x < CW; ++x) { U[x] = __expf(U[x] - m_new); sum += U[x]; }
     l_run = l_run * alpha + sum;
     m_run = m_new;
-    if (p.thr) apply_dropout(p, rc, t * BN, U);
-    store_row_bf16_sw128(ptx::smem_u32(sP), li, U);
+    if (p.thr) {
+      float keep[CW];
+      dropout_keep<NSPLIT>(p, rc, t * BN, hf, keep);
+#pragma unroll
+      for (int x = 0; x < CW; ++x) U[x] *= keep[x];
+    }
+    store_cols_bf16_sw128<CW>(ptx::smem_u32(sP), li, CW * hf, U);
 
     if (t > t_lo && __any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll
-      for (int c = 0; c < DH / 32; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(tmem + TM_O + c * 32 + lane_base, r);
+      for (int c = 0; c < OC / 8; ++c) {
+        uint32_t r[8];
+        const uint32_t ta = tmem + TM_O + hf * OC + c * 8 + lane_base;
+        ptx::tmem_ld_32x32b_x8(ta, r);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int x = 0; x < 32; ++x) r[x] = __float_as_uint(__uint_as_float(r[x]) * alpha);
-        ptx::tmem_st_32x32b_x32(tmem + TM_O + c * 32 + lane_base, r);
+        for (int x = 0; x < 8; ++x) r[x] = __float_as_uint(__uint_as_float(r[x]) * alpha);
+        ptx::tmem_st_32x32b_x8(ta, r);
       }
       ptx::tmem_st_wait();
     }
@@ -181,36 +199,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncwarp();
   }
 
+  // row sum = sum of the column groups' shares (the __syncthreads closing the last tile orders this reuse of sred)
+  sred[hf * 128 + li] = l_run;
+  ptx::named_bar_sync(1 + q, 32 * NSPLIT);
+  float l_tot = 0.f;
+#pragma unroll
+  for (int g = 0; g < NSPLIT; ++g) l_tot += sred[g * 128 + li];
+
   ptx::mbar_wait(bar_o, 0);
   ptx::tc_fence_after();
-  {
-    // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only rows that exist store
-    const bool valid = i < p.Lq;
-    const float inv = 1.f / l_run;
-    __nv_bfloat16* orow = p.o + ((long)b * p.Lq + i) * p.ldo + h * DH;
-#pragma unroll
-    for (int c = 0; c < DH / 32; ++c) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(tmem + TM_O + c * 32 + lane_base, r);
-      ptx::tmem_ld_wait();
-      if (valid) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 o4;
-          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o4);
-#pragma unroll
-          for (int x = 0; x < 4; ++x)
-            o2[x] = __floats2bfloat162_rn(__uint_as_float(r[g * 8 + 2 * x]) * inv, __uint_as_float(r[g * 8 + 2 * x + 1]) * inv);
-          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = o4;
-        }
-      }
-      __syncwarp();
-    }
-    if (valid) {
-      const long nrows = (long)p.B * p.H * p.Lq;
-      p.lse[rc.row_id] = m_run;
-      p.lse[nrows + rc.row_id] = __logf(l_run);
-    }
+  const bool valid = i < p.Lq;
+  tmem_row_to_global<OC>(tmem + TM_O + hf * OC + lane_base, p.o + ((long)b * p.Lq + i) * p.ldo + h * DH + hf * OC, 1.f / l_tot, valid);
+  if (valid && hf == 0) {
+    const long nrows = (long)p.B * p.H * p.Lq;
+    p.lse[rc.row_id] = m_run;
+    p.lse[nrows + rc.row_id] = __logf(l_tot);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -220,8 +223,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-int attn_fwd_tc_launch(const SstAttnDesc& d, const void* q, const void* k, const void* v, const void* E, const int* q_lens,
-                       const int* k_lens, void* o, float* lse, cudaStream_t st) {
+template <int NSPLIT>
+static int attn_fwd_tc_launch_n(const SstAttnDesc& d, const void* q, const void* k, const void* v, const void* E, const int* q_lens,
+                                const int* k_lens, void* o, float* lse, cudaStream_t st) {
   using namespace attn_tc;
   constexpr int DH = 96;
   AttnTcParams p = make_tc_params(d, q_lens, k_lens);
@@ -238,16 +242,24 @@ int attn_fwd_tc_launch(const SstAttnDesc& d, const void* q, const void* k, const
     tmE = tmK;
   }
   constexpr int NATOM = (DH + 63) / 64;
-  constexpr int SMEM = NATOM * (BM * 128 + BN * 128 + PBW * 128 + 2 * BN * 128) + BM * 128 + 1024 + 128;
+  constexpr int SMEM = NATOM * (BM * 128 + BN * 128 + PBW * 128 + 2 * BN * 128) + BM * 128 + 1024 + 64 + NSPLIT * 128 * 4;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     SST_REQUIRE(e == cudaSuccess, SST_E_LAUNCH, "cudaFuncSetAttribute(attn_fwd_tc): %s", cudaGetErrorString(e));
     attr_done = true;
   }
   dim3 grid(cdiv(d.Lq, BM), d.H, d.B);
-  attn_fwd_tc_kernel<DH><<<grid, 128, SMEM, st>>>(tmQ, tmK, tmV, tmE, p);
+  attn_fwd_tc_kernel<DH, NSPLIT><<<grid, 128 * NSPLIT, SMEM, st>>>(tmQ, tmK, tmV, tmE, p);
   return check_launch("attn_fwd_tc");
+}
+
+int attn_tc_nsplit();   // attention_tc_bwd.cu: 2 or 4 column groups (SST_ATTN_NSPLIT, default 4)
+
+int attn_fwd_tc_launch(const SstAttnDesc& d, const void* q, const void* k, const void* v, const void* E, const int* q_lens,
+                       const int* k_lens, void* o, float* lse, cudaStream_t st) {
+  if (attn_tc_nsplit() == 2) return attn_fwd_tc_launch_n<2>(d, q, k, v, E, q_lens, k_lens, o, lse, st);
+  return attn_fwd_tc_launch_n<4>(d, q, k, v, E, q_lens, k_lens, o, lse, st);
 }
 
 }  // namespace sst

@@ -1,6 +1,11 @@
 // Shared pieces of the tensor-core attention kernels (attention_tc.cu forward, attention_tc_bwd.cu backward):
 // tile geometry, the per-row logit evaluation (mask SET -1e8, relative-position bias via the register barrel shift),
 // dropout and the swizzled shared-memory stores that turn register rows into tcgen05 operands.
+//
+// Thread mapping (all three kernels): a (128 query x 64 key) tile lives in TMEM with the query row on the lane axis.
+// Warp w reads lane quarter q = w & 3 (the only one tcgen05.ld lets it touch) and column group hf = w >> 2: with
+// NSPLIT column groups a thread owns CW = 64 / NSPLIT consecutive keys of ONE query row, so 4 * NSPLIT warps share a
+// tile (more warps per scheduler hide the TMEM-load / MUFU / Philox latencies of the per-element math).
 #pragma once
 #include "sst_common.cuh"
 #include "sst_ptx.cuh"
@@ -12,17 +17,17 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long cols, long rows, l
 
 namespace attn_tc {
 
-constexpr int BM = 128;            // query rows per tile  (TMEM lanes, one thread each)
+constexpr int BM = 128;            // query rows per tile  (TMEM lanes)
 constexpr int BN = 64;             // keys per tile
 constexpr int PBW = 192;           // relative offsets a (BM x BN) tile can touch: BM + BN - 1 = 191, padded to the MMA N step
 constexpr float NEG_MASK = -1e8f;  // the reference's masked_fill / out-of-range value (transformer.py:181-196, :354-357)
 constexpr float NEG_BIG = -3.0e38f;  // keys that do not exist (j >= Lk): excluded from the softmax altogether
 
 struct AttnTcParams {
-  int B, H, Lq, Lk, Lkp;           // Lkp = Lk rounded up to 4: pitch of the dropout counter space
+  int B, H, Lq, Lk, Lkp;           // Lkp = Lk rounded up to 8: pitch of the dropout counter space
   int causal, mask_q_rows, R, band;
   float scale;
-  uint32_t thr; float dscale; unsigned long long seed;
+  uint32_t thr; float dscale; unsigned long long seed;   // thr: 16-bit keep threshold (0 = no dropout)
   const int* q_lens; const int* k_lens;
   __nv_bfloat16* o; long ldo;
   float* lse;
@@ -35,11 +40,11 @@ struct AttnTcParams {
 inline AttnTcParams make_tc_params(const SstAttnDesc& d, const int* q_lens, const int* k_lens) {
   AttnTcParams p;
   memset(&p, 0, sizeof(p));
-  p.B = d.B; p.H = d.H; p.Lq = d.Lq; p.Lk = d.Lk; p.Lkp = (d.Lk + 3) & ~3;
+  p.B = d.B; p.H = d.H; p.Lq = d.Lq; p.Lk = d.Lk; p.Lkp = (d.Lk + 7) & ~7;
   p.causal = d.causal; p.mask_q_rows = d.mask_q_rows; p.R = d.rel_dist;
   p.band = d.rel_dist > 0 && d.Lk > d.rel_dist;
   p.scale = d.scale;
-  p.thr = d.drop_p > 0.f ? drop_threshold(d.drop_p) : 0u;
+  p.thr = d.drop_p > 0.f ? drop_threshold16(d.drop_p) : 0u;
   p.dscale = d.drop_p < 1.f ? 1.f / (1.f - d.drop_p) : 0.f;
   p.seed = d.seed;
   p.q_lens = q_lens; p.k_lens = k_lens;
@@ -91,89 +96,136 @@ __device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int
 template <int N, typename F>
 __device__ __forceinline__ void static_for(F&& f) { static_for_impl(f, std::make_integer_sequence<int, N>{}); }
 
-// U[x] <- U[x + K] for the lanes whose shift amount has bit K set
-template <int K>
-__device__ __forceinline__ void shift_stage(float (&U)[96], int s) {
-  const bool sh = (s & K) != 0;
-  static_for<BN + K - 1>([&](auto x) { U[x] = sh ? U[x + K] : U[x]; });
-}
+template <int NSPLIT> struct Split {
+  static constexpr int CW = BN / NSPLIT;                  // keys per thread
+  static constexpr int WIN = CW + 31;                     // bias window before the lane shift
+  static constexpr int WIN_LD = (WIN + 15) / 16 * 16;     // columns actually loaded (x16 granules)
+  static constexpr int THREADS = 128 * NSPLIT;
+  static_assert(CW == 16 || CW == 32, "one or two 16-column TMEM loads per thread");
+};
 
-// Relative-position logits of one query row against the 64 keys of the tile: U[lj] = PB[li][lj - li + 127], lj in [0, 64).
-// The thread's TMEM lane is row li = 32*w + lane.  Columns [96 - 32*w, 96 - 32*w + 96) of PB are loaded (warp-uniform
-// address), leaving a lane-dependent left shift by s = 31 - lane, done as five select stages (16, 8, 4, 2, 1).
-__device__ __forceinline__ void load_bias_window(uint32_t tPB /* incl. lane base */, int w, int lane, float (&U)[96]) {
-  const uint32_t cb = 96 - 32 * w;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    uint32_t r[32];
-    ptx::tmem_ld_32x32b_x32(tPB + cb + c * 32, r);
-    ptx::tmem_ld_wait();
-#pragma unroll
-    for (int x = 0; x < 32; ++x) U[c * 32 + x] = __uint_as_float(r[x]);
-  }
-  const int s = 31 - lane;
-  shift_stage<16>(U, s); shift_stage<8>(U, s); shift_stage<4>(U, s); shift_stage<2>(U, s); shift_stage<1>(U, s);
-}
-
-// logits of one query row against the tile's keys, exactly as MultiHeadAttention.forward builds them:
-//   s = masked ? -1e8 : q.k * scale;   s += |j - i| < R ? q.E[j-i+R-1] : -1e8   (transformer.py:177-204, Q3/Q9)
-// `masked_out[lj>>5]` bit (lj&31) reports that the q.k term was overwritten (its gradient is zero).
-template <bool WANT_MASK>
-__device__ __forceinline__ void tile_logits(const AttnTcParams& p, const RowCtx& rc, uint32_t tS, uint32_t tPB, int w, int lane,
-                                            int j0, float (&U)[96], uint32_t* masked_out = nullptr) {
-  if (p.R > 0) load_bias_window(tPB, w, lane, U);
-#pragma unroll
-  for (int c = 0; c < BN / 32; ++c) {
-    uint32_t r[32];
-    ptx::tmem_ld_32x32b_x32(tS + c * 32, r);
-    ptx::tmem_ld_wait();
-    uint32_t mbits = 0;
-#pragma unroll
-    for (int x = 0; x < 32; ++x) {
-      const int lj = c * 32 + x;
-      const int j = j0 + lj;
-      const bool masked = rc.rowmask || j >= rc.klen || (p.causal && j > rc.i);
-      float s = masked ? NEG_MASK : __uint_as_float(r[x]) * p.scale;
-      if (p.R > 0) {
-        const int rel = j - rc.i;
-        s += (rel > -p.R && rel < p.R) ? U[lj] : NEG_MASK;
-      }
-      U[lj] = j < p.Lk ? s : NEG_BIG;
-      if (WANT_MASK) mbits |= (masked ? 1u : 0u) << x;
-    }
-    if (WANT_MASK) masked_out[c] = mbits;
-  }
-}
-
-// dropout on the probabilities of one row (counter = row_id * Lkp + j, four keys per Philox block; the same stream as
-// the CUDA-core kernels of attention_simt.cu)
-__device__ __forceinline__ void apply_dropout(const AttnTcParams& p, const RowCtx& rc, int j0, float (&U)[96]) {
-  const unsigned long long base = ((unsigned long long)rc.row_id * p.Lkp + j0) >> 2;
-#pragma unroll
-  for (int g = 0; g < BN / 4; ++g) {
-    const Philox4 r = philox4x32_10(p.seed, base + g);
-    U[4 * g + 0] = r.x >= p.thr ? U[4 * g + 0] * p.dscale : 0.f;
-    U[4 * g + 1] = r.y >= p.thr ? U[4 * g + 1] * p.dscale : 0.f;
-    U[4 * g + 2] = r.z >= p.thr ? U[4 * g + 2] * p.dscale : 0.f;
-    U[4 * g + 3] = r.w >= p.thr ? U[4 * g + 3] * p.dscale : 0.f;
-  }
-}
-
-// One 64-element row (128 bytes of bf16) into a K-major SWIZZLE_128B operand tile: 16-byte chunk c of row r lives at
-// chunk c ^ (r & 7).  `sbase` must be 1024-byte aligned.
+// `n16` x16 loads issued back to back, one wait
 template <int N>
-__device__ __forceinline__ void store_row_bf16_sw128(uint32_t sbase, int row, const float (&U)[N]) {
-  static_assert(N >= BN, "row array too short");
+__device__ __forceinline__ void tmem_load_cols(uint32_t taddr, float (&out)[N]) {
+  static_assert(N % 16 == 0, "x16 granules");
+  uint32_t r[N / 16][16];
+#pragma unroll
+  for (int c = 0; c < N / 16; ++c) ptx::tmem_ld_32x32b_x16(taddr + c * 16, r[c]);
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < N / 16; ++c)
+#pragma unroll
+    for (int x = 0; x < 16; ++x) out[c * 16 + x] = __uint_as_float(r[c][x]);
+}
+
+// U[x] <- U[x + K] for the lanes whose shift amount has bit K set
+template <int K, int CW, int N>
+__device__ __forceinline__ void shift_stage(float (&U)[N], int s) {
+  const bool sh = (s & K) != 0;
+  static_for<CW + K - 1>([&](auto x) { U[x] = sh ? U[x + K] : U[x]; });
+}
+
+// Relative-position logits of one query row against the thread's CW keys: U[x] = PB[li][lj - li + 127], lj = CW*hf + x.
+// Row li = 32*q + lane.  Columns [96 - 32*q + CW*hf, + WIN) of PB are loaded (warp-uniform address), leaving a
+// lane-dependent left shift by s = 31 - lane, done as five select stages (16, 8, 4, 2, 1).
+template <int NSPLIT>
+__device__ __forceinline__ void load_bias_window(uint32_t tPB /* incl. lane base */, int q, int hf, int lane,
+                                                 float (&U)[Split<NSPLIT>::WIN_LD]) {
+  constexpr int CW = Split<NSPLIT>::CW;
+  tmem_load_cols(tPB + (uint32_t)(96 - 32 * q + CW * hf), U);
+  const int s = 31 - lane;
+  shift_stage<16, CW>(U, s); shift_stage<8, CW>(U, s); shift_stage<4, CW>(U, s); shift_stage<2, CW>(U, s); shift_stage<1, CW>(U, s);
+}
+
+// logits of one query row against the thread's keys, exactly as MultiHeadAttention.forward builds them:
+//   s = masked ? -1e8 : q.k * scale;   s += |j - i| < R ? q.E[j-i+R-1] : -1e8   (transformer.py:177-204, Q3/Q9)
+// Bit x of `mbits` reports that the q.k term of key x was overwritten (its gradient is zero).
+// `simple` (warp-uniform): no causal mask, every key of the tile exists and is unpadded, no padded row in the warp.
+template <int NSPLIT>
+__device__ __forceinline__ void tile_logits(const AttnTcParams& p, const RowCtx& rc, uint32_t tS, uint32_t tPB, int q, int hf, int lane,
+                                            int j0, bool simple, float (&U)[Split<NSPLIT>::WIN_LD], uint32_t& mbits) {
+  constexpr int CW = Split<NSPLIT>::CW;
+  if (p.R > 0) load_bias_window<NSPLIT>(tPB, q, hf, lane, U);
+  float sv[CW];
+  tmem_load_cols(tS + (uint32_t)(CW * hf), sv);
+  const int jb = j0 + CW * hf;                          // first key of this thread
+  const uint32_t lim = (uint32_t)(2 * p.R - 1);
+  const int d0 = jb - rc.i + p.R - 1;                   // in band  <=>  (unsigned)(d0 + x) < 2R-1
+  mbits = 0;
+  if (simple) {
+#pragma unroll
+    for (int x = 0; x < CW; ++x) {
+      float s = sv[x] * p.scale;
+      if (p.R > 0) s += ((uint32_t)(d0 + x) < lim) ? U[x] : NEG_MASK;
+      U[x] = s;
+    }
+  } else {
+#pragma unroll
+    for (int x = 0; x < CW; ++x) {
+      const int j = jb + x;
+      const bool masked = rc.rowmask || j >= rc.klen || (p.causal && j > rc.i);
+      float s = masked ? NEG_MASK : sv[x] * p.scale;
+      if (p.R > 0) s += ((uint32_t)(d0 + x) < lim) ? U[x] : NEG_MASK;
+      U[x] = j < p.Lk ? s : NEG_BIG;
+      mbits |= (masked ? 1u : 0u) << x;
+    }
+  }
+}
+
+__device__ __forceinline__ bool tile_is_simple(const AttnTcParams& p, const RowCtx& rc, int j0) {
+  const bool mine = !p.causal && !rc.rowmask && (j0 + BN <= min(rc.klen, p.Lk));
+  return __all_sync(0xffffffffu, mine);
+}
+
+// keep factors (0 or 1/(1-pd)) of the thread's CW keys: counter = row_id * Lkp + j, eight keys per Philox block, the same
+// stream as the CUDA-core kernels of attention_simt.cu
+template <int NSPLIT>
+__device__ __forceinline__ void dropout_keep(const AttnTcParams& p, const RowCtx& rc, int j0, int hf, float (&keep)[Split<NSPLIT>::CW]) {
+  constexpr int CW = Split<NSPLIT>::CW;
+  const unsigned long long base = ((unsigned long long)rc.row_id * p.Lkp + j0 + CW * hf) >> 3;
+#pragma unroll
+  for (int g = 0; g < CW / 8; ++g) {
+    const Philox4 r = philox4x32_10(p.seed, base + g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) keep[g * 8 + e] = philox_lane16(r, e) >= p.thr ? p.dscale : 0.f;
+  }
+}
+
+// CW consecutive elements of one row (bf16) into a K-major SWIZZLE_128B operand tile whose rows are 64 elements
+// (128 bytes): 16-byte chunk c of row r lives at chunk c ^ (r & 7).  `sbase` must be 1024-byte aligned.
+template <int CW, int N>
+__device__ __forceinline__ void store_cols_bf16_sw128(uint32_t sbase, int row, int col0, const float (&U)[N]) {
+  static_assert(N >= CW, "row array too short");
   const uint32_t rbase = sbase + row * 128;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < CW / 8; ++c) {
     uint32_t w4[4];
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
       __nv_bfloat162 h2 = __floats2bfloat162_rn(U[c * 8 + 2 * x], U[c * 8 + 2 * x + 1]);
       w4[x] = *reinterpret_cast<uint32_t*>(&h2);
     }
-    ptx::st_shared_v4(rbase + ((uint32_t)(c ^ (row & 7)) << 4), w4[0], w4[1], w4[2], w4[3]);
+    ptx::st_shared_v4(rbase + ((uint32_t)(((col0 >> 3) + c) ^ (row & 7)) << 4), w4[0], w4[1], w4[2], w4[3]);
+  }
+}
+
+// TMEM accumulator row slice [c0, c0 + NC) -> bf16 global row (scaled); every lane loads (warp-collective), `valid` stores
+template <int NC>
+__device__ __forceinline__ void tmem_row_to_global(uint32_t taddr, __nv_bfloat16* dst, float mul, bool valid) {
+  static_assert(NC % 8 == 0, "x8 granules");
+#pragma unroll
+  for (int c = 0; c < NC / 8; ++c) {
+    uint32_t r[8];
+    ptx::tmem_ld_32x32b_x8(taddr + c * 8, r);
+    ptx::tmem_ld_wait();
+    if (valid) {
+      uint4 o4;
+      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o4);
+#pragma unroll
+      for (int x = 0; x < 4; ++x) o2[x] = __floats2bfloat162_rn(__uint_as_float(r[2 * x]) * mul, __uint_as_float(r[2 * x + 1]) * mul);
+      *reinterpret_cast<uint4*>(dst + c * 8) = o4;
+    }
+    __syncwarp();
   }
 }
 

@@ -12,6 +12,7 @@
 //        same S / PB / dP and per-row math, then, transposed so that M = head dim (padded to 128 TMEM lanes), N = keys:
 //        dV^T += dO^T P~        dK^T += Q^T (scale * dS[unmasked])      (A = dO / Q tiles read MN-major, B = P~ / dS tiles)
 #include "attention_tc.cuh"
+#include <stdlib.h>
 
 namespace sst {
 
@@ -46,32 +47,29 @@ __device__ __forceinline__ void issue_s_pb_dp(uint32_t tmem_s, uint32_t tmem_pb,
   }
 }
 
-// Per-row backward math of one tile.  In: U = logits, mbits = "q.k term masked" bits, (Lm, Ll) saved softmax statistics,
-// delta.  Out: U[lj] = dropped-out probability P~ (what multiplies dO in dV), W[lj] = dS (gradient w.r.t. the logit).
+// Per-row backward math of the thread's CW keys.  In: U = logits, (Lm, Ll) saved softmax statistics, delta.
+// Out: U[x] = dropped-out probability P~ (what multiplies dO in dV), W[x] = dS (gradient w.r.t. the logit).
+template <int NSPLIT>
 __device__ __forceinline__ void tile_backward_row(const AttnTcParams& p, const RowCtx& rc, uint32_t tDP /* incl. lane base */, int j0,
-                                                  float Lm, float Ll, float delta, float (&U)[96], float (&W)[BN]) {
-  const unsigned long long base = ((unsigned long long)rc.row_id * p.Lkp + j0) >> 2;
+                                                  int hf, float Lm, float Ll, float delta, float (&U)[Split<NSPLIT>::WIN_LD],
+                                                  float (&W)[Split<NSPLIT>::CW]) {
+  constexpr int CW = Split<NSPLIT>::CW;
+  tmem_load_cols(tDP + (uint32_t)(CW * hf), W);
+  if (p.thr) {
+    float keep[CW];
+    dropout_keep<NSPLIT>(p, rc, j0, hf, keep);
 #pragma unroll
-  for (int c = 0; c < BN / 32; ++c) {
-    uint32_t r[32];
-    ptx::tmem_ld_32x32b_x32(tDP + c * 32, r);
-    ptx::tmem_ld_wait();
+    for (int x = 0; x < CW; ++x) {
+      const float pr = __expf((U[x] - Lm) - Ll);
+      W[x] = pr * (W[x] * keep[x] - delta);
+      U[x] = pr * keep[x];
+    }
+  } else {
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      float keep[4] = {1.f, 1.f, 1.f, 1.f};
-      if (p.thr) {
-        const Philox4 rr = philox4x32_10(p.seed, base + c * 8 + g);
-        keep[0] = rr.x >= p.thr ? p.dscale : 0.f; keep[1] = rr.y >= p.thr ? p.dscale : 0.f;
-        keep[2] = rr.z >= p.thr ? p.dscale : 0.f; keep[3] = rr.w >= p.thr ? p.dscale : 0.f;
-      }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int x = g * 4 + e, lj = c * 32 + x;
-        const float pr = __expf((U[lj] - Lm) - Ll);
-        const float dp = __uint_as_float(r[x]) * keep[e];
-        W[lj] = pr * (dp - delta);
-        U[lj] = pr * keep[e];
-      }
+    for (int x = 0; x < CW; ++x) {
+      const float pr = __expf((U[x] - Lm) - Ll);
+      W[x] = pr * (W[x] - delta);
+      U[x] = pr;
     }
   }
 }
@@ -81,15 +79,18 @@ __device__ __forceinline__ void tile_backward_row(const AttnTcParams& p, const R
 // ------------------------------------------------------------------------------------------------------------------
 // kernel 1: dQ (and delta)
 // ------------------------------------------------------------------------------------------------------------------
-template <int DH>
-__global__ void __launch_bounds__(128, 1)
+template <int DH, int NSPLIT>
+__global__ void __launch_bounds__(128 * NSPLIT, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmE,
                       const __grid_constant__ CUtensorMap tmDO, const attn_tc::AttnTcParams p) {
   using namespace attn_tc;
+  using SP = Split<NSPLIT>;
+  constexpr int CW = SP::CW;
   constexpr int NATOM = (DH + 63) / 64;
   constexpr int Q_ATOM = BM * 128, K_ATOM = BN * 128, E_ATOM = PBW * 128;
   constexpr int REL_ATOMS = PBW / 64;
+  constexpr int OC = DH / NSPLIT;
   constexpr uint32_t TM_S = 0, TM_PB = 64, TM_DP = 256, TM_DQ = 320;
 
   extern __shared__ uint8_t smem_raw[];
@@ -103,10 +104,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRel + REL_ATOMS * Q_ATOM);
   uint64_t* bar_q = bars, *bar_ke = bars + 1, *bar_v = bars + 2 /* [2] */, *bar_s = bars + 4, *bar_dq = bars + 5;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  float* sdelta = reinterpret_cast<float*>(bars + 8);       // [128]
   static_assert(NATOM * K_ATOM == BM * 128, "the dS tile must fit one V buffer");
 
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int li = threadIdx.x;
+  const int q = w & 3, hf = w >> 2;
+  const int li = 32 * q + lane;
   const int i0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
   const int i = i0 + li;
   const bool leader = threadIdx.x == 0;
@@ -127,7 +130,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_base = (uint32_t)(w * 32) << 16;
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
 
   int t_lo, t_hi;
   key_tile_range(p, i0, t_lo, t_hi);
@@ -166,31 +169,36 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   // zero the relative-coordinate dS tile once: a row only ever writes its own 64 columns [127 - li, 191 - li)
   {
     const uint32_t rb = ptx::smem_u32(sRel);
-    for (int k = threadIdx.x; k < REL_ATOMS * Q_ATOM / 16; k += 128) ptx::st_shared_v4(rb + k * 16, 0u, 0u, 0u, 0u);
+    for (int k = threadIdx.x; k < REL_ATOMS * Q_ATOM / 16; k += SP::THREADS) ptx::st_shared_v4(rb + k * 16, 0u, 0u, 0u, 0u);
   }
-  // delta_i = dO_i . O_i, saved softmax statistics
+  // delta_i = dO_i . O_i (column group 0 computes and shares it), saved softmax statistics
   const RowCtx rc = make_row_ctx(p, b, h, i);
   float Lm = 0.f, Ll = 3.0e38f, delta = 0.f;       // rows that do not exist: p = exp(-inf) = 0
   if (valid) {
-    const __nv_bfloat16* orow = p.o + ((long)b * p.Lq + i) * p.ldo + h * DH;
-    const __nv_bfloat16* drow = p.dO + ((long)b * p.Lq + i) * p.ldo + h * DH;
-#pragma unroll
-    for (int c = 0; c < DH / 8; ++c) {
-      const uint4 a4 = *reinterpret_cast<const uint4*>(orow + c * 8), b4 = *reinterpret_cast<const uint4*>(drow + c * 8);
-      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a4);
-      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b4);
-#pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        const float2 fa = __bfloat1622float2(a2[x]), fb = __bfloat1622float2(b2[x]);
-        delta = fmaf(fa.x, fb.x, delta);
-        delta = fmaf(fa.y, fb.y, delta);
-      }
-    }
-    p.delta[rc.row_id] = delta;
     const long nrows = (long)p.B * p.H * p.Lq;
     Lm = p.lse[rc.row_id];
     Ll = p.lse[nrows + rc.row_id];
+    if (hf == 0) {
+      const __nv_bfloat16* orow = p.o + ((long)b * p.Lq + i) * p.ldo + h * DH;
+      const __nv_bfloat16* drow = p.dO + ((long)b * p.Lq + i) * p.ldo + h * DH;
+#pragma unroll
+      for (int c = 0; c < DH / 8; ++c) {
+        const uint4 a4 = *reinterpret_cast<const uint4*>(orow + c * 8), b4 = *reinterpret_cast<const uint4*>(drow + c * 8);
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a4);
+        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b4);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const float2 fa = __bfloat1622float2(a2[x]), fb = __bfloat1622float2(b2[x]);
+          delta = fmaf(fa.x, fb.x, delta);
+          delta = fmaf(fa.y, fb.y, delta);
+        }
+      }
+      p.delta[rc.row_id] = delta;
+    }
   }
+  if (hf == 0) sdelta[li] = delta;
+  __syncthreads();
+  delta = sdelta[li];
 
   const uint32_t qb = ptx::smem_u32(sQ), dob = ptx::smem_u32(sDO), kb = ptx::smem_u32(sK), eb = ptx::smem_u32(sE);
   if (leader) {
@@ -212,20 +220,22 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if (leader && t < t_hi) load_v(t + 1);
     __syncwarp();
 
-    float U[96], W[BN];
-    uint32_t mbits[BN / 32];
-    tile_logits<true>(p, rc, tmem + TM_S + lane_base, tmem + TM_PB + lane_base, w, lane, t * BN, U, mbits);
-    tile_backward_row(p, rc, tmem + TM_DP + lane_base, t * BN, Lm, Ll, delta, U, W);
+    float U[SP::WIN_LD], W[CW];
+    uint32_t mbits;
+    const bool simple = tile_is_simple(p, rc, t * BN);
+    tile_logits<NSPLIT>(p, rc, tmem + TM_S + lane_base, tmem + TM_PB + lane_base, q, hf, lane, t * BN, simple, U, mbits);
+    tile_backward_row<NSPLIT>(p, rc, tmem + TM_DP + lane_base, t * BN, hf, Lm, Ll, delta, U, W);
 
     // bias term: dS at its relative column c = lj - li + 127 (zero outside the band)
     if (p.R > 0) {
       const uint32_t rb = ptx::smem_u32(sRel) + li * 128;
-      const int c0 = (BM - 1) - li;
-      const int d0 = t * BN - i;                   // rel = d0 + lj
+      const int c0 = (BM - 1) - li + CW * hf;
+      const int d0 = t * BN + CW * hf - i + p.R - 1;
+      const uint32_t lim = (uint32_t)(2 * p.R - 1);
 #pragma unroll
-      for (int lj = 0; lj < BN; ++lj) {
-        const int c = c0 + lj, rel = d0 + lj;
-        const float v = (rel > -p.R && rel < p.R) ? W[lj] : 0.f;
+      for (int x = 0; x < CW; ++x) {
+        const int c = c0 + x;
+        const float v = ((uint32_t)(d0 + x) < lim) ? W[x] : 0.f;
         const uint32_t addr = rb + (uint32_t)(c >> 6) * Q_ATOM + ((uint32_t)(((c & 63) >> 3) ^ (li & 7)) << 4) + (uint32_t)(c & 7) * 2;
         const __nv_bfloat16 hv = __float2bfloat16_rn(v);
         asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&hv)) : "memory");
@@ -233,8 +243,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
     // q.k term: scale * dS where the term was not masked
 #pragma unroll
-    for (int lj = 0; lj < BN; ++lj) W[lj] = ((mbits[lj >> 5] >> (lj & 31)) & 1u) ? 0.f : W[lj] * p.scale;
-    store_row_bf16_sw128(ptx::smem_u32(sV + buf * NATOM * K_ATOM), li, W);
+    for (int x = 0; x < CW; ++x) W[x] = ((mbits >> x) & 1u) ? 0.f : W[x] * p.scale;
+    store_cols_bf16_sw128<CW>(ptx::smem_u32(sV + buf * NATOM * K_ATOM), li, CW * hf, W);
 
     ptx::fence_proxy_async();
     ptx::tc_fence_before();
@@ -272,27 +282,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
   ptx::mbar_wait(bar_dq, (uint32_t)((t_hi - t_lo) & 1));
   ptx::tc_fence_after();
-  {
-    __nv_bfloat16* qrow = p.dq + ((long)b * p.Lq + i) * p.ldq + h * DH;
-#pragma unroll
-    for (int c = 0; c < DH / 32; ++c) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(tmem + TM_DQ + c * 32 + lane_base, r);
-      ptx::tmem_ld_wait();
-      if (valid) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 o4;
-          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o4);
-#pragma unroll
-          for (int x = 0; x < 4; ++x)
-            o2[x] = __floats2bfloat162_rn(__uint_as_float(r[g * 8 + 2 * x]), __uint_as_float(r[g * 8 + 2 * x + 1]));
-          *reinterpret_cast<uint4*>(qrow + c * 32 + g * 8) = o4;
-        }
-      }
-      __syncwarp();
-    }
-  }
+  tmem_row_to_global<OC>(tmem + TM_DQ + hf * OC + lane_base, p.dq + ((long)b * p.Lq + i) * p.ldq + h * DH + hf * OC, 1.f, valid);
   ptx::tc_fence_before();
   __syncthreads();
   if (w == 0) {
@@ -304,12 +294,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 // ------------------------------------------------------------------------------------------------------------------
 // kernel 2: dK, dV
 // ------------------------------------------------------------------------------------------------------------------
-template <int DH>
-__global__ void __launch_bounds__(128, 1)
+template <int DH, int NSPLIT>
+__global__ void __launch_bounds__(128 * NSPLIT, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmE,
                        const __grid_constant__ CUtensorMap tmDO, const attn_tc::AttnTcParams p) {
   using namespace attn_tc;
+  using SP = Split<NSPLIT>;
+  constexpr int CW = SP::CW;
   constexpr int NATOM = (DH + 63) / 64;
   constexpr int Q_ATOM = BM * 128, K_ATOM = BN * 128, E_ATOM = PBW * 128;
   constexpr uint32_t TM_S = 0, TM_PB = 64, TM_DP = 256, TM_DV = 320, TM_DK = 384;
@@ -329,7 +321,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int li = threadIdx.x;
+  const int q = w & 3, hf = w >> 2;
+  const int li = 32 * q + lane;
   const int j0 = blockIdx.x * BN, h = blockIdx.y, b = blockIdx.z;
   const bool leader = threadIdx.x == 0;
 
@@ -348,7 +341,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_base = (uint32_t)(w * 32) << 16;
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
 
   int q_lo, q_hi;
   query_tile_range(p, j0, q_lo, q_hi);
@@ -400,14 +393,15 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     ph_s ^= 1u;
     ptx::tc_fence_after();
 
-    float U[96], W[BN];
-    uint32_t mbits[BN / 32];
-    tile_logits<true>(p, rc, tmem + TM_S + lane_base, tmem + TM_PB + lane_base, w, lane, j0, U, mbits);
-    tile_backward_row(p, rc, tmem + TM_DP + lane_base, j0, Lm, Ll, delta, U, W);
+    float U[SP::WIN_LD], W[CW];
+    uint32_t mbits;
+    const bool simple = tile_is_simple(p, rc, j0);
+    tile_logits<NSPLIT>(p, rc, tmem + TM_S + lane_base, tmem + TM_PB + lane_base, q, hf, lane, j0, simple, U, mbits);
+    tile_backward_row<NSPLIT>(p, rc, tmem + TM_DP + lane_base, j0, hf, Lm, Ll, delta, U, W);
 #pragma unroll
-    for (int lj = 0; lj < BN; ++lj) W[lj] = ((mbits[lj >> 5] >> (lj & 31)) & 1u) ? 0.f : W[lj] * p.scale;
-    store_row_bf16_sw128(pb, li, U);
-    store_row_bf16_sw128(dsb, li, W);
+    for (int x = 0; x < CW; ++x) W[x] = ((mbits >> x) & 1u) ? 0.f : W[x] * p.scale;
+    store_cols_bf16_sw128<CW>(pb, li, CW * hf, U);
+    store_cols_bf16_sw128<CW>(dsb, li, CW * hf, W);
 
     ptx::fence_proxy_async();
     ptx::tc_fence_before();
@@ -441,26 +435,23 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   ptx::mbar_wait(bar_acc, (uint32_t)((q_hi - q_lo) & 1));
   ptx::tc_fence_after();
   {
-    // TMEM lane = head-dim index d, column = key: transposed stores (a warp writes 32 consecutive d of one key row)
+    // TMEM lane = head-dim index d, column = key: transposed stores (a warp writes 32 consecutive d of one key row);
+    // column group hf stores keys [CW*hf, CW*hf + CW)
     const int dcol = li;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       __nv_bfloat16* out = which == 0 ? p.dv : p.dk;
       const long ld = which == 0 ? p.ldv : p.ldk;
+      float r[CW];
+      tmem_load_cols(tmem + (which == 0 ? TM_DV : TM_DK) + CW * hf + lane_base, r);
+      if (dcol < DH) {
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(tmem + (which == 0 ? TM_DV : TM_DK) + c * 32 + lane_base, r);
-        ptx::tmem_ld_wait();
-        if (dcol < DH) {
-#pragma unroll
-          for (int x = 0; x < 32; ++x) {
-            const int j = j0 + c * 32 + x;
-            if (j < p.Lk) out[((long)b * p.Lk + j) * ld + h * DH + dcol] = __float2bfloat16_rn(__uint_as_float(r[x]));
-          }
+        for (int x = 0; x < CW; ++x) {
+          const int j = j0 + CW * hf + x;
+          if (j < p.Lk) out[((long)b * p.Lk + j) * ld + h * DH + dcol] = __float2bfloat16_rn(r[x]);
         }
-        __syncwarp();
       }
+      __syncwarp();
     }
   }
   ptx::tc_fence_before();
@@ -471,9 +462,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   }
 }
 
-int attn_bwd_tc_launch(const SstAttnDesc& d, const void* q, const void* k, const void* v, const void* E, const int* q_lens,
-                       const int* k_lens, const void* o, const float* lse, const void* dO, void* dq, void* dk, void* dv,
-                       float* delta, cudaStream_t st) {
+template <int NSPLIT>
+static int attn_bwd_tc_launch_n(const SstAttnDesc& d, const void* q, const void* k, const void* v, const void* E, const int* q_lens,
+                                const int* k_lens, const void* o, const float* lse, const void* dO, void* dq, void* dk, void* dv,
+                                float* delta, cudaStream_t st) {
   using namespace attn_tc;
   constexpr int DH = 96;
   constexpr int NATOM = 2;
@@ -494,18 +486,38 @@ int attn_bwd_tc_launch(const SstAttnDesc& d, const void* q, const void* k, const
   } else {
     tmE = tmK;
   }
-  constexpr int SMEM_DQ = 2 * NATOM * BM * 128 + NATOM * BN * 128 + NATOM * PBW * 128 + 2 * NATOM * BN * 128 + (PBW / 64) * BM * 128 + 1024 + 128;
+  constexpr int SMEM_DQ = 2 * NATOM * BM * 128 + NATOM * BN * 128 + NATOM * PBW * 128 + 2 * NATOM * BN * 128 + (PBW / 64) * BM * 128 +
+                          1024 + 64 + 128 * 4;
   constexpr int SMEM_DKV = 2 * NATOM * BN * 128 + 2 * NATOM * BM * 128 + NATOM * PBW * 128 + 2 * BM * 128 + 1024 + 128;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<DH, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<DH, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV);
     SST_REQUIRE(e == cudaSuccess, SST_E_LAUNCH, "cudaFuncSetAttribute(attn_bwd_tc): %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  attn_bwd_dq_tc_kernel<DH><<<dim3(cdiv(d.Lq, BM), d.H, d.B), 128, SMEM_DQ, st>>>(tmQ, tmK, tmV, tmE, tmDO, p);
-  attn_bwd_dkv_tc_kernel<DH><<<dim3(cdiv(d.Lk, BN), d.H, d.B), 128, SMEM_DKV, st>>>(tmQ, tmK, tmV, tmE, tmDO, p);
+  attn_bwd_dq_tc_kernel<DH, NSPLIT><<<dim3(cdiv(d.Lq, BM), d.H, d.B), 128 * NSPLIT, SMEM_DQ, st>>>(tmQ, tmK, tmV, tmE, tmDO, p);
+  attn_bwd_dkv_tc_kernel<DH, NSPLIT><<<dim3(cdiv(d.Lk, BN), d.H, d.B), 128 * NSPLIT, SMEM_DKV, st>>>(tmQ, tmK, tmV, tmE, tmDO, p);
   return check_launch("attn_bwd_tc", 2);
+}
+
+// column groups per tile (threads = 128 * groups): 4 by default, SST_ATTN_NSPLIT=2 selects the 256-thread variant
+int attn_tc_nsplit() {
+  static int n = 0;
+  if (!n) {
+    const char* e = getenv("SST_ATTN_NSPLIT");
+    n = (e && e[0] == '2') ? 2 : 4;
+  }
+  return n;
+}
+
+int attn_bwd_tc_launch(const SstAttnDesc& d, const void* q, const void* k, const void* v, const void* E, const int* q_lens,
+                       const int* k_lens, const void* o, const float* lse, const void* dO, void* dq, void* dk, void* dv,
+                       float* delta, cudaStream_t st) {
+  if (attn_tc_nsplit() == 2)
+    return attn_bwd_tc_launch_n<2>(d, q, k, v, E, q_lens, k_lens, o, lse, dO, dq, dk, dv, delta, st);
+  return attn_bwd_tc_launch_n<4>(d, q, k, v, E, q_lens, k_lens, o, lse, dO, dq, dk, dv, delta, st);
 }
 
 }  // namespace sst

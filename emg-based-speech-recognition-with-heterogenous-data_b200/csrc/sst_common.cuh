@@ -82,4 +82,18 @@ __host__ __device__ __forceinline__ bool philox_keep(uint64_t seed, uint64_t idx
   return v >= thr;
 }
 
+// 16-bit variant used by the attention kernels (eight keep decisions per Philox block instead of four: the RNG is the
+// largest per-element cost of the fused softmax): element kept iff its 16-bit lane >= thr16, thr16 = round(p * 2^16).
+__host__ __device__ __forceinline__ uint32_t drop_threshold16(float p) {
+  double t = (double)p * 65536.0 + 0.5;
+  return t >= 65535.0 ? 0xffffu : (uint32_t)t;
+}
+__host__ __device__ __forceinline__ uint32_t philox_lane16(const Philox4& r, int sub) {
+  const uint32_t w = (sub >> 1) == 0 ? r.x : (sub >> 1) == 1 ? r.y : (sub >> 1) == 2 ? r.z : r.w;
+  return (sub & 1) ? (w >> 16) : (w & 0xffffu);
+}
+__host__ __device__ __forceinline__ bool philox_keep16(uint64_t seed, uint64_t idx, uint32_t thr16) {
+  return philox_lane16(philox4x32_10(seed, idx >> 3), (int)(idx & 7)) >= thr16;
+}
+
 }  // namespace sst
