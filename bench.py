@@ -252,6 +252,7 @@ def run_ours(args, w):
     with L.Profiler() as prof:
         resident_step(0)
         fam = prof.summary()
+        shapes = prof.summary(by_tag=True)
     tot_ms = sum(d["ms"] for d in fam.values())
     pk = peaks()
     kernels = {}
@@ -262,6 +263,10 @@ def run_ours(args, w):
         if d["bytes"] > 0:
             e["gbs"] = round(d["bytes"] / d["ms"] / 1e6, 1)
         kernels[k] = e
+    gemm_shapes = [{"shape": k, "ms": round(d["ms"], 3), "n": d["launches"], "tflops": round(d["flops"] / d["ms"] / 1e9, 1)}
+                   for k, d in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"]) if k.startswith("gemm")][:args.gemm_shapes]
+    other_shapes = [{"shape": k, "ms": round(d["ms"], 3), "n": d["launches"], "gbs": round(d["bytes"] / d["ms"] / 1e6, 1)}
+                    for k, d in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"]) if not k.startswith("gemm")][:args.gemm_shapes]
     dom = max(fam.items(), key=lambda kv: kv[1]["ms"])
     dk, dd = dom
     if dd["flops"] > 0:
@@ -296,6 +301,7 @@ def run_ours(args, w):
                                      "achieved_tflops": round(step_flops / ms_res / 1e9, 1), "peak": pk["tensor"],
                                      "frac": round(step_flops / ms_res / 1e9 / pk["tensor"], 4)},
             "kernels": kernels, "cpu_baseline": cpu,
+            **({"gemm_shapes": gemm_shapes, "other_shapes": other_shapes} if gemm_shapes else {}),
         }
         print(json.dumps(line))
     if world > 1:
@@ -311,6 +317,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm-shapes", type=int, default=0, help="also list the N most expensive GEMM shapes of a step")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload], name=args.workload)
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -121,7 +121,7 @@ gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, const SimtPar
       if (p.epilogue & SST_EPI_BIAS) v += p.bias[n];
       if (p.epilogue & SST_EPI_RELU) v = fmaxf(v, 0.f);
       if (p.epilogue & SST_EPI_DROPOUT)
-        v = philox_keep(p.seed, (unsigned long long)m * (unsigned long long)p.N + n, p.drop_thr) ? v * p.drop_scale : 0.f;
+        v = philox_keep16(p.seed, (unsigned long long)m * (unsigned long long)p.N + n, p.drop_thr) ? v * p.drop_scale : 0.f;
       if (p.epilogue & SST_EPI_MULMASK)
         v *= (ld_as_f32(p.aux, (long)m * p.ldaux + n, p.aux_dtype) > 0.f) ? p.mask_scale : 0.f;
       const long ci = out_row * p.ldc + n;
@@ -151,7 +151,7 @@ int launch_gemm_simt(const SstGemmDesc& d, const void* A, const void* B, void* C
   }
   p.epilogue = d.epilogue;
   p.alpha = d.alpha; p.mask_scale = d.mask_scale;
-  p.drop_thr = drop_threshold(d.drop_p);
+  p.drop_thr = drop_threshold16(d.drop_p);
   p.drop_scale = d.drop_p < 1.f ? 1.f / (1.f - d.drop_p) : 0.f;
   p.seed = d.seed;
   p.bias = reinterpret_cast<const float*>(bias);

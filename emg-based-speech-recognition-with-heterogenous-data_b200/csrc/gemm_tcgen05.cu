@@ -1,6 +1,7 @@
 // bf16 GEMM on 5th-gen tensor cores: TMA -> 128B-swizzled shared memory -> tcgen05.mma (accumulators in
 // TMEM, double buffered) -> tcgen05.ld epilogue.  Persistent, warp-specialised: warp 0 = TMA producer,
-// warp 1 = MMA issuer (one thread) + TMEM owner, warps 2-5 = epilogue (one TMEM lane quarter each).
+// warp 1 = MMA issuer (one thread) + TMEM owner, warps 2-9 = epilogue (TMEM lane quarter = warp & 3, two warps per
+// quarter splitting the tile's columns).
 //
 // One kernel covers every dense contraction of the hot path (include/sst.h, "GEMM family"):
 //   TN     : C = A[M,K] * B[N,K]^T, both K-major.  A may be read as up to three row-shifted column windows
@@ -15,7 +16,8 @@ namespace sst {
 
 constexpr int G_BM = 128;
 constexpr int G_BK = 64;
-constexpr int G_THREADS = 192;
+constexpr int G_EPI_WARPS = 8;                   // two per TMEM lane quarter, each takes half of the tile's columns
+constexpr int G_THREADS = 64 + 32 * G_EPI_WARPS;
 constexpr int G_A_BYTES = G_BM * G_BK * 2;   // 16 KiB
 
 struct GemmKParams {
@@ -80,7 +82,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-      for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 4); }
+      for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], G_EPI_WARPS); }
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -167,6 +169,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     // ================================ epilogue ====================================
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int cg = (warp - 2) >> 2;               // column group: chunks [cg * BN/64, (cg + 1) * BN/64)
     int acc = 0; uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       int m0, nb, kb0, kb1;
@@ -184,7 +187,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         out_row = (long)chunk * p.remap_T + t;
       }
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = cg * (BN / 64); c < (cg + 1) * (BN / 64); ++c) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + (uint32_t)(acc * BN + c * 32) + ((uint32_t)(q * 32) << 16);
         ptx::tmem_ld_32x32b_x32(taddr, r);
@@ -204,15 +207,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           }
           if (p.epilogue & SST_EPI_DROPOUT) {
-            // logical element index m*N + n; nbase and N are multiples of 4 on this path (checked on the host)
+            // logical element index m*N + n; nbase and N are multiples of 8 on this path (checked on the host); eight
+            // 16-bit keep lanes per Philox block (sst_common.cuh philox_keep16)
             const unsigned long long e0 = (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)nbase;
 #pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4) {
-              Philox4 rr = philox4x32_10(p.seed, (e0 >> 2) + i4);
-              v[i4 * 4 + 0] = rr.x >= p.drop_thr ? v[i4 * 4 + 0] * p.drop_scale : 0.f;
-              v[i4 * 4 + 1] = rr.y >= p.drop_thr ? v[i4 * 4 + 1] * p.drop_scale : 0.f;
-              v[i4 * 4 + 2] = rr.z >= p.drop_thr ? v[i4 * 4 + 2] * p.drop_scale : 0.f;
-              v[i4 * 4 + 3] = rr.w >= p.drop_thr ? v[i4 * 4 + 3] * p.drop_scale : 0.f;
+            for (int i8 = 0; i8 < 4; ++i8) {
+              const Philox4 rr = philox4x32_10(p.seed, (e0 >> 3) + i8);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[i8 * 8 + e] = philox_lane16(rr, e) >= p.drop_thr ? v[i8 * 8 + e] * p.drop_scale : 0.f;
             }
           }
           if (p.epilogue & SST_EPI_MULMASK) {
@@ -235,8 +237,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const long cb = out_row * p.ldc + nbase;
           if (p.atomic_out) {
             float* cp = reinterpret_cast<float*>(p.C) + cb;
+            if (ncols == 32 && (p.ldc & 3) == 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (i < ncols) atomicAdd(cp + i, v[i]);
+              for (int j = 0; j < 8; ++j)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + 4 * j), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                             "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (i < ncols) atomicAdd(cp + i, v[i]);
+            }
           } else if (p.out_f32) {
             float* cp = reinterpret_cast<float*>(p.C) + cb;
             if (ncols == 32 && (p.ldc & 3) == 0) {
@@ -342,9 +351,12 @@ static int launch_bn(const SstGemmDesc& d, const void* A, const void* B, GemmKPa
   const int sms = num_sms();
   int splits = 1;
   if (p.mode_mn) {
+    // split K (= tokens) until the machine is full, but keep >= 16 k-blocks per unit: every unit pays a pipeline fill and
+    // a (BM x BN) fp32 atomic epilogue
     splits = (2 * sms) / tiles;
+    const int max_by_k = p.num_kb / 16;
+    if (splits > max_by_k) splits = max_by_k;
     if (splits < 1) splits = 1;
-    if (splits > p.num_kb) splits = p.num_kb;
   }
   p.kb_per_split = cdiv(p.num_kb, splits);
   p.splits = cdiv(p.num_kb, p.kb_per_split);
@@ -405,18 +417,22 @@ int launch_gemm_tcgen05(const SstGemmDesc& d, const void* A, const void* B, void
   p.m_blks = cdiv(d.M, G_BM);
   p.epilogue = d.epilogue;
   p.alpha = d.alpha; p.mask_scale = d.mask_scale;
-  p.drop_thr = drop_threshold(d.drop_p);
+  p.drop_thr = drop_threshold16(d.drop_p);
   p.drop_scale = d.drop_p < 1.f ? 1.f / (1.f - d.drop_p) : 0.f;
   p.seed = d.seed;
   p.bias = reinterpret_cast<const float*>(bias);
   p.aux = aux; p.ldaux = d.ldaux; p.aux_f32 = d.aux_dtype == SST_F32;
   p.C = C; p.ldc = d.ldc; p.out_f32 = d.out_dtype == SST_F32;
   p.remap_P = d.remap_P; p.remap_T = d.remap_T; p.remap_j0 = d.remap_j0;
-  if (d.epilogue & SST_EPI_DROPOUT) SST_REQUIRE(d.N % 4 == 0, SST_E_ARG, "dropout epilogue needs N %% 4 == 0");
-  // 256-wide tiles when they still fill the machine, otherwise 128-wide ones
-  const long tiles256 = (long)p.m_blks * cdiv(d.N, 256);
-  if (d.N > 128 && (tiles256 >= num_sms() || d.N % 256 == 0 && p.mode_mn)) return launch_bn<256>(d, A, B, p, st);
-  return launch_bn<128>(d, A, B, p, st);
+  if (d.epilogue & SST_EPI_DROPOUT) SST_REQUIRE(d.N % 8 == 0, SST_E_ARG, "dropout epilogue needs N %% 8 == 0");
+  // tile width by wave quantisation: time ~ waves * BN; 256-wide tiles reuse the A tile twice as long, so 128 must win by 10 %
+  if (d.N <= 128) return launch_bn<128>(d, A, B, p, st);
+  if (p.mode_mn) return (d.N % 256 == 0) ? launch_bn<256>(d, A, B, p, st) : launch_bn<128>(d, A, B, p, st);
+  const long sms = num_sms();
+  const long t256 = (long)p.m_blks * cdiv(d.N, 256), t128 = (long)p.m_blks * cdiv(d.N, 128);
+  const long c256 = ((t256 + sms - 1) / sms) * 256, c128 = ((t128 + sms - 1) / sms) * 128;
+  if (c128 * 10 < c256 * 9) return launch_bn<128>(d, A, B, p, st);
+  return launch_bn<256>(d, A, B, p, st);
 }
 
 }  // namespace sst

@@ -66,10 +66,12 @@ class Profiler:
         global _profiler
         _profiler = self._prev
 
-    def summary(self):
+    def summary(self, by_tag=False):
         torch.cuda.synchronize()
         out = {}
-        for kind, flops, nbytes, e0, e1 in self.records:
+        for kind, flops, nbytes, e0, e1, tag in self.records:
+            if by_tag:
+                kind = kind + " " + tag
             d = out.setdefault(kind, dict(ms=0.0, launches=0, flops=0.0, bytes=0.0))
             d["ms"] += e0.elapsed_time(e1)
             d["launches"] += 1
@@ -82,10 +84,10 @@ _profiler = None
 
 
 class _scope:
-    __slots__ = ("kind", "flops", "bytes", "e0")
+    __slots__ = ("kind", "flops", "bytes", "e0", "tag")
 
-    def __init__(self, kind, flops=0.0, bytes=0.0):
-        self.kind, self.flops, self.bytes = kind, flops, bytes
+    def __init__(self, kind, flops=0.0, bytes=0.0, tag=""):
+        self.kind, self.flops, self.bytes, self.tag = kind, flops, bytes, tag
 
     def __enter__(self):
         if _profiler is not None:
@@ -96,7 +98,7 @@ class _scope:
         if _profiler is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            _profiler.records.append((self.kind, self.flops, self.bytes, self.e0, e1))
+            _profiler.records.append((self.kind, self.flops, self.bytes, self.e0, e1, self.tag))
 
 
 def dt(t):
@@ -147,7 +149,8 @@ def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, layout=GEMM_TN, bias=None, aux=None
     m_real = M * remap[1] / remap[0] if remap[0] > 0 else M        # halo rows of a remapped conv GEMM are not work
     tc = d.dtype == BF16 and not force_simt
     kind = ("gemm_tcgen05_wgrad" if layout == GEMM_NT_MN else "gemm_tcgen05") if tc else "gemm_cuda_core"
-    with _scope(kind, 2.0 * m_real * N * K, (m_real * K + N * K) * A.element_size() + m_real * N * Cout.element_size()):
+    tag = "%dx%dx%d seg%d epi%d %s" % (M, N, K, n_seg, epilogue, "f32out" if Cout.dtype == torch.float32 else "") if _profiler is not None else ""
+    with _scope(kind, 2.0 * m_real * N * K, (m_real * K + N * K) * A.element_size() + m_real * N * Cout.element_size(), tag):
         check(lib().sst_gemm(C.byref(d), ptr(A), ptr(B), ptr(Cout), ptr(bias), ptr(aux), stream()), "sst_gemm")
 
 
@@ -197,38 +200,38 @@ def attn_work(d):
 
 
 def attn_fwd(d, q, k, v, E, q_lens, k_lens, o, lse):
-    with _scope("attn_fwd", attn_work(d)[0] if _profiler is not None else 0.0):
+    with _scope("attn_fwd", attn_work(d)[0] if _profiler is not None else 0.0, tag="Lq%d Lk%d R%d" % (d.Lq, d.Lk, d.rel_dist)):
         check(lib().sst_attn_fwd(C.byref(d), ptr(q), ptr(k), ptr(v), ptr(E), ptr(q_lens), ptr(k_lens), ptr(o), ptr(lse),
                                  stream()), "sst_attn_fwd")
 
 
 def attn_bwd(d, q, k, v, E, q_lens, k_lens, o, lse, dO, dq, dk, dv, delta):
-    with _scope("attn_bwd", attn_work(d)[1] if _profiler is not None else 0.0):
+    with _scope("attn_bwd", attn_work(d)[1] if _profiler is not None else 0.0, tag="Lq%d Lk%d R%d" % (d.Lq, d.Lk, d.rel_dist)):
         check(lib().sst_attn_bwd(C.byref(d), ptr(q), ptr(k), ptr(v), ptr(E), ptr(q_lens), ptr(k_lens), ptr(o), ptr(lse),
                                  ptr(dO), ptr(dq), ptr(dk), ptr(dv), ptr(delta), stream()), "sst_attn_bwd")
 
 
 def layernorm_fwd(dtype, rows, D, x, r, drop_p, seed, gamma, beta, y, s_out, mean, rstd, eps=1e-5):
     # algorithmic bytes: read x, r; write y, s (saved pre-norm sum)
-    with _scope("layernorm_fwd", bytes=4.0 * rows * D * (2 if dtype == BF16 else 4)):
+    with _scope("layernorm_fwd", bytes=4.0 * rows * D * (2 if dtype == BF16 else 4), tag="rows%d" % rows):
         check(lib().sst_layernorm_fwd(dtype, _i64(rows), D, ptr(x), ptr(r), _f(drop_p), _u64(seed), ptr(gamma), ptr(beta),
                                       ptr(y), ptr(s_out), ptr(mean), ptr(rstd), _f(eps), stream()), "sst_layernorm_fwd")
 
 
 def layernorm_bwd(dtype, rows, D, dy, s, mean, rstd, gamma, ds, dr, drop_p, seed, dgamma, dbeta):
     # read dy, s; write ds (+ dr when dropout is on)
-    with _scope("layernorm_bwd", bytes=(3.0 + (1.0 if drop_p > 0 else 0.0)) * rows * D * (2 if dtype == BF16 else 4)):
+    with _scope("layernorm_bwd", bytes=(3.0 + (1.0 if drop_p > 0 else 0.0)) * rows * D * (2 if dtype == BF16 else 4), tag="rows%d" % rows):
         check(lib().sst_layernorm_bwd(dtype, _i64(rows), D, ptr(dy), ptr(s), ptr(mean), ptr(rstd), ptr(gamma), ptr(ds),
                                       ptr(dr), _f(drop_p), _u64(seed), ptr(dgamma), ptr(dbeta), stream()), "sst_layernorm_bwd")
 
 
 def colstats(dtype, x, rows, Cc, ld, stats):
-    with _scope("bn_colstats", bytes=1.0 * rows * Cc * (2 if dtype == BF16 else 4)):
+    with _scope("bn_colstats", bytes=1.0 * rows * Cc * (2 if dtype == BF16 else 4), tag="rows%d" % rows):
         check(lib().sst_colstats(dtype, ptr(x), _i64(rows), Cc, _i64(ld), ptr(stats), stream()), "sst_colstats")
 
 
 def colsum_accum(dtype, x, rows, Cc, ld, out):
-    with _scope("bias_colsum", bytes=1.0 * rows * Cc * (2 if dtype == BF16 else 4)):
+    with _scope("bias_colsum", bytes=1.0 * rows * Cc * (2 if dtype == BF16 else 4), tag="rows%d C%d" % (rows, Cc)):
         check(lib().sst_colsum_accum(dtype, ptr(x), _i64(rows), Cc, _i64(ld), ptr(out), stream()), "sst_colsum_accum")
 
 
@@ -240,7 +243,8 @@ def bn_finalize(stats, count, Cc, eps, momentum, mean, invstd, running_mean, run
 def bn_apply(dtype, n_chunks, T, Cc, xa, lda, sa, xb, ldb, sb, relu, out, lead, trail):
     """sa / sb = (mean, invstd, gamma, beta) tuples; xb / sb may be None."""
     nb = (None, None, None, None) if sb is None else sb
-    with _scope("bn_apply", bytes=(2.0 + (1.0 if xb is not None else 0.0)) * n_chunks * T * Cc * (2 if dtype == BF16 else 4)):
+    with _scope("bn_apply", bytes=(2.0 + (1.0 if xb is not None else 0.0)) * n_chunks * T * Cc * (2 if dtype == BF16 else 4),
+                tag="T%d %s" % (T, "2br" if xb is not None else "1br")):
         check(lib().sst_bn_apply(dtype, _i64(n_chunks), T, Cc, ptr(xa), _i64(lda), ptr(sa[0]), ptr(sa[1]), ptr(sa[2]), ptr(sa[3]),
                                  ptr(xb), _i64(ldb), ptr(nb[0]), ptr(nb[1]), ptr(nb[2]), ptr(nb[3]), int(relu), ptr(out),
                                  lead, trail, stream()), "sst_bn_apply")
@@ -251,7 +255,7 @@ def bn_bwd(dtype, n_chunks, T, Cc, dout, ld_dout, y, y_lead, y_trail, relu,
            xb, ldb, mean_b, invstd_b, gamma_b, dxb, ld_dxb, lead_b, trail_b, dgamma_b, dbeta_b, red):
     # two passes (reduce, apply): dout, y, xa (+xb) read twice; dxa (+dxb) written
     with _scope("bn_bwd", bytes=(2.0 * (3.0 + (1.0 if xb is not None else 0.0)) + 1.0 + (1.0 if xb is not None else 0.0))
-                * n_chunks * T * Cc * (2 if dtype == BF16 else 4)):
+                * n_chunks * T * Cc * (2 if dtype == BF16 else 4), tag="T%d %s" % (T, "2br" if xb is not None else "1br")):
         check(lib().sst_bn_bwd(dtype, _i64(n_chunks), T, Cc, ptr(dout), _i64(ld_dout), ptr(y), y_lead, y_trail, int(relu),
                                ptr(xa), _i64(lda), ptr(mean_a), ptr(invstd_a), ptr(gamma_a), ptr(dxa), _i64(ld_dxa), lead_a, trail_a,
                                ptr(dgamma_a), ptr(dbeta_a),

@@ -79,6 +79,40 @@ def check_grads_against_golden(z, meta, grads, tol, label="", slack=3.0, report=
     return worst
 
 
+def _philox4x32_10(seed, ctr):
+    """numpy Philox4x32-10 with the key/counter layout of csrc/sst_common.cuh; returns the four 32-bit outputs."""
+    M32 = np.uint64(0xFFFFFFFF)
+    c0 = ctr & M32
+    c1 = ctr >> np.uint64(32)
+    c2 = np.full_like(c0, 0x5353542D)
+    c3 = np.full_like(c0, 0x62323030)
+    k0 = np.uint64(seed & 0xFFFFFFFF)
+    k1 = np.uint64((seed >> 32) & 0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c0
+        p1 = np.uint64(0xCD9E8D57) * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & M32
+        hi1, lo1 = p1 >> np.uint64(32), p1 & M32
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0 = (k0 + np.uint64(0x9E3779B9)) & M32
+        k1 = (k1 + np.uint64(0xBB67AE85)) & M32
+    return c0, c1, c2, c3
+
+
+def philox_keep_mask16(seed, n_elems, p):
+    """Host mirror of csrc/sst_common.cuh philox_keep16(): eight 16-bit keep lanes per Philox block (LayerNorm residual
+    dropout, GEMM dropout epilogue, attention probabilities)."""
+    idx = np.arange(n_elems, dtype=np.uint64)
+    c = _philox4x32_10(seed, idx >> np.uint64(3))
+    sub = idx & np.uint64(7)
+    word = sub >> np.uint64(1)
+    w = np.where(word == 0, c[0], np.where(word == 1, c[1], np.where(word == 2, c[2], c[3])))
+    lane = np.where((sub & np.uint64(1)) == 1, w >> np.uint64(16), w & np.uint64(0xFFFF))
+    t = p * 65536.0 + 0.5
+    thr = 0xFFFF if t >= 65535.0 else int(t)
+    return torch.from_numpy(lane >= np.uint64(thr))
+
+
 def philox_keep_mask(seed, n_elems, p):
     """Host mirror of csrc/sst_common.cuh philox_keep(): keep[idx] for idx in [0, n_elems)."""
     idx = np.arange(n_elems, dtype=np.uint64)

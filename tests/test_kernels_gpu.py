@@ -46,8 +46,8 @@ def test_layernorm_fwd_bwd(L, dtype, p):
     # recover the dropout mask from s: s = x + keep*r/(1-p)
     sf = s.float()
     if p > 0:
-        from helpers import philox_keep_mask
-        keep = philox_keep_mask(77, rows * D, p).view(rows, D).to(DEV)
+        from helpers import philox_keep_mask16
+        keep = philox_keep_mask16(77, rows * D, p).view(rows, D).to(DEV)
         frac = keep.float().mean().item()
         assert abs(frac - (1 - p)) < 0.01
         s_ref = x.float() + torch.where(keep, r.float() / (1 - p), torch.zeros_like(sf))
