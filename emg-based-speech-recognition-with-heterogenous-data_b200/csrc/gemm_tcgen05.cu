@@ -175,9 +175,52 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int m0, nb, kb0, kb1;
       decode_unit(p, u, m0, nb, kb0, kb1);
       const int n0 = nb * BN;
+      const int m = m0 + q * 32 + lane;
+      // Epilogue inputs that do not depend on the accumulator are produced BEFORE waiting for it, i.e. under the MMA
+      // main loop: the dropout keep bits (Philox, eight 16-bit lanes per block) and the ReLU/dropout mask bits of `aux`.
+      uint32_t keep_bits[BN / 64], mask_bits[BN / 64];
+      if (p.epilogue & SST_EPI_DROPOUT) {
+#pragma unroll
+        for (int lc = 0; lc < BN / 64; ++lc) {
+          const int nbase = n0 + (cg * (BN / 64) + lc) * 32;
+          const unsigned long long e0 = (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)nbase;
+          uint32_t bits = 0;
+#pragma unroll
+          for (int i8 = 0; i8 < 4; ++i8) {
+            const Philox4 rr = philox4x32_10(p.seed, (e0 >> 3) + i8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) bits |= (philox_lane16(rr, e) >= p.drop_thr ? 1u : 0u) << (i8 * 8 + e);
+          }
+          keep_bits[lc] = bits;
+        }
+      }
+      if (p.epilogue & SST_EPI_MULMASK) {
+#pragma unroll
+        for (int lc = 0; lc < BN / 64; ++lc) {
+          const int nbase = n0 + (cg * (BN / 64) + lc) * 32;
+          uint32_t bits = 0;
+          if (m < p.M && nbase < p.N) {
+            const int ncols = min(32, p.N - nbase);
+            const long ab = (long)m * p.ldaux + nbase;
+            if (!p.aux_f32 && ncols == 32 && (p.ldaux & 7) == 0) {
+              const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + ab);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 w = __ldg(ap + j);
+                const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&w);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bits |= (__bfloat162float(h[i]) > 0.f ? 1u : 0u) << (j * 8 + i);
+              }
+            } else {
+              for (int i = 0; i < ncols; ++i)
+                bits |= (ld_as_f32(p.aux, ab + i, p.aux_f32 ? SST_F32 : SST_BF16) > 0.f ? 1u : 0u) << i;
+            }
+          }
+          mask_bits[lc] = bits;
+        }
+      }
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
-      const int m = m0 + q * 32 + lane;
       bool row_ok = m < p.M;
       long out_row = m;
       if (p.remap_P > 0) {
@@ -186,8 +229,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         row_ok = row_ok && t >= 0 && t < p.remap_T;
         out_row = (long)chunk * p.remap_T + t;
       }
-#pragma unroll 1
-      for (int c = cg * (BN / 64); c < (cg + 1) * (BN / 64); ++c) {
+#pragma unroll
+      for (int lc0 = 0; lc0 < BN / 64; ++lc0) {
+        const int c = cg * (BN / 64) + lc0;
         uint32_t r[32];
         const uint32_t taddr = tmem_base + (uint32_t)(acc * BN + c * 32) + ((uint32_t)(q * 32) << 16);
         ptx::tmem_ld_32x32b_x32(taddr, r);
@@ -207,32 +251,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           }
           if (p.epilogue & SST_EPI_DROPOUT) {
-            // logical element index m*N + n; nbase and N are multiples of 8 on this path (checked on the host); eight
-            // 16-bit keep lanes per Philox block (sst_common.cuh philox_keep16)
-            const unsigned long long e0 = (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)nbase;
+            const uint32_t kb = keep_bits[lc0];
 #pragma unroll
-            for (int i8 = 0; i8 < 4; ++i8) {
-              const Philox4 rr = philox4x32_10(p.seed, (e0 >> 3) + i8);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[i8 * 8 + e] = philox_lane16(rr, e) >= p.drop_thr ? v[i8 * 8 + e] * p.drop_scale : 0.f;
-            }
+            for (int i = 0; i < 32; ++i) v[i] = ((kb >> i) & 1u) ? v[i] * p.drop_scale : 0.f;
           }
           if (p.epilogue & SST_EPI_MULMASK) {
-            const long ab = (long)m * p.ldaux + nbase;
-            if (!p.aux_f32 && ncols == 32 && (p.ldaux & 7) == 0) {
-              const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + ab);
+            const uint32_t mb = mask_bits[lc0];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 w = __ldg(ap + j);
-                const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&w);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[j * 8 + i] *= (__bfloat162float(h[i]) > 0.f) ? p.mask_scale : 0.f;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < ncols) v[i] *= (ld_as_f32(p.aux, ab + i, p.aux_f32 ? SST_F32 : SST_BF16) > 0.f) ? p.mask_scale : 0.f;
-            }
+            for (int i = 0; i < 32; ++i) v[i] *= ((mb >> i) & 1u) ? p.mask_scale : 0.f;
           }
           const long cb = out_row * p.ldc + nbase;
           if (p.atomic_out) {

@@ -98,7 +98,7 @@ ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ r, T* __restrict__ 
 // ds = rstd * (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat));  dr = ds * keep/(1-p);
 // dgamma += sum_rows dy*xhat, dbeta += sum_rows dy  (per-lane register partials -> smem -> one atomic per block/column)
 template <typename T, int NV, bool EXACT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ s, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, const float* __restrict__ gamma, T* __restrict__ ds, T* __restrict__ dr,
               float* __restrict__ dgamma, float* __restrict__ dbeta, long rows, int D, uint32_t thr, float dscale,
@@ -597,9 +597,10 @@ int sst_layernorm_bwd(int dtype, int64_t rows, int D, const void* dy, const void
   const uint32_t thr = (dr != nullptr && drop_p > 0.f) ? drop_threshold16(drop_p) : 0u;
   if (thr == 0) dr = nullptr;
   const float dscale = drop_p < 1.f ? 1.f / (1.f - drop_p) : 0.f;
-  long blocks = (rows + 7) / 8;
-  long cap = (long)num_sms() * 6;
-  const int grid = (int)(blocks < cap ? blocks : cap);
+  // two resident blocks per SM and no more blocks than that: every block ends with 2*D global atomics (dgamma, dbeta)
+  long blocks = (rows + 63) / 64;
+  long cap = (long)num_sms() * 2;
+  const int grid = (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
   const size_t smem = (size_t)2 * D * sizeof(float);
 #define SST_LN_BWD(T_, NV_, EX_)                                                                                             \
   ln_bwd_kernel<T_, NV_, EX_><<<grid, 256, smem, st>>>((const T_*)dy, (const T_*)s, mean, rstd, gamma, (T_*)ds, (T_*)dr, dgamma, dbeta, \

@@ -52,6 +52,7 @@ class Engine:
         self.force_simt = False
         self._packed_version = None
         self._bn_scratch = torch.empty(3 * self.D, dtype=torch.float64, device=self.dev)
+        self._side = None                  # side stream for work that can run under the decoder (CTC)
         assert self.D % 64 == 0 and self.dh % 8 == 0
 
     # ------------------------------------------------------------------------------------------------ utils
@@ -506,12 +507,17 @@ class Engine:
     def dec_head(self, x_dec, M):
         return self._linear_fwd(x_dec, M, "w_out", bias=self.P["w_out.bias"], out_dtype=torch.float32, ldc=self.LDH)
 
-    def forward(self, x_raw, lengths, y=None, tgt_lens=None, training=True, seed=0):
-        """Model.forward_training (architecture.py:101-139).  Returns (enc_logits (B*L, 64) fp32, dec_logits (B*S, 64) fp32 | None, ctx)."""
+    def forward(self, x_raw, lengths, y=None, tgt_lens=None, training=True, seed=0, ctc=None):
+        """Model.forward_training (architecture.py:101-139).  Returns (enc_logits (B*L, 64) fp32, dec_logits (B*S, 64) fp32 | None, ctx).
+        `ctc` = (targets (B, Smax) int64, target lengths int32, coefficient): start the CTC loss + gradient on the side stream as
+        soon as the encoder logits exist, so that its serial alpha/beta recursion runs under the decoder forward."""
         x_enc, ctx = self.encode(x_raw, lengths, training, seed)
         B, Lmax = ctx.B, ctx.Lmax
         ctx.enc_logits = self.enc_head(x_enc, B * Lmax)
         ctx.dec_logits = None
+        ctx.loss_out = torch.zeros(3, dtype=torch.float32, device=self.dev)
+        if ctc is not None:
+            self._ctc_async(ctx, *ctc)
         if y is not None and self.n_dec >= 0 and y.numel() > 0:
             if tgt_lens is None:
                 tgt_lens = (y != PAD).sum(1).to(torch.int32)
@@ -519,20 +525,45 @@ class Engine:
             ctx.dec_logits = self.dec_head(x_dec, B * y.shape[1])
         return ctx.enc_logits, ctx.dec_logits, ctx
 
+    def _ctc(self, ctx, ctc_targets, ctc_tgt_lens, coef):
+        B, Lx = ctx.B, ctx.Lmax
+        Smax = ctc_targets.shape[1]
+        ctx.ctc_ws = (self.empty(B * Lx * self.n_out_enc, dtype=torch.float32),
+                      self.empty(2 * B * Lx * (2 * Smax + 1), dtype=torch.float32),      # alpha and beta lattices
+                      self.empty(B, dtype=torch.float32))
+        ctx.d_enc_logits = self.empty(B * Lx, self.LDH)
+        L.ctc_loss(L.F32, self.dt, B, Lx, self.n_out_enc, self.n_out_enc - 1, ctx.enc_logits, self.LDH, ctc_targets, Smax, ctx.lens,
+                   ctc_tgt_lens, coef, ctx.ctc_ws[0], ctx.ctc_ws[1], ctx.ctc_ws[2], ctx.d_enc_logits, self.LDH, ctx.loss_out[2:])
+
+    def _ctc_async(self, ctx, ctc_targets, ctc_tgt_lens, coef):
+        """CTC on the side stream; every tensor it touches stays referenced by ctx until the main stream has joined."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        main = torch.cuda.current_stream()
+        # allocate on the main stream (its caching-allocator pool), run on the side stream
+        B, Lx = ctx.B, ctx.Lmax
+        Smax = ctc_targets.shape[1]
+        ctx.ctc_ws = (self.empty(B * Lx * self.n_out_enc, dtype=torch.float32),
+                      self.empty(2 * B * Lx * (2 * Smax + 1), dtype=torch.float32),
+                      self.empty(B, dtype=torch.float32))
+        ctx.d_enc_logits = self.empty(B * Lx, self.LDH)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            L.ctc_loss(L.F32, self.dt, B, Lx, self.n_out_enc, self.n_out_enc - 1, ctx.enc_logits, self.LDH, ctc_targets, Smax, ctx.lens,
+                       ctc_tgt_lens, coef, ctx.ctc_ws[0], ctx.ctc_ws[1], ctx.ctc_ws[2], ctx.d_enc_logits, self.LDH, ctx.loss_out[2:])
+            ctx.ctc_done = torch.cuda.Event()
+            ctx.ctc_done.record(self._side)
+
     def losses(self, ctx, ctc_targets, ctc_tgt_lens, dec_target, n_valid, alpha, eps_ls=0.1, want_grad=True):
         """recognition_model.py:93-107 on the saved logits.  Writes d(loss)/d(logits) (compute dtype, pitch 64) into ctx and
         returns a float32[3] device tensor (loss, loss_dec, loss_enc)."""
-        B, Lx = ctx.B, ctx.Lmax
-        out = torch.zeros(3, dtype=torch.float32, device=self.dev)
-        Smax = ctc_targets.shape[1]
-        lp_ws = self.empty(B * Lx * self.n_out_enc, dtype=torch.float32)
-        a_ws = self.empty(2 * B * Lx * (2 * Smax + 1), dtype=torch.float32)      # alpha and beta lattices
-        nll = self.empty(B, dtype=torch.float32)
+        B = ctx.B
+        out = ctx.loss_out
         has_dec = ctx.dec_logits is not None
-        c_enc = alpha if has_dec else 1.0
-        ctx.d_enc_logits = self.empty(B * Lx, self.LDH)
-        L.ctc_loss(L.F32, self.dt, B, Lx, self.n_out_enc, self.n_out_enc - 1, ctx.enc_logits, self.LDH, ctc_targets, Smax, ctx.lens,
-                   ctc_tgt_lens, c_enc, lp_ws, a_ws, nll, ctx.d_enc_logits, self.LDH, out[2:])
+        if ctx.get("ctc_done") is not None:
+            torch.cuda.current_stream().wait_event(ctx.ctc_done)        # started in forward() on the side stream
+        else:
+            self._ctc(ctx, ctc_targets, ctc_tgt_lens, alpha if has_dec else 1.0)
         if has_dec:
             S = ctx.S
             rows = B * S

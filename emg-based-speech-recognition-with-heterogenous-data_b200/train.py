@@ -234,7 +234,8 @@ class Trainer:
         has_dec = eng.n_dec > 0
         _, _, ctx = eng.forward(X, dev_batch['lengths'], dev_batch['tgt_in'] if has_dec else None,
                                 dev_batch['tgt_lens'] if has_dec else None, training=True,
-                                seed=self.seed * 1000003 + self.batch_idx)
+                                seed=self.seed * 1000003 + self.batch_idx,
+                                ctc=(dev_batch['ctc_tgt'], dev_batch['ctc_lens'], self.alpha if has_dec else 1.0))
         losses = eng.losses(ctx, dev_batch['ctc_tgt'], dev_batch['ctc_lens'], dev_batch['tgt_out'] if has_dec else None,
                             dev_batch['n_valid'], self.alpha, self.eps_ls)
         will_step = self.sum_batch_size >= self.batch_size_grad
