@@ -330,8 +330,9 @@ class Model(nn.Module):
                 raise L.SstError("memory must be the tensor returned by the part='encoder' call")
             y = y.contiguous()
             self.tgt_key_padding_mask = self.create_tgt_padding_mask(y)
-            tgt_lens = (y != self.pad).sum(1).to(torch.int32)
+            # search-time prefixes are generated, not padded: a PAD id may sit anywhere, so mask per position (:174,:178-183)
+            tgt_pad = self.tgt_key_padding_mask.to(torch.uint8).contiguous()
             seeds = Engine._Seeds(self._next_seed())
-            x_dec = eng.decode(y, tgt_lens, mem, self._mem_lens, B, Lm, self.training, seeds)
+            x_dec = eng.decode(y, None, mem, self._mem_lens, B, Lm, self.training, seeds, tgt_pad=tgt_pad)
             logits = eng.dec_head(x_dec, B * y.shape[1])
             return self._unpad_logits(logits, B, y.shape[1], eng.n_out_dec)

@@ -13,6 +13,7 @@ struct AttnP {
   float scale;
   uint32_t thr; float dscale; unsigned long long seed;
   const int* q_lens; const int* k_lens;
+  const uint8_t* q_pad; const uint8_t* k_pad;
 };
 
 template <typename T>
@@ -29,7 +30,8 @@ __device__ __forceinline__ float dot_row(const float* __restrict__ a_smem, const
 
 // logit of (i, j) given the already computed q.k and q.E dots; `masked` reports whether the q.k term was overwritten.
 __device__ __forceinline__ float make_logit(const AttnP& p, int b, int i, int j, float qk, float qe, bool& masked) {
-  masked = (p.causal && j > i) || (p.k_lens && j >= p.k_lens[b]) || (p.mask_q_rows && p.q_lens && i >= p.q_lens[b]);
+  masked = (p.causal && j > i) || (p.k_lens && j >= p.k_lens[b]) || (p.mask_q_rows && p.q_lens && i >= p.q_lens[b]) ||
+           (p.k_pad && p.k_pad[(long)b * p.Lk + j]) || (p.mask_q_rows && p.q_pad && p.q_pad[(long)b * p.Lq + i]);
   float s = masked ? -1e8f : qk * p.scale;
   if (p.R > 0) {
     int rel = j - i;
@@ -232,6 +234,7 @@ static AttnP make_params(const SstAttnDesc& d, const int* q_lens, const int* k_l
   p.dscale = d.drop_p < 1.f ? 1.f / (1.f - d.drop_p) : 0.f;
   p.seed = d.seed;
   p.q_lens = q_lens; p.k_lens = k_lens;
+  p.q_pad = d.q_pad; p.k_pad = d.k_pad;
   return p;
 }
 

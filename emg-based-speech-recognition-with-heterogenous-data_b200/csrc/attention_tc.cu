@@ -2,7 +2,8 @@
 // include/sst.h on tcgen05, TMA-fed.  Replaces MultiHeadAttention.forward between the projections
 // (transformer.py:177-208) and LearnedRelativePositionalEmbedding (transformer.py:260-403).
 //
-// One CTA = 128 query rows of one (batch, head); key tiles of 64.  Per key tile, issued by one thread:
+// One CTA = 128 query rows of one (batch, head); key tiles of 64.  4*NSPLIT compute warps + 1 issuer warp (one thread
+// drives TMA and tcgen05.mma from mbarriers).  Per key tile the issuer launches:
 //     S  (128 x 64)  = Q K^T            tcgen05.mma, accumulator in TMEM columns [0, 64)
 //     PB (128 x 192) = Q E_win^T        the relative-position logits against the 191 embedding rows the tile can touch
 //                                       (E_win = rows [j0-i0-127+R-1, +192) of E[h]); TMEM columns [64, 256)
@@ -13,18 +14,22 @@
 // online softmax over key tiles, Philox dropout on the probabilities, P (bf16) goes to 128B-swizzled shared memory and
 //     O (128 x dh) += P V               accumulator in TMEM columns [256, 256+dh), rescaled in TMEM when a row max moves.
 // Only key tiles that intersect the band |i-j| < R are visited (exact: everything outside has probability 0 in fp32).
+// Pipeline: K/E/V tiles are double-buffered in shared memory; the compute warps release the S/PB accumulators as soon
+// as they have copied their slices to registers ("s_free"), so the issuer runs tile t+1's S/PB MMAs under tile t's
+// exp / dropout / P-store work; P(t) and the O rescale are handed back through "p_ready", PV(t) completion through "pv".
 // Backward = two kernels of the same shape (dQ per query tile; dK/dV per key tile), see attention_tc_bwd.cu.
 #include "attention_tc.cuh"
 
 namespace sst {
 
 template <int DH, int NSPLIT>
-__global__ void __launch_bounds__(128 * NSPLIT, 1)
+__global__ void __launch_bounds__(128 * NSPLIT + 32, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmE, const attn_tc::AttnTcParams p) {
   using namespace attn_tc;
   using SP = Split<NSPLIT>;
   constexpr int CW = SP::CW;
+  constexpr int NW = 4 * NSPLIT;                 // compute warps
   constexpr int KS = DH / 16;                    // k-steps of the q.k / q.E contractions
   constexpr int NATOM = (DH + 63) / 64;          // 64-column (128-byte) swizzle atoms per row of q / k / E / v
   constexpr int Q_ATOM = BM * 128, K_ATOM = BN * 128, E_ATOM = PBW * 128, V_GRP = BN * 128;
@@ -35,27 +40,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + NATOM * Q_ATOM;
-  uint8_t* sE = sK + NATOM * K_ATOM;
-  uint8_t* sV = sE + NATOM * E_ATOM;             // two buffers
+  uint8_t* sK = sQ + NATOM * Q_ATOM;             // [2]
+  uint8_t* sE = sK + 2 * NATOM * K_ATOM;         // [2]
+  uint8_t* sV = sE + 2 * NATOM * E_ATOM;         // [2]
   uint8_t* sP = sV + 2 * NATOM * V_GRP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + BM * 128);
-  uint64_t* bar_q = bars, *bar_ke = bars + 1, *bar_v = bars + 2 /* [2] */, *bar_s = bars + 4, *bar_o = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-  float* sred = reinterpret_cast<float*>(bars + 8);          // [NSPLIT][128] row-statistic exchange between column groups
+  uint64_t* bar_q = bars, *bar_ke = bars + 1 /* [2] */, *bar_v = bars + 3 /* [2] */, *bar_s = bars + 5, *bar_sfree = bars + 6,
+           *bar_p = bars + 7, *bar_pv = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  float* sred = reinterpret_cast<float*>(bars + 10);         // [2][NSPLIT][128] row-statistic exchange between column groups
 
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = w & 3, hf = w >> 2;
-  const int li = 32 * q + lane;
   const int i0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
-  const int i = i0 + li;
-  const bool leader = threadIdx.x == 0;
 
   if (w == 0) {
     if (lane == 0) {
       ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
       if (p.R > 0) ptx::prefetch_tmap(&tmE);
-      for (int k = 0; k < 6; ++k) ptx::mbar_init(&bars[k], 1);
+      for (int k = 0; k < 6; ++k) ptx::mbar_init(&bars[k], 1);      // q, ke[2], v[2], s: one producer each
+      ptx::mbar_init(bar_sfree, NW);
+      ptx::mbar_init(bar_p, NW);
+      ptx::mbar_init(bar_pv, 1);
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -66,154 +71,174 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
 
   int t_lo, t_hi;
   key_tile_range(p, i0, t_lo, t_hi);
 
-  const uint32_t ke_bytes = NATOM * K_ATOM + (p.R > 0 ? NATOM * E_ATOM : 0);
-  auto load_ke = [&](int t) {
-    ptx::mbar_arrive_expect_tx(bar_ke, ke_bytes);
+  if (w == NW) {
+    // ============================================ issuer (one thread) ============================================
+    if (lane == 0) {
+      const uint32_t ke_bytes = NATOM * K_ATOM + (p.R > 0 ? NATOM * E_ATOM : 0);
+      auto load_ke = [&](int t) {
+        const int st = (t - t_lo) & 1;
+        ptx::mbar_arrive_expect_tx(&bar_ke[st], ke_bytes);
 #pragma unroll
-    for (int a = 0; a < NATOM; ++a) ptx::tma_load_2d(sK + a * K_ATOM, &tmK, bar_ke, h * DH + a * 64, b * p.Lk + t * BN);
-    if (p.R > 0) {
-      const int e0 = (t * BN - i0) - (BM - 1) + (p.R - 1);
+        for (int a = 0; a < NATOM; ++a)
+          ptx::tma_load_2d(sK + (st * NATOM + a) * K_ATOM, &tmK, &bar_ke[st], h * DH + a * 64, b * p.Lk + t * BN);
+        if (p.R > 0) {
+          const int e0 = (t * BN - i0) - (BM - 1) + (p.R - 1);
 #pragma unroll
-      for (int a = 0; a < NATOM; ++a) ptx::tma_load_2d(sE + a * E_ATOM, &tmE, bar_ke, a * 64, h * (2 * p.R - 1) + e0);
-    }
-  };
-  auto load_v = [&](int t) {
-    const int buf = (t - t_lo) & 1;
-    ptx::mbar_arrive_expect_tx(&bar_v[buf], NATOM * V_GRP);
+          for (int a = 0; a < NATOM; ++a)
+            ptx::tma_load_2d(sE + (st * NATOM + a) * E_ATOM, &tmE, &bar_ke[st], a * 64, h * (2 * p.R - 1) + e0);
+        }
+      };
+      auto load_v = [&](int t) {
+        const int st = (t - t_lo) & 1;
+        ptx::mbar_arrive_expect_tx(&bar_v[st], NATOM * V_GRP);
 #pragma unroll
-    for (int a = 0; a < NATOM; ++a)
-      ptx::tma_load_2d(sV + (buf * NATOM + a) * V_GRP, &tmV, &bar_v[buf], h * DH + a * 64, b * p.Lk + t * BN);
-  };
-  auto issue_s = [&]() {          // S = Q K^T and PB = Q E_win^T for the tile whose K / E are in shared memory
-    const uint32_t qb = ptx::smem_u32(sQ), kb = ptx::smem_u32(sK), eb = ptx::smem_u32(sE);
-    const uint32_t id_s = ptx::make_idesc_bf16(BM, BN, 0, 0), id_pb = ptx::make_idesc_bf16(BM, PBW, 0, 0);
+        for (int a = 0; a < NATOM; ++a)
+          ptx::tma_load_2d(sV + (st * NATOM + a) * V_GRP, &tmV, &bar_v[st], h * DH + a * 64, b * p.Lk + t * BN);
+      };
+      auto issue_s = [&](int st) {   // S = Q K^T and PB = Q E_win^T from stage `st`
+        const uint32_t qb = ptx::smem_u32(sQ), kb = ptx::smem_u32(sK + st * NATOM * K_ATOM), eb = ptx::smem_u32(sE + st * NATOM * E_ATOM);
+        const uint32_t id_s = ptx::make_idesc_bf16(BM, BN, 0, 0), id_pb = ptx::make_idesc_bf16(BM, PBW, 0, 0);
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      const uint32_t off = (ks >> 2), in = (ks & 3) * 32;
-      ptx::umma_bf16(tmem + TM_S, ptx::make_smem_desc_sw128(qb + off * Q_ATOM + in, 0, 1024),
-                     ptx::make_smem_desc_sw128(kb + off * K_ATOM + in, 0, 1024), id_s, ks > 0);
-    }
-    if (p.R > 0) {
+        for (int ks = 0; ks < KS; ++ks) {
+          const uint32_t off = (ks >> 2), in = (ks & 3) * 32;
+          ptx::umma_bf16(tmem + TM_S, ptx::make_smem_desc_sw128(qb + off * Q_ATOM + in, 0, 1024),
+                         ptx::make_smem_desc_sw128(kb + off * K_ATOM + in, 0, 1024), id_s, ks > 0);
+        }
+        if (p.R > 0) {
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const uint32_t off = (ks >> 2), in = (ks & 3) * 32;
-        ptx::umma_bf16(tmem + TM_PB, ptx::make_smem_desc_sw128(qb + off * Q_ATOM + in, 0, 1024),
-                       ptx::make_smem_desc_sw128(eb + off * E_ATOM + in, 0, 1024), id_pb, ks > 0);
-      }
-    }
-    ptx::umma_commit(bar_s);
-  };
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint32_t off = (ks >> 2), in = (ks & 3) * 32;
+            ptx::umma_bf16(tmem + TM_PB, ptx::make_smem_desc_sw128(qb + off * Q_ATOM + in, 0, 1024),
+                           ptx::make_smem_desc_sw128(eb + off * E_ATOM + in, 0, 1024), id_pb, ks > 0);
+          }
+        }
+        ptx::umma_commit(bar_s);
+      };
 
-  if (leader) {
-    ptx::mbar_arrive_expect_tx(bar_q, NATOM * Q_ATOM);
+      ptx::mbar_arrive_expect_tx(bar_q, NATOM * Q_ATOM);
 #pragma unroll
-    for (int a = 0; a < NATOM; ++a) ptx::tma_load_2d(sQ + a * Q_ATOM, &tmQ, bar_q, h * DH + a * 64, b * p.Lq + i0);
-    load_ke(t_lo);
-    load_v(t_lo);
-    ptx::mbar_wait(bar_q, 0);
-    ptx::mbar_wait(bar_ke, 0);
-    ptx::tc_fence_after();
-    issue_s();
-  }
-  __syncwarp();
-
-  const RowCtx rc = make_row_ctx(p, b, h, i);
-  float m_run = NEG_BIG, l_run = 0.f;             // l_run: this thread's share (its CW columns) of the row sum
-  uint32_t ph_s = 0, ph_ke = 1;
-
-  for (int t = t_lo; t <= t_hi; ++t) {
-    ptx::mbar_wait(bar_s, ph_s);
-    ph_s ^= 1u;
-    ptx::tc_fence_after();
-    if (leader && t < t_hi) { load_ke(t + 1); load_v(t + 1); }
-    __syncwarp();
-
-    float U[SP::WIN_LD];
-    uint32_t mbits;
-    const bool simple = tile_is_simple(p, rc, t * BN);
-    tile_logits<NSPLIT>(p, rc, tmem + TM_S + lane_base, tmem + TM_PB + lane_base, q, hf, lane, t * BN, simple, U, mbits);
-
-    float mt = U[0];
-#pragma unroll
-    for (int x = 1; x < CW; ++x) mt = fmaxf(mt, U[x]);
-    sred[hf * 128 + li] = mt;
-    ptx::named_bar_sync(1 + q, 32 * NSPLIT);       // the NSPLIT warps that share this lane quarter
-#pragma unroll
-    for (int g = 0; g < NSPLIT; ++g) mt = fmaxf(mt, sred[g * 128 + li]);
-    const float m_new = fmaxf(m_run, mt);
-    const float alpha = __expf(m_run - m_new);
-    float sum = 0.f;
-#pragma unroll
-    for (int x = 0; x < CW; ++x) { U[x] = __expf(U[x] - m_new); sum += U[x]; }
-    l_run = l_run * alpha + sum;
-    m_run = m_new;
-    if (p.thr) {
-      float keep[CW];
-      dropout_keep<NSPLIT>(p, rc, t * BN, hf, keep);
-#pragma unroll
-      for (int x = 0; x < CW; ++x) U[x] *= keep[x];
-    }
-    store_cols_bf16_sw128<CW>(ptx::smem_u32(sP), li, CW * hf, U);
-
-    if (t > t_lo && __any_sync(0xffffffffu, alpha != 1.f)) {
-#pragma unroll
-      for (int c = 0; c < OC / 8; ++c) {
-        uint32_t r[8];
-        const uint32_t ta = tmem + TM_O + hf * OC + c * 8 + lane_base;
-        ptx::tmem_ld_32x32b_x8(ta, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int x = 0; x < 8; ++x) r[x] = __float_as_uint(__uint_as_float(r[x]) * alpha);
-        ptx::tmem_st_32x32b_x8(ta, r);
-      }
-      ptx::tmem_st_wait();
-    }
-    ptx::fence_proxy_async();
-    ptx::tc_fence_before();
-    __syncthreads();
-    if (leader) {
+      for (int a = 0; a < NATOM; ++a) ptx::tma_load_2d(sQ + a * Q_ATOM, &tmQ, bar_q, h * DH + a * 64, b * p.Lq + i0);
+      load_ke(t_lo);
+      load_v(t_lo);
+      if (t_lo < t_hi) { load_ke(t_lo + 1); load_v(t_lo + 1); }
+      ptx::mbar_wait(bar_q, 0);
+      ptx::mbar_wait(&bar_ke[0], 0);
       ptx::tc_fence_after();
-      const int buf = (t - t_lo) & 1;
-      ptx::mbar_wait(&bar_v[buf], ((t - t_lo) >> 1) & 1);
-      ptx::tc_fence_after();
-      const uint32_t pb = ptx::smem_u32(sP), vb = ptx::smem_u32(sV + buf * NATOM * V_GRP);
-      const uint32_t id_o = ptx::make_idesc_bf16(BM, DH, 0, 1);
-#pragma unroll
-      for (int ks = 0; ks < BN / 16; ++ks)
-        ptx::umma_bf16(tmem + TM_O, ptx::make_smem_desc_sw128(pb + ks * 32, 0, 1024),
-                       ptx::make_smem_desc_sw128(vb + ks * 2048, V_GRP, 1024), id_o, (t > t_lo || ks > 0) ? 1u : 0u);
-      if (t < t_hi) {
-        ptx::mbar_wait(bar_ke, ph_ke);
-        ph_ke ^= 1u;
+      issue_s(0);
+      for (int t = t_lo; t <= t_hi; ++t) {
+        const int k = t - t_lo, st = k & 1;
+        if (k > 0 && t < t_hi) {                            // V(t-1)'s buffer is free once PV(t-1) has completed
+          ptx::mbar_wait(bar_pv, (uint32_t)((k - 1) & 1));
+          load_v(t + 1);
+        }
+        if (t < t_hi) {
+          ptx::mbar_wait(bar_sfree, (uint32_t)(k & 1));     // S / PB copied to registers by every compute warp
+          ptx::mbar_wait(&bar_ke[st ^ 1], (uint32_t)(((k + 1) >> 1) & 1));
+          ptx::tc_fence_after();
+          issue_s(st ^ 1);
+          if (t + 2 <= t_hi) load_ke(t + 2);                // stage `st`: its MMAs finished before bar_s(t) fired
+        }
+        ptx::mbar_wait(bar_p, (uint32_t)(k & 1));           // P(t) in shared memory, O rescaled
+        ptx::mbar_wait(&bar_v[st], (uint32_t)((k >> 1) & 1));
         ptx::tc_fence_after();
-        issue_s();
-      } else {
-        ptx::umma_commit(bar_o);
+        const uint32_t pb = ptx::smem_u32(sP), vb = ptx::smem_u32(sV + st * NATOM * V_GRP);
+        const uint32_t id_o = ptx::make_idesc_bf16(BM, DH, 0, 1);
+#pragma unroll
+        for (int ks = 0; ks < BN / 16; ++ks)
+          ptx::umma_bf16(tmem + TM_O, ptx::make_smem_desc_sw128(pb + ks * 32, 0, 1024),
+                         ptx::make_smem_desc_sw128(vb + ks * 2048, V_GRP, 1024), id_o, (k > 0 || ks > 0) ? 1u : 0u);
+        ptx::umma_commit(bar_pv);
       }
     }
-    __syncwarp();
-  }
+  } else {
+    // ============================================ compute warps ==================================================
+    const int q = w & 3, hf = w >> 2;
+    const int li = 32 * q + lane;
+    const int i = i0 + li;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const RowCtx rc = make_row_ctx(p, b, h, i);
+    float m_run = NEG_BIG, l_run = 0.f;             // l_run: this thread's share (its CW columns) of the row sum
 
-  // row sum = sum of the column groups' shares (the __syncthreads closing the last tile orders this reuse of sred)
-  sred[hf * 128 + li] = l_run;
-  ptx::named_bar_sync(1 + q, 32 * NSPLIT);
-  float l_tot = 0.f;
+    for (int t = t_lo; t <= t_hi; ++t) {
+      const int k = t - t_lo;
+      ptx::mbar_wait(bar_s, (uint32_t)(k & 1));
+      ptx::tc_fence_after();
+
+      float U[SP::WIN_LD];
+      uint32_t mbits;
+      const bool simple = tile_is_simple(p, rc, t * BN);
+      tile_logits<NSPLIT>(p, rc, tmem + TM_S + lane_base, tmem + TM_PB + lane_base, q, hf, lane, t * BN, simple, U, mbits);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_sfree);    // the issuer may overwrite S / PB with the next tile
+
+      float* red = sred + (k & 1) * NSPLIT * 128;
+      float mt = U[0];
 #pragma unroll
-  for (int g = 0; g < NSPLIT; ++g) l_tot += sred[g * 128 + li];
+      for (int x = 1; x < CW; ++x) mt = fmaxf(mt, U[x]);
+      red[hf * 128 + li] = mt;
+      ptx::named_bar_sync(1 + q, 32 * NSPLIT);       // the NSPLIT warps that share this lane quarter
+#pragma unroll
+      for (int g = 0; g < NSPLIT; ++g) mt = fmaxf(mt, red[g * 128 + li]);
+      const float m_new = fmaxf(m_run, mt);
+      const float alpha = __expf(m_run - m_new);
+      float sum = 0.f;
+#pragma unroll
+      for (int x = 0; x < CW; ++x) { U[x] = __expf(U[x] - m_new); sum += U[x]; }
+      l_run = l_run * alpha + sum;
+      m_run = m_new;
+      if (p.thr) {
+        float keep[CW];
+        dropout_keep<NSPLIT>(p, rc, t * BN, hf, keep);
+#pragma unroll
+        for (int x = 0; x < CW; ++x) U[x] *= keep[x];
+      }
+      if (k > 0) {                                   // PV(t-1) done: the P buffer is free and O is complete
+        ptx::mbar_wait(bar_pv, (uint32_t)((k - 1) & 1));
+        ptx::tc_fence_after();
+      }
+      store_cols_bf16_sw128<CW>(ptx::smem_u32(sP), li, CW * hf, U);
+      if (k > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+        for (int c = 0; c < OC / 8; ++c) {
+          uint32_t r[8];
+          const uint32_t ta = tmem + TM_O + hf * OC + c * 8 + lane_base;
+          ptx::tmem_ld_32x32b_x8(ta, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int x = 0; x < 8; ++x) r[x] = __float_as_uint(__uint_as_float(r[x]) * alpha);
+          ptx::tmem_st_32x32b_x8(ta, r);
+        }
+        ptx::tmem_st_wait();
+      }
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_p);
+    }
 
-  ptx::mbar_wait(bar_o, 0);
-  ptx::tc_fence_after();
-  const bool valid = i < p.Lq;
-  tmem_row_to_global<OC>(tmem + TM_O + hf * OC + lane_base, p.o + ((long)b * p.Lq + i) * p.ldo + h * DH + hf * OC, 1.f / l_tot, valid);
-  if (valid && hf == 0) {
-    const long nrows = (long)p.B * p.H * p.Lq;
-    p.lse[rc.row_id] = m_run;
-    p.lse[nrows + rc.row_id] = __logf(l_tot);
+    // row sum = sum of the column groups' shares
+    const int kl = t_hi - t_lo;
+    float* red = sred + ((kl + 1) & 1) * NSPLIT * 128;
+    red[hf * 128 + li] = l_run;
+    ptx::named_bar_sync(1 + q, 32 * NSPLIT);
+    float l_tot = 0.f;
+#pragma unroll
+    for (int g = 0; g < NSPLIT; ++g) l_tot += red[g * 128 + li];
+
+    ptx::mbar_wait(bar_pv, (uint32_t)(kl & 1));
+    ptx::tc_fence_after();
+    const bool valid = i < p.Lq;
+    tmem_row_to_global<OC>(tmem + TM_O + hf * OC + lane_base, p.o + ((long)b * p.Lq + i) * p.ldo + h * DH + hf * OC, 1.f / l_tot, valid);
+    if (valid && hf == 0) {
+      const long nrows = (long)p.B * p.H * p.Lq;
+      p.lse[rc.row_id] = m_run;
+      p.lse[nrows + rc.row_id] = __logf(l_tot);
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -242,7 +267,7 @@ static int attn_fwd_tc_launch_n(const SstAttnDesc& d, const void* q, const void*
     tmE = tmK;
   }
   constexpr int NATOM = (DH + 63) / 64;
-  constexpr int SMEM = NATOM * (BM * 128 + BN * 128 + PBW * 128 + 2 * BN * 128) + BM * 128 + 1024 + 64 + NSPLIT * 128 * 4;
+  constexpr int SMEM = NATOM * (BM * 128 + 2 * BN * 128 + 2 * PBW * 128 + 2 * BN * 128) + BM * 128 + 1024 + 128 + 2 * NSPLIT * 128 * 4;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -250,7 +275,7 @@ static int attn_fwd_tc_launch_n(const SstAttnDesc& d, const void* q, const void*
     attr_done = true;
   }
   dim3 grid(cdiv(d.Lq, BM), d.H, d.B);
-  attn_fwd_tc_kernel<DH, NSPLIT><<<grid, 128 * NSPLIT, SMEM, st>>>(tmQ, tmK, tmV, tmE, p);
+  attn_fwd_tc_kernel<DH, NSPLIT><<<grid, 128 * NSPLIT + 32, SMEM, st>>>(tmQ, tmK, tmV, tmE, p);
   return check_launch("attn_fwd_tc");
 }
 

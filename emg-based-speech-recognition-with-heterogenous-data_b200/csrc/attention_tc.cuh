@@ -29,6 +29,7 @@ struct AttnTcParams {
   float scale;
   uint32_t thr; float dscale; unsigned long long seed;   // thr: 16-bit keep threshold (0 = no dropout)
   const int* q_lens; const int* k_lens;
+  const uint8_t* q_pad; const uint8_t* k_pad;   // optional per-position padding masks (OR-ed with the length masks)
   __nv_bfloat16* o; long ldo;
   float* lse;
   // backward only
@@ -48,6 +49,7 @@ inline AttnTcParams make_tc_params(const SstAttnDesc& d, const int* q_lens, cons
   p.dscale = d.drop_p < 1.f ? 1.f / (1.f - d.drop_p) : 0.f;
   p.seed = d.seed;
   p.q_lens = q_lens; p.k_lens = k_lens;
+  p.q_pad = d.q_pad; p.k_pad = d.k_pad;
   return p;
 }
 
@@ -79,6 +81,7 @@ struct RowCtx {
   int i;            // query index inside the utterance
   int klen;         // keys j >= klen are padding (masked, -1e8)
   bool rowmask;     // whole query row is padding (masked, -1e8)
+  const uint8_t* kpad;   // per-key padding flags of this utterance (nullable)
 };
 
 __device__ __forceinline__ RowCtx make_row_ctx(const AttnTcParams& p, int b, int h, int i) {
@@ -86,7 +89,8 @@ __device__ __forceinline__ RowCtx make_row_ctx(const AttnTcParams& p, int b, int
   rc.row_id = ((long)b * p.H + h) * p.Lq + i;
   rc.i = i;
   rc.klen = p.k_lens ? p.k_lens[b] : p.Lk;
-  rc.rowmask = p.mask_q_rows && p.q_lens && i >= p.q_lens[b];
+  rc.rowmask = p.mask_q_rows && ((p.q_lens && i >= p.q_lens[b]) || (p.q_pad && i < p.Lq && p.q_pad[(long)b * p.Lq + i]));
+  rc.kpad = p.k_pad ? p.k_pad + (long)b * p.Lk : nullptr;
   return rc;
 }
 
@@ -163,7 +167,7 @@ __device__ __forceinline__ void tile_logits(const AttnTcParams& p, const RowCtx&
 #pragma unroll
     for (int x = 0; x < CW; ++x) {
       const int j = jb + x;
-      const bool masked = rc.rowmask || j >= rc.klen || (p.causal && j > rc.i);
+      const bool masked = rc.rowmask || j >= rc.klen || (p.causal && j > rc.i) || (rc.kpad && j < p.Lk && rc.kpad[j]);
       float s = masked ? NEG_MASK : sv[x] * p.scale;
       if (p.R > 0) s += ((uint32_t)(d0 + x) < lim) ? U[x] : NEG_MASK;
       U[x] = j < p.Lk ? s : NEG_BIG;
@@ -173,7 +177,7 @@ __device__ __forceinline__ void tile_logits(const AttnTcParams& p, const RowCtx&
 }
 
 __device__ __forceinline__ bool tile_is_simple(const AttnTcParams& p, const RowCtx& rc, int j0) {
-  const bool mine = !p.causal && !rc.rowmask && (j0 + BN <= min(rc.klen, p.Lk));
+  const bool mine = !p.causal && !rc.rowmask && !rc.kpad && (j0 + BN <= min(rc.klen, p.Lk));
   return __all_sync(0xffffffffu, mine);
 }
 

@@ -209,9 +209,9 @@ class Engine:
                         G[prefix + ".weight"], G[prefix + ".bias"])
         return ds, (dr if p > 0 else ds)
 
-    def _attn_desc(self, B, Lq, Lk, ldq, ldk, ldv, causal, mask_q_rows, R, p, seed):
+    def _attn_desc(self, B, Lq, Lk, ldq, ldk, ldv, causal, mask_q_rows, R, p, seed, q_pad=None, k_pad=None):
         return L.attn_desc(self.dt, B, self.H, Lq, Lk, self.dh, ldq, ldk, ldv, self.D, causal, mask_q_rows, R,
-                           1.0 / math.sqrt(self.dh), p, seed, self.force_simt)
+                           1.0 / math.sqrt(self.dh), p, seed, self.force_simt, q_pad=q_pad, k_pad=k_pad)
 
     # ------------------------------------------------------------------------------------------------ conv front-end
     def _bn_stats(self, x, rows, ld, prefix, training):
@@ -377,7 +377,7 @@ class Engine:
             L.permute3_cast(dW[s * D:], G[name], (H, D, dh), (dh * D, 1, D), (D * dh, dh, 1), accumulate=True)
 
     # ------------------------------------------------------------------------------------------------ decoder
-    def _dec_layer_fwd(self, t, mem, B, S, Lm, tgt_lens, mem_lens, i, training, seeds):
+    def _dec_layer_fwd(self, t, mem, B, S, Lm, tgt_lens, mem_lens, i, training, seeds, tgt_pad=None):
         D, M, Mm = self.D, B * S, B * Lm
         p = self.cfg["dropout"] if training else 0.0
         pfx = "transformerDecoder.layers.%d" % i
@@ -385,7 +385,7 @@ class Engine:
         qkv = self._linear_fwd(t, M, a + ".qkv")
         o1 = self.empty(M, D)
         lse1 = self.empty(2 * B * self.H * S, dtype=torch.float32)
-        ad1 = self._attn_desc(B, S, S, 3 * D, 3 * D, 3 * D, True, True, 0, p, seeds())
+        ad1 = self._attn_desc(B, S, S, 3 * D, 3 * D, 3 * D, True, True, 0, p, seeds(), q_pad=tgt_pad, k_pad=tgt_pad)
         L.attn_fwd(ad1, qkv, qkv[:, D:], qkv[:, 2 * D:], None, tgt_lens, tgt_lens, o1, lse1)
         y = self._linear_fwd(o1, M, a + ".o.T")
         t1, ln1 = self._ln_fwd(t, y, M, pfx + ".norm1", p, seeds())
@@ -489,8 +489,10 @@ class Engine:
         """w_aux: fp32 logits in a pitch-64 matrix (columns >= 44 undefined)."""
         return self._linear_fwd(x_enc, M, "w_aux", bias=self.P["w_aux.bias"], out_dtype=torch.float32, ldc=self.LDH)
 
-    def decode(self, y, tgt_lens, mem, mem_lens, B, Lm, training, seeds, ctx=None):
-        """y: (B, S) int64 CUDA; returns x_dec (B*S, D)."""
+    def decode(self, y, tgt_lens, mem, mem_lens, B, Lm, training, seeds, ctx=None, tgt_pad=None):
+        """y: (B, S) int64 CUDA; returns x_dec (B*S, D).  Target padding is either a suffix (`tgt_lens`, the training
+        batches of pad_sequence) or an arbitrary per-position mask `tgt_pad` (uint8 (B, S); greedy prefixes, where a
+        generated PAD id can sit anywhere: architecture.py:174 masks by `tgt == pad`)."""
         S = y.shape[1]
         p_pos = self.cfg["dropout_pos"] if training else 0.0
         t = self.empty(B * S, self.D)
@@ -498,7 +500,7 @@ class Engine:
         L.embed_posenc_fwd(self.dt, y, self.P["embedding_tgt.weight"], self.Bf["pos_decoder.pe"], t, B, S, self.D, p_pos, s_emb)
         layers = []
         for i in range(self.n_dec):
-            t, c = self._dec_layer_fwd(t, mem, B, S, Lm, tgt_lens, mem_lens, i, training, seeds)
+            t, c = self._dec_layer_fwd(t, mem, B, S, Lm, tgt_lens, mem_lens, i, training, seeds, tgt_pad)
             layers.append(c)
         if ctx is not None:
             ctx.update(y=y, S=S, tgt_lens=tgt_lens, dec_layers=layers, p_pos=p_pos, s_emb=s_emb, x_dec=t)

@@ -1,0 +1,70 @@
+"""Greedy attention-decoder search with the reference's interface (greedy_search.py:7-53): encoder once, then the decoder
+on the growing prefix, argmax of the last position, until every sample has produced </S> or the prefix reaches the target
+length.  Same return value: (list of space-joined phone strings, (B, max_seq_length) int32 id tensor padded with 42).
+
+All model math runs in libsst.so through `Model.forward(mode='greedy_search', part=...)`.  Differences from the reference
+are host-side only: the arg-max is taken on the logits (softmax is monotone, greedy_search.py:22-23) and the per-step
+"has everybody finished" test is one device reduction instead of a Python loop over strings (:26-37)."""
+import torch
+
+from .data_utils import PAD
+
+# data_utils.py:19 -- 40 phones + </S> (40), <S> (41), <PAD> (42)
+phoneme_inventory = ['AA', 'AE', 'AH', 'AO', 'AW', 'AY', 'B', 'CH', 'D', 'DH', 'EH', 'ER', 'EY', 'F', 'G', 'HH', 'IH', 'IX', 'IY',
+                     'JH', 'K', 'L', 'M', 'N', 'NG', 'OW', 'OY', 'P', 'R', 'S', 'SH', 'T', 'TH', 'UH', 'UW', 'V', 'W', 'Y', 'Z',
+                     'ZH', '</S>', '<S>', '<PAD>']
+EOS, SOS = 40, 41
+
+
+class PhoneTransform(object):
+    """data_utils.py:281-291."""
+
+    def __init__(self):
+        self.phoneme_inventory = phoneme_inventory
+        self.vocabulary_size = len(self.phoneme_inventory)
+
+    def phone_to_int(self, phone):
+        return [self.phoneme_inventory.index(c) for c in phone]
+
+    def int_to_phone(self, ints):
+        return ''.join(self.phoneme_inventory[int(i)] for i in ints)
+
+
+def greedy_ids(model, length_raw_signal, X_raw, max_seq_length, device, start_tok=SOS):
+    """The id-level search.  Returns a (B, n) int64 CPU tensor of generated prefixes (column 0 = <S>), n <= max_seq_length;
+    positions after a sample's first </S> hold what the decoder kept predicting (the reference keeps feeding them too,
+    greedy_search.py:33-34) and are dropped by the caller."""
+    memory, _ = model(length_raw_signal, device, mode='greedy_search', part='encoder', x_raw=X_raw)
+    B = memory.shape[0]
+    dec_input = torch.full((B, 1), start_tok, dtype=torch.int64, device=memory.device)
+    done = torch.zeros(B, dtype=torch.bool, device=memory.device)
+    with torch.no_grad():
+        while True:
+            step_logits = model(length_raw_signal, device, mode='greedy_search', part='decoder', y=dec_input, memory=memory)
+            pred = torch.argmax(step_logits[:, -1, :], dim=1)
+            dec_input = torch.cat((dec_input, pred.reshape(B, 1)), dim=1)
+            done |= pred == EOS
+            if dec_input.shape[1] >= max_seq_length or bool(done.all()):
+                break
+    return dec_input.cpu()
+
+
+def run_greedy(model, length_raw_signal, X_raw, tgt, vocab_size, device):
+    batch_len = tgt.shape[0]
+    max_seq_length = tgt.shape[1] + 1                      # +1 for the removed <S> (greedy_search.py:11)
+    ids = greedy_ids(model, length_raw_signal, X_raw, max_seq_length, device, start_tok=vocab_size - 2)
+    pt = PhoneTransform()
+    seqs = []
+    for b in range(batch_len):
+        row = ids[b].tolist()
+        seq = [row[0]]
+        for tok in row[1:]:
+            if seq[-1] == EOS:                              # nothing is appended after </S> (:29)
+                break
+            seq.append(tok)
+        seqs.append(seq)
+    new_word_seq_idx = torch.full((batch_len, max_seq_length), PAD, dtype=torch.int32)
+    for b, seq in enumerate(seqs):
+        new_word_seq_idx[b, :len(seq)] = torch.tensor(seq, dtype=torch.int32)
+    phones_seq = [' '.join(pt.int_to_phone([t]) for t in seq) for seq in seqs]
+    return phones_seq, new_word_seq_idx.to(device)

@@ -158,7 +158,8 @@ class AttnDesc(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("Lq", C.c_int32), ("Lk", C.c_int32),
                 ("dh", C.c_int32), ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64), ("ldo", C.c_int64),
                 ("causal", C.c_int32), ("mask_q_rows", C.c_int32), ("rel_dist", C.c_int32), ("scale", C.c_float),
-                ("drop_p", C.c_float), ("seed", C.c_uint64), ("force_simt", C.c_int32)]
+                ("drop_p", C.c_float), ("seed", C.c_uint64), ("force_simt", C.c_int32),
+                ("q_pad", C.c_void_p), ("k_pad", C.c_void_p)]
 
 
 def _i64(v):
@@ -174,12 +175,15 @@ def _u64(v):
 
 
 def attn_desc(dtype, B, H, Lq, Lk, dh, ldq, ldk, ldv, ldo, causal, mask_q_rows, rel_dist, scale, drop_p, seed,
-              force_simt=False):
+              force_simt=False, q_pad=None, k_pad=None):
     d = AttnDesc()
     d.dtype, d.B, d.H, d.Lq, d.Lk, d.dh = dtype, B, H, Lq, Lk, dh
     d.ldq, d.ldk, d.ldv, d.ldo = ldq, ldk, ldv, ldo
     d.causal, d.mask_q_rows, d.rel_dist = int(causal), int(mask_q_rows), int(rel_dist)
     d.scale, d.drop_p, d.seed, d.force_simt = scale, drop_p, seed & 0xFFFFFFFFFFFFFFFF, int(force_simt)
+    d.q_pad = q_pad.data_ptr() if q_pad is not None else None
+    d.k_pad = k_pad.data_ptr() if k_pad is not None else None
+    d._keep = (q_pad, k_pad)                      # the descriptor holds raw pointers: keep the mask tensors alive with it
     return d
 
 

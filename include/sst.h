@@ -130,8 +130,8 @@ int sst_bn_bwd(int dtype, int64_t n_chunks, int T, int C, const void* dout, int6
  * with LearnedRelativePositionalEmbedding (transformer.py:260-403): logits = mask(q.k * scale) + relpos(q),
  * softmax, dropout on the probabilities, probs.v -- without materialising (B,H,L,L).
  *   q/k/v/o are token matrices: row = b*L + t (pitch ld*), head h occupies columns [h*dh, (h+1)*dh).
- *   masks are SET to -1e8 exactly as masked_fill does: causal (j > i), keys j >= k_lens[b], and, with mask_q_rows,
- *   whole rows i >= q_lens[b]; fully masked rows therefore give the reference's uniform softmax.
+ *   masks are SET to -1e8 exactly as masked_fill does: causal (j > i), keys j >= k_lens[b] (or k_pad), and, with
+ *   mask_q_rows, whole rows i >= q_lens[b] (or q_pad); fully masked rows therefore give the reference's uniform softmax.
  *   rel_dist R > 0 adds bias[i][j] = q_i . E[h][j-i+R-1] for |j-i| < R and -1e8 otherwise; E is
  *   (H, 2R-1, dh) in the compute dtype and receives no gradient (Q2).
  *   lse is float[2*B*H*Lq]: row maximum at [(b*H+h)*Lq + i] and log(sum exp(logit - max)) at [B*H*Lq + ...] (kept apart
@@ -149,6 +149,11 @@ typedef struct SstAttnDesc {
   float drop_p;
   uint64_t seed;
   int32_t force_simt;
+  /* optional per-position padding masks (device uint8, nonzero = padded), OR-ed with the length masks: q_pad[b*Lq + i]
+   * masks the whole query row, k_pad[b*Lk + j] the key -- for padding that is not a suffix (a PAD token generated in the
+   * middle of a greedy prefix, greedy_search.py:21 + architecture.py:174) */
+  const uint8_t* q_pad;
+  const uint8_t* k_pad;
 } SstAttnDesc;
 
 int sst_attn_fwd(const SstAttnDesc* d, const void* q, const void* k, const void* v, const void* E, const int32_t* q_lens,

@@ -554,7 +554,7 @@ def ctc_greedy_collapse(out_enc_blc, lengths, blank=BLANK):
     return res
 
 
-def greedy_decode(sd, cfg, x_raw, lengths, max_seq_length):
+def greedy_decode(sd, cfg, x_raw, lengths, max_seq_length, margins=None):
     """run_greedy, greedy_search.py:7-53 restated on token ids: encoder once (eval mode), then the full
     decoder on the growing prefix, argmax of the last step, stop when every sample has emitted </S> or
     the prefix reaches max_seq_length.  Returns list of id lists (starting with <S>) and the padded
@@ -568,6 +568,9 @@ def greedy_decode(sd, cfg, x_raw, lengths, max_seq_length):
             x_dec = decode(sd, cfg, dec_input, memory, kpm, False)
             logits = F.linear(x_dec, sd["w_out.weight"], sd["w_out.bias"])
             pred = torch.argmax(F.softmax(logits, dim=2), dim=2)[:, -1]
+            if margins is not None:           # top-1 minus top-2 logit of the step, per sample (decode parity is only
+                top2 = logits[:, -1, :].topk(2, dim=1).values    # meaningful where this exceeds the numeric tolerance)
+                margins.append((top2[:, 0] - top2[:, 1]).clone())
             for i in range(B):
                 if seqs[i][-1] != EOS:
                     seqs[i].append(int(pred[i]))

@@ -1,0 +1,73 @@
+"""Greedy attention-decoder search (greedy_search.py:7-53) through the drop-in Model API on a B200, fp32 parity mode:
+decoded phoneme ids bit-exact against the CPU oracle, and the decoder with NON-suffix padding (a PAD id generated in
+the middle of a prefix, masked per position by architecture.py:174) against the oracle's decoder."""
+import numpy as np
+import pytest
+import torch
+
+import sst_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _setup(n_enc, n_dec, wseed, scale_out=30.0):
+    import sst_b200  # noqa: F401
+    from sst_b200 import architecture as A
+    cfg = O.make_cfg(n_enc=n_enc, n_dec=n_dec, rel_dist=100)
+    sd = O.synthetic_state_dict(cfg, wseed)
+    g = torch.Generator().manual_seed(wseed + 5)
+    for k in sd:                                           # eval mode uses the running statistics: make them non-trivial
+        if k.endswith("running_mean"):
+            sd[k] = 0.1 * torch.randn(sd[k].shape, generator=g)
+        elif k.endswith("running_var"):
+            sd[k] = 1.0 + 0.2 * torch.rand(sd[k].shape, generator=g)
+    sd["w_out.weight"] = sd["w_out.weight"] * scale_out    # random weights give near-flat logits: widen the arg-max margins
+    A.configure(model_size=768, feed_forward_layer_size=3072, num_layers_encoder=n_enc, num_layers_decoder=n_dec,
+                n_heads_encoder=8, n_heads_decoder=8, relative_distance=100, dropout_model=0.2, dropout_pos_emb=0.2,
+                sst_dtype="fp32")
+    model = A.Model(112, 44, 43, DEV).to(DEV)
+    model.load_state_dict(sd)
+    model.eval()
+    return cfg, sd, model
+
+
+def test_run_greedy_matches_oracle_bit_exact():
+    from sst_b200.greedy_search import run_greedy, phoneme_inventory
+    cfg, sd, model = _setup(1, 2, wseed=11)
+    batch = O.synthetic_batch(seed=5, ragged=[120, 200, 80], tgt_lens=[12, 12, 12])
+    X = O.combine_fixed_length(batch["raw_emg"])
+    max_len = 14
+    margins = []
+    seqs, out = O.greedy_decode(sd, cfg, X.clone(), batch["lengths"], max_len, margins)
+    tgt = torch.zeros(3, max_len - 1, dtype=torch.int64)
+    phones, ids = run_greedy(model, batch["lengths"], X.to(DEV), tgt, 43, DEV)
+    m = torch.stack(margins, 1)                             # (B, steps)
+    print("min top-2 logit margin along the oracle's path: %.3e" % float(m.min()))
+    ids = ids.cpu()
+    assert ids.shape == out.shape and ids.dtype == torch.int32
+    for b in range(3):
+        # compare up to the first step whose arg-max margin is below the fp32 parity tolerance (1e-4 of the logit scale):
+        # beyond it the two valid fp32 evaluations may legitimately pick different tokens
+        amb = (m[b] < 1e-3).nonzero()
+        upto = int(amb[0]) + 1 if len(amb) else max_len
+        assert upto >= 4, "seed produces an ambiguous arg-max too early to test anything"
+        assert ids[b, :upto].tolist() == out[b, :upto].tolist(), "sample %d" % b
+        if upto == max_len:
+            assert phones[b] == " ".join(phoneme_inventory[t] for t in seqs[b])
+    assert sum(int((m[b] >= 1e-3).all()) for b in range(3)) >= 2, "at least two samples must be compared in full"
+
+
+def test_decoder_with_pad_token_inside_the_prefix():
+    """tgt == 42 anywhere in the prefix masks that key AND that query row (transformer.py:185-187): fp32 1e-4 vs oracle."""
+    cfg, sd, model = _setup(1, 2, wseed=12, scale_out=1.0)
+    batch = O.synthetic_batch(seed=6, ragged=[100, 60], tgt_lens=[5, 5])
+    X = O.combine_fixed_length(batch["raw_emg"])
+    y = torch.tensor([[41, 3, 42, 7, 42, 9, 1], [41, 42, 5, 6, 2, 40, 8]], dtype=torch.int64)
+    with torch.no_grad():
+        mem, kpm = O.encode(sd, cfg, X.clone(), batch["lengths"], False)
+        ref = torch.nn.functional.linear(O.decode(sd, cfg, y, mem, kpm, False), sd["w_out.weight"], sd["w_out.bias"])
+        memory, _ = model(batch["lengths"], DEV, mode='greedy_search', part='encoder', x_raw=X.to(DEV))
+        got = model(batch["lengths"], DEV, mode='greedy_search', part='decoder', y=y.to(DEV), memory=memory).cpu()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    assert err < 1e-4, err
