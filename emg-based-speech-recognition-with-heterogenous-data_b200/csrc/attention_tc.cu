@@ -169,17 +169,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       ptx::tc_fence_after();
 
       float U[SP::WIN_LD];
-      uint32_t mbits;
-      const bool simple = tile_is_simple(p, rc, t * BN);
-      tile_logits<NSPLIT>(p, rc, tmem + TM_S + lane_base, tmem + TM_PB + lane_base, q, hf, lane, t * BN, simple, U, mbits);
+      const bool skip = block_out_of_band<NSPLIT>(p, i0 + 32 * q, t * BN + CW * hf);
+      float* red = sred + (k & 1) * NSPLIT * 128;
+      float mt = NEG_BIG;
+      if (!skip) {
+        uint32_t mbits;
+        const bool simple = tile_is_simple(p, rc, t * BN);
+        tile_logits<NSPLIT>(p, rc, tmem + TM_S + lane_base, tmem + TM_PB + lane_base, q, hf, lane, t * BN, simple, U, mbits);
+        mt = U[0];
+#pragma unroll
+        for (int x = 1; x < CW; ++x) mt = fmaxf(mt, U[x]);
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_sfree);    // the issuer may overwrite S / PB with the next tile
 
-      float* red = sred + (k & 1) * NSPLIT * 128;
-      float mt = U[0];
-#pragma unroll
-      for (int x = 1; x < CW; ++x) mt = fmaxf(mt, U[x]);
       red[hf * 128 + li] = mt;
       ptx::named_bar_sync(1 + q, 32 * NSPLIT);       // the NSPLIT warps that share this lane quarter
 #pragma unroll
@@ -187,21 +191,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float m_new = fmaxf(m_run, mt);
       const float alpha = __expf(m_run - m_new);
       float sum = 0.f;
+      if (!skip) {
 #pragma unroll
-      for (int x = 0; x < CW; ++x) { U[x] = __expf(U[x] - m_new); sum += U[x]; }
+        for (int x = 0; x < CW; ++x) { U[x] = __expf(U[x] - m_new); sum += U[x]; }
+        if (p.thr) {
+          float keep[CW];
+          dropout_keep<NSPLIT>(p, rc, t * BN, hf, keep);
+#pragma unroll
+          for (int x = 0; x < CW; ++x) U[x] *= keep[x];
+        }
+      }
       l_run = l_run * alpha + sum;
       m_run = m_new;
-      if (p.thr) {
-        float keep[CW];
-        dropout_keep<NSPLIT>(p, rc, t * BN, hf, keep);
-#pragma unroll
-        for (int x = 0; x < CW; ++x) U[x] *= keep[x];
-      }
       if (k > 0) {                                   // PV(t-1) done: the P buffer is free and O is complete
         ptx::mbar_wait(bar_pv, (uint32_t)((k - 1) & 1));
         ptx::tc_fence_after();
       }
-      store_cols_bf16_sw128<CW>(ptx::smem_u32(sP), li, CW * hf, U);
+      if (!skip) store_cols_bf16_sw128<CW>(ptx::smem_u32(sP), li, CW * hf, U);
+      else store_zero_cols_sw128<CW>(ptx::smem_u32(sP), li, CW * hf);
       if (k > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll
         for (int c = 0; c < OC / 8; ++c) {

@@ -176,6 +176,22 @@ __device__ __forceinline__ void tile_logits(const AttnTcParams& p, const RowCtx&
   }
 }
 
+// The (32 query rows of this warp) x (CW keys of this thread's column group) block lies entirely outside the band
+// |i - j| < R: every logit there is <= -1e8 below an in-band one, its probability is exactly 0 in fp32 and the block
+// needs no TMEM load, shift, exp or Philox at all.  Warp-uniform.
+template <int NSPLIT>
+__device__ __forceinline__ bool block_out_of_band(const AttnTcParams& p, int iw0 /* first row of the warp */, int jb /* first key */) {
+  constexpr int CW = Split<NSPLIT>::CW;
+  return p.R > 0 && (jb - (iw0 + 31) >= p.R || iw0 - (jb + CW - 1) >= p.R);
+}
+
+template <int CW>
+__device__ __forceinline__ void store_zero_cols_sw128(uint32_t sbase, int row, int col0) {
+  const uint32_t rbase = sbase + row * 128;
+#pragma unroll
+  for (int c = 0; c < CW / 8; ++c) ptx::st_shared_v4(rbase + ((uint32_t)(((col0 >> 3) + c) ^ (row & 7)) << 4), 0u, 0u, 0u, 0u);
+}
+
 __device__ __forceinline__ bool tile_is_simple(const AttnTcParams& p, const RowCtx& rc, int j0) {
   const bool mine = !p.causal && !rc.rowmask && !rc.kpad && (j0 + BN <= min(rc.klen, p.Lk));
   return __all_sync(0xffffffffu, mine);

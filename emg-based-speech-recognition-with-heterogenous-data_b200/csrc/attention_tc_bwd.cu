@@ -211,6 +211,17 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
   __syncwarp();
 
+  // shared-memory address of this thread's CW relative columns c = (127 - li + CW*hf) + x in the swizzled dS_rel tile
+  uint32_t rel_addr[CW];
+  {
+    const uint32_t rb = ptx::smem_u32(sRel) + li * 128;
+    const int c0 = (BM - 1) - li + CW * hf;
+#pragma unroll
+    for (int x = 0; x < CW; ++x) {
+      const int c = c0 + x;
+      rel_addr[x] = rb + (uint32_t)(c >> 6) * Q_ATOM + ((uint32_t)(((c & 63) >> 3) ^ (li & 7)) << 4) + (uint32_t)(c & 7) * 2;
+    }
+  }
   uint32_t ph_s = 0, ph_ke = 1, ph_dq = 0;
   for (int t = t_lo; t <= t_hi; ++t) {
     const int buf = (t - t_lo) & 1;
@@ -220,31 +231,35 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if (leader && t < t_hi) load_v(t + 1);
     __syncwarp();
 
-    float U[SP::WIN_LD], W[CW];
-    uint32_t mbits;
-    const bool simple = tile_is_simple(p, rc, t * BN);
-    tile_logits<NSPLIT>(p, rc, tmem + TM_S + lane_base, tmem + TM_PB + lane_base, q, hf, lane, t * BN, simple, U, mbits);
-    tile_backward_row<NSPLIT>(p, rc, tmem + TM_DP + lane_base, t * BN, hf, Lm, Ll, delta, U, W);
-
-    // bias term: dS at its relative column c = lj - li + 127 (zero outside the band)
-    if (p.R > 0) {
-      const uint32_t rb = ptx::smem_u32(sRel) + li * 128;
-      const int c0 = (BM - 1) - li + CW * hf;
-      const int d0 = t * BN + CW * hf - i + p.R - 1;
-      const uint32_t lim = (uint32_t)(2 * p.R - 1);
+    const bool skip = block_out_of_band<NSPLIT>(p, i0 + 32 * q, t * BN + CW * hf);
+    if (!skip) {
+      float U[SP::WIN_LD], W[CW];
+      uint32_t mbits;
+      const bool simple = tile_is_simple(p, rc, t * BN);
+      tile_logits<NSPLIT>(p, rc, tmem + TM_S + lane_base, tmem + TM_PB + lane_base, q, hf, lane, t * BN, simple, U, mbits);
+      tile_backward_row<NSPLIT>(p, rc, tmem + TM_DP + lane_base, t * BN, hf, Lm, Ll, delta, U, W);
+      // bias term: dS at its relative column c = lj - li + 127 (zero outside the band); addresses are tile-independent
+      if (p.R > 0) {
+        const int d0 = t * BN + CW * hf - i + p.R - 1;
+        const uint32_t lim = (uint32_t)(2 * p.R - 1);
 #pragma unroll
-      for (int x = 0; x < CW; ++x) {
-        const int c = c0 + x;
-        const float v = ((uint32_t)(d0 + x) < lim) ? W[x] : 0.f;
-        const uint32_t addr = rb + (uint32_t)(c >> 6) * Q_ATOM + ((uint32_t)(((c & 63) >> 3) ^ (li & 7)) << 4) + (uint32_t)(c & 7) * 2;
-        const __nv_bfloat16 hv = __float2bfloat16_rn(v);
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&hv)) : "memory");
+        for (int x = 0; x < CW; ++x) {
+          const float v = ((uint32_t)(d0 + x) < lim) ? W[x] : 0.f;
+          const __nv_bfloat16 hv = __float2bfloat16_rn(v);
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(rel_addr[x]), "h"(*reinterpret_cast<const uint16_t*>(&hv)) : "memory");
+        }
       }
-    }
-    // q.k term: scale * dS where the term was not masked
+      // q.k term: scale * dS where the term was not masked
 #pragma unroll
-    for (int x = 0; x < CW; ++x) W[x] = ((mbits >> x) & 1u) ? 0.f : W[x] * p.scale;
-    store_cols_bf16_sw128<CW>(ptx::smem_u32(sV + buf * NATOM * K_ATOM), li, CW * hf, W);
+      for (int x = 0; x < CW; ++x) W[x] = ((mbits >> x) & 1u) ? 0.f : W[x] * p.scale;
+      store_cols_bf16_sw128<CW>(ptx::smem_u32(sV + buf * NATOM * K_ATOM), li, CW * hf, W);
+    } else {
+      if (p.R > 0) {
+#pragma unroll
+        for (int x = 0; x < CW; ++x) asm volatile("st.shared.u16 [%0], %1;" ::"r"(rel_addr[x]), "h"((uint16_t)0) : "memory");
+      }
+      store_zero_cols_sw128<CW>(ptx::smem_u32(sV + buf * NATOM * K_ATOM), li, CW * hf);
+    }
 
     ptx::fence_proxy_async();
     ptx::tc_fence_before();
@@ -393,15 +408,20 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     ph_s ^= 1u;
     ptx::tc_fence_after();
 
-    float U[SP::WIN_LD], W[CW];
-    uint32_t mbits;
-    const bool simple = tile_is_simple(p, rc, j0);
-    tile_logits<NSPLIT>(p, rc, tmem + TM_S + lane_base, tmem + TM_PB + lane_base, q, hf, lane, j0, simple, U, mbits);
-    tile_backward_row<NSPLIT>(p, rc, tmem + TM_DP + lane_base, j0, hf, Lm, Ll, delta, U, W);
+    if (!block_out_of_band<NSPLIT>(p, u * BM + 32 * q, j0 + CW * hf)) {
+      float U[SP::WIN_LD], W[CW];
+      uint32_t mbits;
+      const bool simple = tile_is_simple(p, rc, j0);
+      tile_logits<NSPLIT>(p, rc, tmem + TM_S + lane_base, tmem + TM_PB + lane_base, q, hf, lane, j0, simple, U, mbits);
+      tile_backward_row<NSPLIT>(p, rc, tmem + TM_DP + lane_base, j0, hf, Lm, Ll, delta, U, W);
 #pragma unroll
-    for (int x = 0; x < CW; ++x) W[x] = ((mbits >> x) & 1u) ? 0.f : W[x] * p.scale;
-    store_cols_bf16_sw128<CW>(pb, li, CW * hf, U);
-    store_cols_bf16_sw128<CW>(dsb, li, CW * hf, W);
+      for (int x = 0; x < CW; ++x) W[x] = ((mbits >> x) & 1u) ? 0.f : W[x] * p.scale;
+      store_cols_bf16_sw128<CW>(pb, li, CW * hf, U);
+      store_cols_bf16_sw128<CW>(dsb, li, CW * hf, W);
+    } else {
+      store_zero_cols_sw128<CW>(pb, li, CW * hf);
+      store_zero_cols_sw128<CW>(dsb, li, CW * hf);
+    }
 
     ptx::fence_proxy_async();
     ptx::tc_fence_before();

@@ -1,6 +1,6 @@
 // bf16 GEMM on 5th-gen tensor cores: TMA -> 128B-swizzled shared memory -> tcgen05.mma (accumulators in
 // TMEM, double buffered) -> tcgen05.ld epilogue.  Persistent, warp-specialised: warp 0 = TMA producer,
-// warp 1 = MMA issuer (one thread) + TMEM owner, warps 2-9 = epilogue (TMEM lane quarter = warp & 3, two warps per
+// warp 1 = MMA issuer (one thread) + TMEM owner, warps 2-17 = epilogue (TMEM lane quarter = warp & 3, four warps per
 // quarter splitting the tile's columns).
 //
 // One kernel covers every dense contraction of the hot path (include/sst.h, "GEMM family"):
@@ -16,7 +16,8 @@ namespace sst {
 
 constexpr int G_BM = 128;
 constexpr int G_BK = 64;
-constexpr int G_EPI_WARPS = 8;                   // two per TMEM lane quarter, each takes half of the tile's columns
+constexpr int G_EPI_WARPS = 16;                  // four per TMEM lane quarter, each takes a quarter of the tile's columns
+constexpr int G_CGROUPS = G_EPI_WARPS / 4;       // column groups
 constexpr int G_THREADS = 64 + 32 * G_EPI_WARPS;
 constexpr int G_A_BYTES = G_BM * G_BK * 2;   // 16 KiB
 
@@ -169,7 +170,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     // ================================ epilogue ====================================
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
-    const int cg = (warp - 2) >> 2;               // column group: chunks [cg * BN/64, (cg + 1) * BN/64)
+    const int cg = (warp - 2) >> 2;               // column group: chunks [cg * CPW, (cg + 1) * CPW)
     int acc = 0; uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       int m0, nb, kb0, kb1;
@@ -178,11 +179,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int m = m0 + q * 32 + lane;
       // Epilogue inputs that do not depend on the accumulator are produced BEFORE waiting for it, i.e. under the MMA
       // main loop: the dropout keep bits (Philox, eight 16-bit lanes per block) and the ReLU/dropout mask bits of `aux`.
-      uint32_t keep_bits[BN / 64], mask_bits[BN / 64];
+      constexpr int CPW = BN / 32 / G_CGROUPS;      // 32-column chunks per epilogue warp
+      uint32_t keep_bits[CPW], mask_bits[CPW];
       if (p.epilogue & SST_EPI_DROPOUT) {
 #pragma unroll
-        for (int lc = 0; lc < BN / 64; ++lc) {
-          const int nbase = n0 + (cg * (BN / 64) + lc) * 32;
+        for (int lc = 0; lc < CPW; ++lc) {
+          const int nbase = n0 + (cg * CPW + lc) * 32;
           const unsigned long long e0 = (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)nbase;
           uint32_t bits = 0;
 #pragma unroll
@@ -196,8 +198,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (p.epilogue & SST_EPI_MULMASK) {
 #pragma unroll
-        for (int lc = 0; lc < BN / 64; ++lc) {
-          const int nbase = n0 + (cg * (BN / 64) + lc) * 32;
+        for (int lc = 0; lc < CPW; ++lc) {
+          const int nbase = n0 + (cg * CPW + lc) * 32;
           uint32_t bits = 0;
           if (m < p.M && nbase < p.N) {
             const int ncols = min(32, p.N - nbase);
@@ -230,8 +232,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         out_row = (long)chunk * p.remap_T + t;
       }
 #pragma unroll
-      for (int lc0 = 0; lc0 < BN / 64; ++lc0) {
-        const int c = cg * (BN / 64) + lc0;
+      for (int lc0 = 0; lc0 < CPW; ++lc0) {
+        const int c = cg * CPW + lc0;
         uint32_t r[32];
         const uint32_t taddr = tmem_base + (uint32_t)(acc * BN + c * 32) + ((uint32_t)(q * 32) << 16);
         ptx::tmem_ld_32x32b_x32(taddr, r);
