@@ -246,6 +246,54 @@ __global__ void ce_finalize_kernel(const float* __restrict__ row_ce, const float
   if (threadIdx.x == 0) *loss_out = (float)((1.0 - eps) * a * inv_nvalid + eps * inv_S * b);
 }
 
+// CTC best-path decode of one utterance per block: arg-max per frame (lowest index wins ties, as torch.argmax), merge
+// repeats, drop blanks; order-preserving compaction with a block-wide exclusive scan per 256-frame chunk.
+template <typename T>
+__global__ void __launch_bounds__(256)
+ctc_greedy_kernel(const T* __restrict__ x, long ld, const int* __restrict__ in_lens, int L, int C, int blank,
+                  int* __restrict__ out_ids, int* __restrict__ out_lens) {
+  __shared__ int s_am[257];        // arg-max of the chunk's frames, [0] = last frame of the previous chunk
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int Tn = in_lens ? min(in_lens[b], L) : L;
+  if (tid == 0) { s_am[0] = -1; s_base = 0; }
+  for (int k = tid; k < L; k += 256) out_ids[(long)b * L + k] = -1;
+  __syncthreads();
+  for (int f0 = 0; f0 < Tn; f0 += 256) {
+    const int f = f0 + tid;
+    int am = -1;
+    if (f < Tn) {
+      const T* row = x + ((long)b * L + f) * ld;
+      float best = to_f32(row[0]);
+      am = 0;
+      for (int c = 1; c < C; ++c) {
+        const float v = to_f32(row[c]);
+        if (v > best) { best = v; am = c; }
+      }
+    }
+    s_am[tid + 1] = am;
+    __syncthreads();
+    const int keep = (f < Tn && am != blank && am != s_am[tid]) ? 1 : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int within = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[w] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int k = 0; k < w; ++k) off += s_warp[k];
+    if (keep) out_ids[(long)b * L + off + within] = am;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int k = 0; k < 8; ++k) tot += s_warp[k];
+      s_base += tot;
+      s_am[0] = s_am[min(256, Tn - f0)];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) out_lens[b] = s_base;
+}
+
 }  // namespace sst
 
 using namespace sst;
@@ -299,6 +347,18 @@ int sst_ctc_loss(int logits_dtype, int grad_dtype, int B, int L, int C, int blan
   }
   ctc_finalize_kernel<<<1, 32, 0, st>>>(nll, tgt_lens, B, loss_out);
   return check_launch("ctc_loss", 4);
+}
+
+/* CTC best-path decode (BASELINE.json config 5; the reference has no CTC decode of its own):
+ * out_ids int32 (B, L) = collapsed label sequence padded with -1, out_lens int32[B]. */
+int sst_ctc_greedy(int logits_dtype, int B, int L, int C, int blank, const void* logits, int64_t ld, const int32_t* in_lens,
+                   int32_t* out_ids, int32_t* out_lens, void* stream) {
+  SST_REQUIRE(C >= 1 && blank < C && out_ids && out_lens, SST_E_ARG, "ctc_greedy: bad arguments");
+  if (B <= 0 || L <= 0) return SST_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (logits_dtype == SST_F32) ctc_greedy_kernel<float><<<B, 256, 0, st>>>((const float*)logits, ld, in_lens, L, C, blank, out_ids, out_lens);
+  else ctc_greedy_kernel<__nv_bfloat16><<<B, 256, 0, st>>>((const __nv_bfloat16*)logits, ld, in_lens, L, C, blank, out_ids, out_lens);
+  return check_launch("ctc_greedy");
 }
 
 /* logits (rows, ld) with rows = B*S; loss = (1-eps)*CE(ignore_index, mean over non-ignored) + eps/S * sum(exp(logits)).

@@ -489,6 +489,16 @@ class Engine:
         """w_aux: fp32 logits in a pitch-64 matrix (columns >= 44 undefined)."""
         return self._linear_fwd(x_enc, M, "w_aux", bias=self.P["w_aux.bias"], out_dtype=torch.float32, ldc=self.LDH)
 
+    def ctc_greedy(self, x_raw, lengths):
+        """Inference (BASELINE.json config 5): encoder forward in eval mode + CTC best-path decode on the device.
+        Returns (ids int32 (B, Lmax) padded with -1, lens int32 (B,)) -- still on the device, no host sync."""
+        x_enc, ctx = self.encode(x_raw, lengths, training=False)
+        logits = self.enc_head(x_enc, ctx.B * ctx.Lmax)
+        ids = torch.empty(ctx.B, ctx.Lmax, dtype=torch.int32, device=self.dev)
+        lens = torch.empty(ctx.B, dtype=torch.int32, device=self.dev)
+        L.ctc_greedy(L.F32, ctx.B, ctx.Lmax, self.n_out_enc, self.n_out_enc - 1, logits, self.LDH, ctx.lens, ids, lens)
+        return ids, lens
+
     def decode(self, y, tgt_lens, mem, mem_lens, B, Lm, training, seeds, ctx=None, tgt_pad=None):
         """y: (B, S) int64 CUDA; returns x_dec (B*S, D).  Target padding is either a suffix (`tgt_lens`, the training
         batches of pad_sequence) or an arbitrary per-position mask `tgt_pad` (uint8 (B, S); greedy prefixes, where a

@@ -68,3 +68,20 @@ def run_greedy(model, length_raw_signal, X_raw, tgt, vocab_size, device):
         new_word_seq_idx[b, :len(seq)] = torch.tensor(seq, dtype=torch.int32)
     phones_seq = [' '.join(pt.int_to_phone([t]) for t in seq) for seq in seqs]
     return phones_seq, new_word_seq_idx.to(device)
+
+
+def run_ctc_greedy(model, length_raw_signal, X_raw, device=None):
+    """CTC best-path decode on the encoder's w_aux head (BASELINE.json config 5; no counterpart in the reference, whose only
+    greedy search is the attention decoder above -- SURVEY.md Q16).  Returns (list of space-joined phone strings, list of id lists)."""
+    model._check_input(X_raw)
+    was_training = model.training
+    model.eval()
+    try:
+        eng = model._packed_engine()
+        ids, lens = eng.ctc_greedy(X_raw, [int(v) for v in length_raw_signal])
+    finally:
+        model.train(was_training)
+    ids, lens = ids.cpu(), lens.cpu()
+    seqs = [ids[b, :int(lens[b])].tolist() for b in range(ids.shape[0])]
+    pt = PhoneTransform()
+    return [' '.join(pt.int_to_phone([t]) for t in s) for s in seqs], seqs

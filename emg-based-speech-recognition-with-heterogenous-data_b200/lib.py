@@ -283,6 +283,11 @@ def ce_sumexp_loss(logits_dtype, grad_dtype, rows, S, Cc, logits, ld, target, ig
                                        stream()), "sst_ce_sumexp_loss")
 
 
+def ctc_greedy(logits_dtype, B, L, Cc, blank, logits, ld, in_lens, out_ids, out_lens):
+    check(lib().sst_ctc_greedy(logits_dtype, B, L, Cc, blank, ptr(logits), _i64(ld), ptr(in_lens), ptr(out_ids), ptr(out_lens),
+                               stream()), "sst_ctc_greedy")
+
+
 def shift_left(x, n_chunks, T, Cc, r):
     check(lib().sst_shift_left(ptr(x), _i64(n_chunks), T, Cc, r, stream()), "sst_shift_left")
 

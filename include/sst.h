@@ -178,6 +178,11 @@ int sst_attn_bwd(const SstAttnDesc* d, const void* q, const void* k, const void*
 int sst_ctc_loss(int logits_dtype, int grad_dtype, int B, int L, int C, int blank, const void* logits, int64_t ld,
                  const int64_t* targets, int Smax, const int32_t* in_lens, const int32_t* tgt_lens, float gcoef, float* lp_ws,
                  float* alpha_ws, float* nll, void* grad, int64_t ldg, float* loss_out, void* stream);
+/* CTC best-path decode (BASELINE.json config 5): arg-max per frame, merge repeats, drop `blank`.  logits (B*L, ld);
+ * out_ids int32 (B, L) padded with -1, out_lens int32[B].  The reference has no CTC decode; the oracle is
+ * torch.argmax + collapse on the reference's w_aux logits. */
+int sst_ctc_greedy(int logits_dtype, int B, int L, int C, int blank, const void* logits, int64_t ld, const int32_t* in_lens,
+                   int32_t* out_ids, int32_t* out_lens, void* stream);
 int sst_ce_sumexp_loss(int logits_dtype, int grad_dtype, int64_t rows, int S, int C, const void* logits, int64_t ld,
                        const int64_t* target, int ignore, float eps, int64_t n_valid, float gcoef, float* row_ws, void* grad,
                        int64_t ldg, float* loss_out, void* stream);
