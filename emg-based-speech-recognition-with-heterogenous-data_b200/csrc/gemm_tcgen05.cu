@@ -50,7 +50,8 @@ template <int BN> struct GemmCfg {
   static constexpr int STAGE_BYTES = G_A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;                       // two accumulator buffers
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = G_EPI_WARPS * 2048;        // per epilogue warp: 32 rows x 64 B of bf16 output
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STAGING_BYTES;
 };
 
 __device__ __forceinline__ void decode_unit(const GemmKParams& p, int u, int& m0, int& n0, int& kb0, int& kb1) {
@@ -73,6 +74,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull = empty + Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -231,6 +233,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         row_ok = row_ok && t >= 0 && t < p.remap_T;
         out_row = (long)chunk * p.remap_T + t;
       }
+      // Coalesced bf16 stores: the warp's (32 rows x 32 columns) chunk is transposed through shared memory so that one store
+      // instruction writes 8 rows x 64 contiguous bytes (full sectors) instead of 32 rows x 16 bytes.  Lane l stores the
+      // 16-byte piece (l & 3) of rows it*8 + (l >> 2); the row bookkeeping of those rows comes from their owner lanes.
+      const bool staged = !p.atomic_out && !p.out_f32 && !(p.epilogue & SST_EPI_ACCUM) && (p.ldc & 7) == 0;
+      long st_row[4];
+      bool st_ok[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int src = it * 8 + (lane >> 2);
+        st_row[it] = __shfl_sync(0xffffffffu, out_row, src);
+        st_ok[it] = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, src) != 0;
+      }
+      const uint32_t stg = ptx::smem_u32(staging) + (uint32_t)(warp - 2) * 2048;
 #pragma unroll
       for (int lc0 = 0; lc0 < CPW; ++lc0) {
         const int c = cg * CPW + lc0;
@@ -239,7 +254,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         ptx::tmem_ld_32x32b_x32(taddr, r);
         ptx::tmem_ld_wait();
         const int nbase = n0 + c * 32;
-        if (row_ok && nbase < p.N) {
+        const bool chunk_staged = staged && nbase + 32 <= p.N;          // warp-uniform
+        if ((row_ok || chunk_staged) && nbase < p.N) {
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
@@ -263,7 +279,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int i = 0; i < 32; ++i) v[i] *= ((mb >> i) & 1u) ? p.mask_scale : 0.f;
           }
           const long cb = out_row * p.ldc + nbase;
-          if (p.atomic_out) {
+          if (chunk_staged) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j * 8 + 2 * i], v[j * 8 + 2 * i + 1]);
+                w4[i] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              ptx::st_shared_v4(stg + lane * 64 + ((uint32_t)(j ^ ((lane >> 1) & 3)) << 4), w4[0], w4[1], w4[2], w4[3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int rl = it * 8 + (lane >> 2), piece = lane & 3;
+              uint4 o;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                           : "r"(stg + rl * 64 + ((uint32_t)(piece ^ ((rl >> 1) & 3)) << 4)));
+              if (st_ok[it])
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + st_row[it] * p.ldc + nbase + piece * 8) = o;
+            }
+            __syncwarp();
+          } else if (!row_ok) {
+            // nothing to store for this lane
+          } else if (p.atomic_out) {
             float* cp = reinterpret_cast<float*>(p.C) + cb;
             if (ncols == 32 && (p.ldc & 3) == 0) {
 #pragma unroll
