@@ -12,12 +12,27 @@
 
 namespace sst {
 
-__global__ void shift_left_kernel(float* __restrict__ x, long n_chunks, int Tlen, int Cc, int r) {
-  const long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= n_chunks * Cc) return;
-  float* p = x + (id / Cc) * (long)Tlen * Cc + (id % Cc);
-  for (int t = 0; t < Tlen - r; ++t) p[(long)t * Cc] = p[(long)(t + r) * Cc];
-  for (int t = Tlen - r; t < Tlen; ++t) p[(long)t * Cc] = 0.f;
+// one block per chunk, in place: every thread first reads its (shifted) elements, the block synchronises, then writes
+constexpr int SHIFT_PER_THREAD = 64;
+__global__ void __launch_bounds__(256)
+shift_left_kernel(float* __restrict__ x, long n_chunks, int Tlen, int Cc, int r) {
+  float* p = x + (long)blockIdx.x * Tlen * Cc;
+  const int n = Tlen * Cc, lim = (Tlen - r) * Cc, off = r * Cc;
+  for (int base = 0; base < n; base += 256 * SHIFT_PER_THREAD) {     // chunks longer than 16 K elements: sequential passes
+    float v[SHIFT_PER_THREAD];                                       // pass k only reads elements >= its own range: safe
+#pragma unroll
+    for (int k = 0; k < SHIFT_PER_THREAD; ++k) {
+      const int e = base + k * 256 + threadIdx.x;
+      v[k] = (e < lim) ? p[e + off] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SHIFT_PER_THREAD; ++k) {
+      const int e = base + k * 256 + threadIdx.x;
+      if (e < n) p[e] = v[k];
+    }
+    __syncthreads();
+  }
 }
 
 // x: (n, Tin, 8) fp32 -> col: (n*Tin/2, 32):  [k*8 + c] = x[2t+k-1][c] (zero outside), [24 + c] = x[2t][c]
@@ -144,6 +159,36 @@ __global__ void permute3_cast_kernel(const TI* __restrict__ in, TO* __restrict__
   }
 }
 
+// Same mapping for the transposing cases (unit input stride along one of (j, k), unit output stride along the other):
+// a 32 x 32 tile of (j, k) goes through shared memory so that both the global read and the global write are coalesced.
+// IN_J: the input is contiguous along j (s1 == 1) and the output along k (o2 == 1); otherwise the reverse.
+template <typename TI, typename TO, bool IN_J>
+__global__ void __launch_bounds__(256)
+permute3_tiled_kernel(const TI* __restrict__ in, TO* __restrict__ out, long d1, long d2, long s0, long s1, long s2, long o0, long o1,
+                      long o2, int accumulate) {
+  __shared__ float tile[32][33];
+  const long a = blockIdx.z, j0 = (long)blockIdx.y * 32, k0 = (long)blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    // read: tx runs along the input's contiguous dim
+    const long j = IN_J ? j0 + tx : j0 + r, k = IN_J ? k0 + r : k0 + tx;
+    if (j < d1 && k < d2) tile[IN_J ? r : tx][IN_J ? tx : r] = to_f32(in[a * s0 + j * s1 + k * s2]);   // tile[k - k0][j - j0] when IN_J
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    // write: tx runs along the output's contiguous dim
+    const long j = IN_J ? j0 + r : j0 + tx, k = IN_J ? k0 + tx : k0 + r;
+    if (j < d1 && k < d2) {
+      const long oi = a * o0 + j * o1 + k * o2;
+      float v = tile[IN_J ? tx : r][IN_J ? r : tx];
+      if (accumulate) v += to_f32(out[oi]);
+      out[oi] = from_f32<TO>(v);
+    }
+  }
+}
+
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
                              float lr, float beta1, float beta2, float eps, float wd, float bc1, float sqrt_bc2) {
   for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long)gridDim.x * blockDim.x * 4) {
@@ -187,8 +232,8 @@ extern "C" {
 int sst_shift_left(float* x, int64_t n_chunks, int T, int Cc, int r, void* stream) {
   SST_REQUIRE(r >= 0 && r < T, SST_E_ARG, "shift_left: bad shift %d", r);
   if (r == 0 || n_chunks <= 0) return SST_OK;
-  const long ids = n_chunks * Cc;
-  shift_left_kernel<<<(int)((ids + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, n_chunks, T, Cc, r);
+  SST_REQUIRE((long)r * Cc <= 256L * SHIFT_PER_THREAD, SST_E_ARG, "shift_left: shift %d too large for the in-place passes", r);
+  shift_left_kernel<<<(int)n_chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, n_chunks, T, Cc, r);
   return check_launch("shift_left");
 }
 
@@ -255,8 +300,23 @@ int sst_permute3_cast(int in_dtype, int out_dtype, const void* in, void* out, in
   const long total = d0 * d1 * d2;
   if (total <= 0) return SST_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int grid = ew_grid2(total, 256);
   typedef __nv_bfloat16 bf;
+  const bool in_j = (s1 == 1 && o2 == 1 && s2 != 1), in_k = (s2 == 1 && o1 == 1 && o2 != 1);
+  if ((in_j || in_k) && d1 >= 32 && d2 >= 32 && d0 <= 65535 && (d1 + 31) / 32 <= 65535) {
+    const dim3 grid((unsigned)((d2 + 31) / 32), (unsigned)((d1 + 31) / 32), (unsigned)d0), block(32, 8);
+#define SST_P3T(TI_, TO_)                                                                                                    \
+    do {                                                                                                                     \
+      if (in_j) permute3_tiled_kernel<TI_, TO_, true><<<grid, block, 0, st>>>((const TI_*)in, (TO_*)out, d1, d2, s0, s1, s2, o0, o1, o2, accumulate); \
+      else permute3_tiled_kernel<TI_, TO_, false><<<grid, block, 0, st>>>((const TI_*)in, (TO_*)out, d1, d2, s0, s1, s2, o0, o1, o2, accumulate);    \
+    } while (0)
+    if (in_dtype == SST_F32 && out_dtype == SST_F32) SST_P3T(float, float);
+    else if (in_dtype == SST_F32) SST_P3T(float, bf);
+    else if (out_dtype == SST_F32) SST_P3T(bf, float);
+    else SST_P3T(bf, bf);
+#undef SST_P3T
+    return check_launch("permute3_cast");
+  }
+  const int grid = ew_grid2(total, 256);
   if (in_dtype == SST_F32 && out_dtype == SST_F32) permute3_cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, d0, d1, d2, s0, s1, s2, o0, o1, o2, accumulate);
   else if (in_dtype == SST_F32) permute3_cast_kernel<float, bf><<<grid, 256, 0, st>>>((const float*)in, (bf*)out, d0, d1, d2, s0, s1, s2, o0, o1, o2, accumulate);
   else if (out_dtype == SST_F32) permute3_cast_kernel<bf, float><<<grid, 256, 0, st>>>((const bf*)in, (float*)out, d0, d1, d2, s0, s1, s2, o0, o1, o2, accumulate);

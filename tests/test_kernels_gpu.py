@@ -314,6 +314,24 @@ def test_embed_gather_shift_permute_adamw(L):
     acc = torch.ones(4, 64, 16, device=DEV)
     L.permute3_cast(pk, acc, (4, 64, 16), (16 * 64, 1, 64), (64 * 16, 16, 1), accumulate=True)
     assert rel(acc, 1 + w.bfloat16().float()) < 1e-6
+    # the real chunk shape of the training-time shift (architecture.py:104-108), every shift amount
+    x = torch.randn(3, 1600, 8, device=DEV, generator=g)
+    for r in range(1, 8):
+        xs = x.clone()
+        L.shift_left(xs, 3, 1600, 8, r)
+        assert torch.equal(xs, O.shift_left_(x.cpu().clone(), r).to(DEV)), r
+    # tiled transposing paths of permute3_cast (both orientations, ragged tile edges, dtype casts, accumulate)
+    a3 = torch.randn(3, 70, 100, device=DEV, generator=g)
+    t1 = torch.empty(3, 100, 70, device=DEV, dtype=torch.bfloat16)                  # input contiguous along k, output along j
+    L.permute3_cast(a3, t1, (3, 70, 100), (7000, 100, 1), (7000, 1, 70))
+    assert torch.equal(t1, a3.transpose(1, 2).contiguous().bfloat16())
+    t2 = torch.ones(3, 100, 70, device=DEV)                                          # input contiguous along j, output along k
+    L.permute3_cast(a3, t2, (3, 100, 70), (7000, 1, 100), (7000, 70, 1), accumulate=True)
+    assert rel(t2, 1 + a3.transpose(1, 2)) < 1e-6
+    wlin = torch.randn(768, 3072, device=DEV, generator=g)
+    wt = torch.empty(3072, 768, device=DEV, dtype=torch.bfloat16)
+    L.permute3_cast(wlin, wt, (1, 3072, 768), (0, 1, 3072), (0, 768, 1))
+    assert torch.equal(wt, wlin.t().contiguous().bfloat16())
     # adamw vs torch
     n = 1003 * 4
     p = torch.randn(n, device=DEV, generator=g); gr = torch.randn(n, device=DEV, generator=g) * 1e-3
