@@ -292,7 +292,8 @@ int attn_fwd_tc_launch(const SstAttnDesc& d, const void* q, const void* k, const
 
 int attn_bwd_tc_launch(const SstAttnDesc& d, const void* q, const void* k, const void* v, const void* E, const int* q_lens,
                        const int* k_lens, const void* o, const float* lse, const void* dO, void* dq, void* dk, void* dv,
-                       float* delta, cudaStream_t st);
+                       float* delta, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t attn_bwd_tc_ws_bytes(const SstAttnDesc& d);
 
 static bool use_tc(const SstAttnDesc& d) { return d.dtype == SST_BF16 && !d.force_simt && d.dh == 96; }
 
@@ -320,14 +321,20 @@ int sst_attn_fwd(const SstAttnDesc* d, const void* q, const void* k, const void*
   return attn_fwd_simt_launch(*d, q, k, v, E, q_lens, k_lens, o, lse, reinterpret_cast<cudaStream_t>(stream));
 }
 
+size_t sst_attn_bwd_workspace_bytes(const SstAttnDesc* d) {
+  if (!d || !use_tc(*d) || d->B * d->H * d->Lq == 0) return 0;
+  return attn_bwd_tc_ws_bytes(*d);
+}
+
 int sst_attn_bwd(const SstAttnDesc* d, const void* q, const void* k, const void* v, const void* E, const int32_t* q_lens,
                  const int32_t* k_lens, const void* o, const float* lse, const void* dO, void* dq, void* dk, void* dv,
-                 float* delta, void* stream) {
+                 float* delta, void* ws, size_t ws_bytes, void* stream) {
   int rc = attn_check(d, q, k, v, E);
   if (rc) return rc;
   if (d->B * d->H * d->Lq == 0) return SST_OK;
   if (use_tc(*d))
-    return attn_bwd_tc_launch(*d, q, k, v, E, q_lens, k_lens, o, lse, dO, dq, dk, dv, delta, reinterpret_cast<cudaStream_t>(stream));
+    return attn_bwd_tc_launch(*d, q, k, v, E, q_lens, k_lens, o, lse, dO, dq, dk, dv, delta, ws, ws_bytes,
+                              reinterpret_cast<cudaStream_t>(stream));
   return attn_bwd_simt_launch(*d, q, k, v, E, q_lens, k_lens, o, lse, dO, dq, dk, dv, delta, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -23,6 +23,8 @@ constexpr int PBW = 192;           // relative offsets a (BM x BN) tile can touc
 constexpr float NEG_MASK = -1e8f;  // the reference's masked_fill / out-of-range value (transformer.py:181-196, :354-357)
 constexpr float NEG_BIG = -3.0e38f;  // keys that do not exist (j >= Lk): excluded from the softmax altogether
 
+struct AttnTcParams;
+
 struct AttnTcParams {
   int B, H, Lq, Lk, Lkp;           // Lkp = Lk rounded up to 8: pitch of the dropout counter space
   int causal, mask_q_rows, R, band;
@@ -36,7 +38,23 @@ struct AttnTcParams {
   const __nv_bfloat16* dO;                 // pitch ldo
   float* delta;                            // [B*H*Lq]  dO_i . O_i   (written by the dQ kernel, read by the dK/dV kernel)
   __nv_bfloat16 *dq, *dk, *dv; long ldq, ldk, ldv;
+  // (query tile, key tile) hand-off between the two backward kernels: bf16 (128 x 64) tiles of P~ and of scale*dS, row-major,
+  // tile index = ((b*H + h)*nQT + u)*max_kt + (kt - first key tile of query tile u)
+  __nv_bfloat16 *ws_p, *ws_ds;
+  int nQT, max_kt;
 };
+
+// key tiles a query tile can touch at most (size of one query tile's slot row in the hand-off workspace)
+inline int attn_max_key_tiles(const SstAttnDesc& d) {
+  const int nkt = (d.Lk + BN - 1) / BN;
+  if (!(d.rel_dist > 0 && d.Lk > d.rel_dist)) return nkt;
+  const int m = (BM + 2 * d.rel_dist - 3) / BN + 2;
+  return m < nkt ? m : nkt;
+}
+inline size_t attn_bwd_ws_bytes(const SstAttnDesc& d) {
+  const size_t tiles = (size_t)d.B * d.H * ((d.Lq + BM - 1) / BM) * attn_max_key_tiles(d);
+  return 2 * tiles * BM * BN * sizeof(__nv_bfloat16);
+}
 
 inline AttnTcParams make_tc_params(const SstAttnDesc& d, const int* q_lens, const int* k_lens) {
   AttnTcParams p;

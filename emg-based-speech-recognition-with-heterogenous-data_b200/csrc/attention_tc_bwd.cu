@@ -8,8 +8,10 @@
 //        dQ += dS_rel E_win                          the bias term: dS scattered to its RELATIVE column j-i (the inverse of
 //                                                    the forward skew) in a (128 x 192) shared-memory tile
 //      also writes delta_i = dO_i . O_i for kernel 2.  No gradient flows to E.
-//   kernel 2 (dK, dV) one CTA = 64 keys of one (batch, head), loop over the query tiles (128) inside the band:
-//        same S / PB / dP and per-row math, then, transposed so that M = head dim (padded to 128 TMEM lanes), N = keys:
+//      and hands every (query tile, key tile) pair's P~ and scale*dS[unmasked] to kernel 2 as bf16 (128 x 64) tiles in a
+//      workspace (the expensive per-element recompute is NOT repeated).
+//   kernel 2 (dK, dV) one CTA = 64 keys of one (batch, head), loop over the query tiles (128) inside the band: a pure
+//      TMA -> tcgen05 pipeline (double-buffered), transposed so that M = head dim (padded to 128 TMEM lanes), N = keys:
 //        dV^T += dO^T P~        dK^T += Q^T (scale * dS[unmasked])      (A = dO / Q tiles read MN-major, B = P~ / dS tiles)
 #include "attention_tc.cuh"
 #include <stdlib.h>
@@ -72,6 +74,23 @@ __device__ __forceinline__ void tile_backward_row(const AttnTcParams& p, const R
       U[x] = pr;
     }
   }
+}
+
+template <int CW, int N>
+__device__ __forceinline__ void store_cols_bf16_global(__nv_bfloat16* dst, const float (&U)[N]) {
+#pragma unroll
+  for (int c = 0; c < CW / 8; ++c) {
+    uint4 o;
+    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int x = 0; x < 4; ++x) o2[x] = __floats2bfloat162_rn(U[c * 8 + 2 * x], U[c * 8 + 2 * x + 1]);
+    *reinterpret_cast<uint4*>(dst + c * 8) = o;
+  }
+}
+template <int CW>
+__device__ __forceinline__ void store_zero_cols_global(__nv_bfloat16* dst) {
+#pragma unroll
+  for (int c = 0; c < CW / 8; ++c) *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(0u, 0u, 0u, 0u);
 }
 
 }  // namespace attn_tc
@@ -222,6 +241,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       rel_addr[x] = rb + (uint32_t)(c >> 6) * Q_ATOM + ((uint32_t)(((c & 63) >> 3) ^ (li & 7)) << 4) + (uint32_t)(c & 7) * 2;
     }
   }
+  // this thread's slice (row li, columns [CW*hf, +CW)) of the query tile's first hand-off tile
+  const long tile0 = (((long)b * p.H + h) * p.nQT + blockIdx.x) * p.max_kt;
+  __nv_bfloat16* tile_p = p.ws_p + tile0 * BM * BN + li * BN + CW * hf;
+  __nv_bfloat16* tile_ds = p.ws_ds + tile0 * BM * BN + li * BN + CW * hf;
   uint32_t ph_s = 0, ph_ke = 1, ph_dq = 0;
   for (int t = t_lo; t <= t_hi; ++t) {
     const int buf = (t - t_lo) & 1;
@@ -253,7 +276,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
       for (int x = 0; x < CW; ++x) W[x] = ((mbits >> x) & 1u) ? 0.f : W[x] * p.scale;
       store_cols_bf16_sw128<CW>(ptx::smem_u32(sV + buf * NATOM * K_ATOM), li, CW * hf, W);
+      store_cols_bf16_global<CW>(tile_p + (long)(t - t_lo) * BM * BN, U);
+      store_cols_bf16_global<CW>(tile_ds + (long)(t - t_lo) * BM * BN, W);
     } else {
+      store_zero_cols_global<CW>(tile_p + (long)(t - t_lo) * BM * BN);
+      store_zero_cols_global<CW>(tile_ds + (long)(t - t_lo) * BM * BN);
       if (p.R > 0) {
 #pragma unroll
         for (int x = 0; x < CW; ++x) asm volatile("st.shared.u16 [%0], %1;" ::"r"(rel_addr[x]), "h"((uint16_t)0) : "memory");
@@ -307,185 +334,185 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// kernel 2: dK, dV
+// kernel 2: dK, dV from the hand-off tiles
 // ------------------------------------------------------------------------------------------------------------------
-template <int DH, int NSPLIT>
-__global__ void __launch_bounds__(128 * NSPLIT, 1)
-attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmE,
-                       const __grid_constant__ CUtensorMap tmDO, const attn_tc::AttnTcParams p) {
+// Persistent: grid = #SMs, every CTA walks the (batch, head, key tile) items blockIdx.x, blockIdx.x + gridDim.x, ...;
+// the (item, query tile) pairs form one stream through a two-stage shared-memory ring, the dV^T / dK^T accumulators are
+// double-buffered in TMEM so that the epilogue of one item runs under the MMAs of the next.
+struct DkvCursor {
+  int item, u, q_hi, b, h, kt;
+  bool first;     // first query tile of its item
+};
+
+template <int DH>
+__global__ void __launch_bounds__(160, 1)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                       const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmDS,
+                       const attn_tc::AttnTcParams p, int n_kt, int n_items) {
   using namespace attn_tc;
-  using SP = Split<NSPLIT>;
-  constexpr int CW = SP::CW;
   constexpr int NATOM = (DH + 63) / 64;
-  constexpr int Q_ATOM = BM * 128, K_ATOM = BN * 128, E_ATOM = PBW * 128;
-  constexpr uint32_t TM_S = 0, TM_PB = 64, TM_DP = 256, TM_DV = 320, TM_DK = 384;
+  constexpr int Q_ATOM = BM * 128;
+  constexpr int STAGE = 2 * NATOM * Q_ATOM + 2 * BM * 128;       // Q, dO (two 64-column groups each), P~, dS
+  constexpr int OUT_BYTES = BN * DH * 2;                         // one (64 keys x dh) bf16 output tile
   static_assert(NATOM == 2, "M = 128 TMEM lanes are fed from two 64-wide head-dim groups");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sK = smem;
-  uint8_t* sV = sK + NATOM * K_ATOM;
-  uint8_t* sQ = sV + NATOM * K_ATOM;
-  uint8_t* sDO = sQ + NATOM * Q_ATOM;
-  uint8_t* sE = sDO + NATOM * Q_ATOM;
-  uint8_t* sP = sE + NATOM * E_ATOM;
-  uint8_t* sdS = sP + BM * 128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + BM * 128);
-  uint64_t* bar_kv = bars, *bar_in = bars + 1, *bar_s = bars + 2, *bar_acc = bars + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint8_t* sOut = smem + 2 * STAGE;                              // dV tile then dK tile, row = key, dh contiguous
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 2 * OUT_BYTES);
+  uint64_t* bar_full = bars /* [2] */, *bar_done = bars + 2 /* [2] */, *bar_acc = bars + 4 /* [2] */, *bar_free = bars + 6 /* [2] */;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = w & 3, hf = w >> 2;
-  const int li = 32 * q + lane;
-  const int j0 = blockIdx.x * BN, h = blockIdx.y, b = blockIdx.z;
-  const bool leader = threadIdx.x == 0;
 
   if (w == 0) {
     if (lane == 0) {
-      ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmDO);
-      if (p.R > 0) ptx::prefetch_tmap(&tmE);
-      for (int k = 0; k < 4; ++k) ptx::mbar_init(&bars[k], 1);
+      ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmDO); ptx::prefetch_tmap(&tmP); ptx::prefetch_tmap(&tmDS);
+      for (int k = 0; k < 6; ++k) ptx::mbar_init(&bars[k], 1);
+      ptx::mbar_init(&bar_free[0], 4);
+      ptx::mbar_init(&bar_free[1], 4);
       ptx::fence_barrier_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_alloc(tmem_slot, 256);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
 
-  int q_lo, q_hi;
-  query_tile_range(p, j0, q_lo, q_hi);
-
-  const uint32_t in_bytes = 2 * NATOM * Q_ATOM + (p.R > 0 ? NATOM * E_ATOM : 0);
-  auto load_in = [&](int u) {
-    const int i0 = u * BM;
-    ptx::mbar_arrive_expect_tx(bar_in, in_bytes);
-#pragma unroll
-    for (int a = 0; a < NATOM; ++a) {
-      ptx::tma_load_2d(sQ + a * Q_ATOM, &tmQ, bar_in, h * DH + a * 64, b * p.Lq + i0);
-      ptx::tma_load_2d(sDO + a * Q_ATOM, &tmDO, bar_in, h * DH + a * 64, b * p.Lq + i0);
-    }
-    if (p.R > 0) {
-      const int e0 = (j0 - i0) - (BM - 1) + (p.R - 1);
-#pragma unroll
-      for (int a = 0; a < NATOM; ++a) ptx::tma_load_2d(sE + a * E_ATOM, &tmE, bar_in, a * 64, h * (2 * p.R - 1) + e0);
-    }
+  auto open_item = [&](DkvCursor& c) -> bool {        // position the cursor on the first query tile of c.item
+    if (c.item >= n_items) return false;
+    c.kt = c.item % n_kt;
+    const int bh = c.item / n_kt;
+    c.h = bh % p.H; c.b = bh / p.H;
+    int q_lo;
+    query_tile_range(p, c.kt * BN, q_lo, c.q_hi);
+    c.u = q_lo; c.first = true;
+    return true;
+  };
+  auto advance = [&](DkvCursor& c) -> bool {
+    if (c.u < c.q_hi) { ++c.u; c.first = false; return true; }
+    c.item += gridDim.x;
+    return open_item(c);
   };
 
-  const uint32_t qb = ptx::smem_u32(sQ), dob = ptx::smem_u32(sDO), kb = ptx::smem_u32(sK), vb = ptx::smem_u32(sV),
-                 eb = ptx::smem_u32(sE), pb = ptx::smem_u32(sP), dsb = ptx::smem_u32(sdS);
-  if (leader) {
-    ptx::mbar_arrive_expect_tx(bar_kv, 2 * NATOM * K_ATOM);
+  if (w == 4) {
+    if (lane == 0) {
+      auto load = [&](const DkvCursor& c, int g) {
+        const int st = g & 1;
+        uint8_t* sb = smem + st * STAGE;
+        int t_lo, t_hi;
+        key_tile_range(p, c.u * BM, t_lo, t_hi);
+        const long tile = (((long)c.b * p.H + c.h) * p.nQT + c.u) * p.max_kt + (c.kt - t_lo);
+        ptx::mbar_arrive_expect_tx(&bar_full[st], STAGE);
 #pragma unroll
-    for (int a = 0; a < NATOM; ++a) {
-      ptx::tma_load_2d(sK + a * K_ATOM, &tmK, bar_kv, h * DH + a * 64, b * p.Lk + j0);
-      ptx::tma_load_2d(sV + a * K_ATOM, &tmV, bar_kv, h * DH + a * 64, b * p.Lk + j0);
-    }
-    load_in(q_lo);
-    ptx::mbar_wait(bar_kv, 0);
-    ptx::mbar_wait(bar_in, 0);
-    ptx::tc_fence_after();
-    issue_s_pb_dp<DH>(tmem + TM_S, tmem + TM_PB, tmem + TM_DP, qb, dob, kb, vb, eb, p.R > 0);
-    ptx::umma_commit(bar_s);
-  }
-  __syncwarp();
-
-  const long nrows = (long)p.B * p.H * p.Lq;
-  uint32_t ph_s = 0, ph_in = 1, ph_acc = 0;
-  for (int u = q_lo; u <= q_hi; ++u) {
-    const int i = u * BM + li;
-    const bool valid = i < p.Lq;
-    const RowCtx rc = make_row_ctx(p, b, h, i);
-    float Lm = 0.f, Ll = 3.0e38f, delta = 0.f;
-    if (valid) { Lm = p.lse[rc.row_id]; Ll = p.lse[nrows + rc.row_id]; delta = p.delta[rc.row_id]; }
-
-    ptx::mbar_wait(bar_s, ph_s);
-    ph_s ^= 1u;
-    ptx::tc_fence_after();
-
-    if (!block_out_of_band<NSPLIT>(p, u * BM + 32 * q, j0 + CW * hf)) {
-      float U[SP::WIN_LD], W[CW];
-      uint32_t mbits;
-      const bool simple = tile_is_simple(p, rc, j0);
-      tile_logits<NSPLIT>(p, rc, tmem + TM_S + lane_base, tmem + TM_PB + lane_base, q, hf, lane, j0, simple, U, mbits);
-      tile_backward_row<NSPLIT>(p, rc, tmem + TM_DP + lane_base, j0, hf, Lm, Ll, delta, U, W);
-#pragma unroll
-      for (int x = 0; x < CW; ++x) W[x] = ((mbits >> x) & 1u) ? 0.f : W[x] * p.scale;
-      store_cols_bf16_sw128<CW>(pb, li, CW * hf, U);
-      store_cols_bf16_sw128<CW>(dsb, li, CW * hf, W);
-    } else {
-      store_zero_cols_sw128<CW>(pb, li, CW * hf);
-      store_zero_cols_sw128<CW>(dsb, li, CW * hf);
-    }
-
-    ptx::fence_proxy_async();
-    ptx::tc_fence_before();
-    __syncthreads();
-    if (leader) {
-      ptx::tc_fence_after();
+        for (int a = 0; a < NATOM; ++a) {
+          ptx::tma_load_2d(sb + a * Q_ATOM, &tmQ, &bar_full[st], c.h * DH + a * 64, c.b * p.Lq + c.u * BM);
+          ptx::tma_load_2d(sb + (NATOM + a) * Q_ATOM, &tmDO, &bar_full[st], c.h * DH + a * 64, c.b * p.Lq + c.u * BM);
+        }
+        ptx::tma_load_2d(sb + 2 * NATOM * Q_ATOM, &tmP, &bar_full[st], 0, (int)(tile * BM));
+        ptx::tma_load_2d(sb + 2 * NATOM * Q_ATOM + BM * 128, &tmDS, &bar_full[st], 0, (int)(tile * BM));
+      };
+      DkvCursor cur, nxt;
+      cur.item = blockIdx.x;
+      bool have = open_item(cur);
+      nxt = cur;
+      bool have_next = have && advance(nxt);
+      if (have) load(cur, 0);
+      if (have_next) load(nxt, 1);
       const uint32_t id_t = ptx::make_idesc_bf16(128, BN, 1, 1);       // M = head dim (two 64-wide groups), N = keys
-#pragma unroll
-      for (int ks = 0; ks < BM / 16; ++ks)
-        ptx::umma_bf16(tmem + TM_DV, ptx::make_smem_desc_sw128(dob + ks * 2048, Q_ATOM, 1024),
-                       ptx::make_smem_desc_sw128(pb + ks * 2048, Q_ATOM, 1024), id_t, (u > q_lo || ks > 0) ? 1u : 0u);
-#pragma unroll
-      for (int ks = 0; ks < BM / 16; ++ks)
-        ptx::umma_bf16(tmem + TM_DK, ptx::make_smem_desc_sw128(qb + ks * 2048, Q_ATOM, 1024),
-                       ptx::make_smem_desc_sw128(dsb + ks * 2048, Q_ATOM, 1024), id_t, (u > q_lo || ks > 0) ? 1u : 0u);
-      ptx::umma_commit(bar_acc);
-      if (u < q_hi) {
-        ptx::mbar_wait(bar_acc, ph_acc);            // Q, dO, E, P~ and dS tiles are free again
-        load_in(u + 1);
-        ptx::mbar_wait(bar_in, ph_in);
-        ph_in ^= 1u;
+      int g = 0, n_done_items = 0;
+      while (have) {
+        const int st = g & 1;
+        const int ab = n_done_items & 1;                               // TMEM accumulator buffer of the current item
+        if (cur.first && n_done_items >= 2) {                          // the epilogue has drained this buffer (item - 2)
+          ptx::mbar_wait(&bar_free[ab], (uint32_t)(((n_done_items >> 1) - 1) & 1));
+          ptx::tc_fence_after();
+        }
+        ptx::mbar_wait(&bar_full[st], (uint32_t)((g >> 1) & 1));
         ptx::tc_fence_after();
-        issue_s_pb_dp<DH>(tmem + TM_S, tmem + TM_PB, tmem + TM_DP, qb, dob, kb, vb, eb, p.R > 0);
-        ptx::umma_commit(bar_s);
+        const uint32_t qb = ptx::smem_u32(smem + st * STAGE), dob = qb + NATOM * Q_ATOM, pb = qb + 2 * NATOM * Q_ATOM,
+                       dsb = pb + BM * 128;
+        const uint32_t t_dv = tmem + ab * 128, t_dk = t_dv + 64;
+#pragma unroll
+        for (int ks = 0; ks < BM / 16; ++ks)
+          ptx::umma_bf16(t_dv, ptx::make_smem_desc_sw128(dob + ks * 2048, Q_ATOM, 1024),
+                         ptx::make_smem_desc_sw128(pb + ks * 2048, Q_ATOM, 1024), id_t, (!cur.first || ks > 0) ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < BM / 16; ++ks)
+          ptx::umma_bf16(t_dk, ptx::make_smem_desc_sw128(qb + ks * 2048, Q_ATOM, 1024),
+                         ptx::make_smem_desc_sw128(dsb + ks * 2048, Q_ATOM, 1024), id_t, (!cur.first || ks > 0) ? 1u : 0u);
+        ptx::umma_commit(&bar_done[st]);
+        const bool last_of_item = cur.u == cur.q_hi;
+        if (last_of_item) { ptx::umma_commit(&bar_acc[ab]); ++n_done_items; }
+        // move on: `nxt` (already loaded into stage st^1) becomes current; fetch the tile after it into stage st
+        cur = nxt; have = have_next;
+        if (have) {
+          have_next = advance(nxt);
+          if (have_next) {
+            ptx::mbar_wait(&bar_done[st], (uint32_t)((g >> 1) & 1));    // the MMAs just issued have finished reading stage st
+            load(nxt, g + 2);
+          }
+        }
+        ++g;
       }
     }
-    ph_acc ^= 1u;
-    __syncwarp();
-  }
-
-  ptx::mbar_wait(bar_acc, (uint32_t)((q_hi - q_lo) & 1));
-  ptx::tc_fence_after();
-  {
-    // TMEM lane = head-dim index d, column = key: transposed stores (a warp writes 32 consecutive d of one key row);
-    // column group hf stores keys [CW*hf, CW*hf + CW)
-    const int dcol = li;
+  } else {
+    // epilogue warps: TMEM lane = head-dim index d, column = key.  The (dh x 64) accumulators are transposed through shared
+    // memory and leave as 16-byte row pieces (a key row of dV / dK is dh contiguous bf16).
+    const uint32_t lane_base = (uint32_t)(w * 32) << 16;
+    const int dcol = w * 32 + lane, tid = threadIdx.x;
+    int n_items_done = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_items_done) {
+      const int kt = item % n_kt, bh = item / n_kt, h = bh % p.H, b = bh / p.H;
+      const int j0 = kt * BN, ab = n_items_done & 1;
+      ptx::mbar_wait(&bar_acc[ab], (uint32_t)((n_items_done >> 1) & 1));
+      ptx::tc_fence_after();
+      __nv_bfloat16* so = reinterpret_cast<__nv_bfloat16*>(sOut);
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      __nv_bfloat16* out = which == 0 ? p.dv : p.dk;
-      const long ld = which == 0 ? p.ldv : p.ldk;
-      float r[CW];
-      tmem_load_cols(tmem + (which == 0 ? TM_DV : TM_DK) + CW * hf + lane_base, r);
-      if (dcol < DH) {
+      for (int which = 0; which < 2; ++which) {
 #pragma unroll
-        for (int x = 0; x < CW; ++x) {
-          const int j = j0 + CW * hf + x;
-          if (j < p.Lk) out[((long)b * p.Lk + j) * ld + h * DH + dcol] = __float2bfloat16_rn(r[x]);
+        for (int c = 0; c < BN / 16; ++c) {
+          float r[16];
+          tmem_load_cols(tmem + ab * 128 + which * 64 + c * 16 + lane_base, r);
+          if (dcol < DH) {
+#pragma unroll
+            for (int x = 0; x < 16; ++x) so[(which * BN + c * 16 + x) * DH + dcol] = __float2bfloat16_rn(r[x]);
+          }
         }
       }
+      ptx::tc_fence_before();
       __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar_free[ab]);         // the issuer may reuse this accumulator buffer
+      ptx::named_bar_sync(1, 128);
+      constexpr int PIECES = DH / 8;                          // 16-byte pieces per key row
+      for (int k = tid; k < 2 * BN * PIECES; k += 128) {
+        const int which = k / (BN * PIECES), rem = k - which * BN * PIECES, jr = rem / PIECES, pc = rem - jr * PIECES;
+        const int j = j0 + jr;
+        if (j < p.Lk) {
+          const uint4 v = *reinterpret_cast<const uint4*>(so + (which * BN + jr) * DH + pc * 8);
+          __nv_bfloat16* out = which == 0 ? p.dv : p.dk;
+          const long ld = which == 0 ? p.ldv : p.ldk;
+          *reinterpret_cast<uint4*>(out + ((long)b * p.Lk + j) * ld + h * DH + pc * 8) = v;
+        }
+      }
+      ptx::named_bar_sync(1, 128);                            // sOut is rewritten by the next item
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (w == 0) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem, 512);
+    ptx::tmem_dealloc(tmem, 256);
   }
 }
 
 template <int NSPLIT>
 static int attn_bwd_tc_launch_n(const SstAttnDesc& d, const void* q, const void* k, const void* v, const void* E, const int* q_lens,
                                 const int* k_lens, const void* o, const float* lse, const void* dO, void* dq, void* dk, void* dv,
-                                float* delta, cudaStream_t st) {
+                                float* delta, void* ws, size_t ws_bytes, cudaStream_t st) {
   using namespace attn_tc;
   constexpr int DH = 96;
   constexpr int NATOM = 2;
@@ -506,19 +533,34 @@ static int attn_bwd_tc_launch_n(const SstAttnDesc& d, const void* q, const void*
   } else {
     tmE = tmK;
   }
+  SST_REQUIRE(ws != nullptr && ws_bytes >= attn_bwd_ws_bytes(d), SST_E_ARG, "attn_bwd: workspace of %zu bytes required (got %zu)",
+              attn_bwd_ws_bytes(d), ws_bytes);
+  p.nQT = cdiv(d.Lq, BM);
+  p.max_kt = attn_max_key_tiles(d);
+  const long tiles = (long)d.B * d.H * p.nQT * p.max_kt;
+  p.ws_p = reinterpret_cast<__nv_bfloat16*>(ws);
+  p.ws_ds = p.ws_p + tiles * BM * BN;
+  SST_REQUIRE(tiles * BM < (1L << 31), SST_E_ARG, "attn_bwd: hand-off workspace exceeds the TMA row coordinate range");
+  CUtensorMap tmP, tmDS;
+  if ((rc = make_tmap_bf16_2d(&tmP, p.ws_p, BN, tiles * BM, BN, 64, BM))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmDS, p.ws_ds, BN, tiles * BM, BN, 64, BM))) return rc;
   constexpr int SMEM_DQ = 2 * NATOM * BM * 128 + NATOM * BN * 128 + NATOM * PBW * 128 + 2 * NATOM * BN * 128 + (PBW / 64) * BM * 128 +
                           1024 + 64 + 128 * 4;
-  constexpr int SMEM_DKV = 2 * NATOM * BN * 128 + 2 * NATOM * BM * 128 + NATOM * PBW * 128 + 2 * BM * 128 + 1024 + 128;
+  constexpr int SMEM_DKV = 2 * (2 * NATOM * BM * 128 + 2 * BM * 128) + 2 * BN * DH * 2 + 1024 + 128;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<DH, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<DH, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV);
+      e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV);
     SST_REQUIRE(e == cudaSuccess, SST_E_LAUNCH, "cudaFuncSetAttribute(attn_bwd_tc): %s", cudaGetErrorString(e));
     attr_done = true;
   }
   attn_bwd_dq_tc_kernel<DH, NSPLIT><<<dim3(cdiv(d.Lq, BM), d.H, d.B), 128 * NSPLIT, SMEM_DQ, st>>>(tmQ, tmK, tmV, tmE, tmDO, p);
-  attn_bwd_dkv_tc_kernel<DH, NSPLIT><<<dim3(cdiv(d.Lk, BN), d.H, d.B), 128 * NSPLIT, SMEM_DKV, st>>>(tmQ, tmK, tmV, tmE, tmDO, p);
+  {
+    const int n_kt = cdiv(d.Lk, BN), n_items = n_kt * d.H * d.B;
+    const int grid = n_items < num_sms() ? n_items : num_sms();
+    attn_bwd_dkv_tc_kernel<DH><<<grid, 160, SMEM_DKV, st>>>(tmQ, tmDO, tmP, tmDS, p, n_kt, n_items);
+  }
   return check_launch("attn_bwd_tc", 2);
 }
 
@@ -534,10 +576,12 @@ int attn_tc_nsplit() {
 
 int attn_bwd_tc_launch(const SstAttnDesc& d, const void* q, const void* k, const void* v, const void* E, const int* q_lens,
                        const int* k_lens, const void* o, const float* lse, const void* dO, void* dq, void* dk, void* dv,
-                       float* delta, cudaStream_t st) {
+                       float* delta, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (attn_tc_nsplit() == 2)
-    return attn_bwd_tc_launch_n<2>(d, q, k, v, E, q_lens, k_lens, o, lse, dO, dq, dk, dv, delta, st);
-  return attn_bwd_tc_launch_n<4>(d, q, k, v, E, q_lens, k_lens, o, lse, dO, dq, dk, dv, delta, st);
+    return attn_bwd_tc_launch_n<2>(d, q, k, v, E, q_lens, k_lens, o, lse, dO, dq, dk, dv, delta, ws, ws_bytes, st);
+  return attn_bwd_tc_launch_n<4>(d, q, k, v, E, q_lens, k_lens, o, lse, dO, dq, dk, dv, delta, ws, ws_bytes, st);
 }
+
+size_t attn_bwd_tc_ws_bytes(const SstAttnDesc& d) { return attn_tc::attn_bwd_ws_bytes(d); }
 
 }  // namespace sst

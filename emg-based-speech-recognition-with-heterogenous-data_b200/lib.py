@@ -209,10 +209,31 @@ def attn_fwd(d, q, k, v, E, q_lens, k_lens, o, lse):
                                  stream()), "sst_attn_fwd")
 
 
-def attn_bwd(d, q, k, v, E, q_lens, k_lens, o, lse, dO, dq, dk, dv, delta):
+_attn_ws = {}
+
+
+def attn_bwd_workspace(d, device):
+    """Scratch for sst_attn_bwd (hand-off tiles between its two kernels): one buffer per device, grown on demand and shared
+    by every attention call of the step (calls on one stream are ordered)."""
+    lib().sst_attn_bwd_workspace_bytes.restype = C.c_size_t
+    need = int(lib().sst_attn_bwd_workspace_bytes(C.byref(d)))
+    if need == 0:
+        return None, 0
+    buf = _attn_ws.get(device)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(need, dtype=torch.uint8, device=device)
+        _attn_ws[device] = buf
+    return buf, need
+
+
+def attn_bwd(d, q, k, v, E, q_lens, k_lens, o, lse, dO, dq, dk, dv, delta, ws=None):
+    if ws is None:
+        ws, _ = attn_bwd_workspace(d, q.device)
+    nbytes = ws.numel() * ws.element_size() if ws is not None else 0
     with _scope("attn_bwd", attn_work(d)[1] if _profiler is not None else 0.0, tag="Lq%d Lk%d R%d" % (d.Lq, d.Lk, d.rel_dist)):
         check(lib().sst_attn_bwd(C.byref(d), ptr(q), ptr(k), ptr(v), ptr(E), ptr(q_lens), ptr(k_lens), ptr(o), ptr(lse),
-                                 ptr(dO), ptr(dq), ptr(dk), ptr(dv), ptr(delta), stream()), "sst_attn_bwd")
+                                 ptr(dO), ptr(dq), ptr(dk), ptr(dv), ptr(delta), ptr(ws), C.c_size_t(nbytes), stream()),
+              "sst_attn_bwd")
 
 
 def layernorm_fwd(dtype, rows, D, x, r, drop_p, seed, gamma, beta, y, s_out, mean, rstd, eps=1e-5):

@@ -158,10 +158,14 @@ typedef struct SstAttnDesc {
 
 int sst_attn_fwd(const SstAttnDesc* d, const void* q, const void* k, const void* v, const void* E, const int32_t* q_lens,
                  const int32_t* k_lens, void* o, float* lse, void* stream);
-/* dq/dk/dv use the pitches of q/k/v; delta is a caller-provided float[B*H*Lq] scratch. */
+/* dq/dk/dv use the pitches of q/k/v; delta is a caller-provided float[B*H*Lq] scratch; ws a caller-provided scratch of
+ * sst_attn_bwd_workspace_bytes(d) bytes (16-byte aligned; 0 bytes / NULL allowed for the CUDA-core path): the tensor-core
+ * path hands the recomputed probabilities and logit gradients of every (query tile, key tile) pair from its dQ kernel to
+ * its dK/dV kernel through it instead of recomputing them. */
+size_t sst_attn_bwd_workspace_bytes(const SstAttnDesc* d);
 int sst_attn_bwd(const SstAttnDesc* d, const void* q, const void* k, const void* v, const void* E, const int32_t* q_lens,
                  const int32_t* k_lens, const void* o, const float* lse, const void* dO, void* dq, void* dk, void* dv,
-                 float* delta, void* stream);
+                 float* delta, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Losses (recognition_model.py:93-107).
