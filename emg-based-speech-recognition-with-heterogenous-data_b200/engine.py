@@ -499,6 +499,62 @@ class Engine:
         L.ctc_greedy(L.F32, ctx.B, ctx.Lmax, self.n_out_enc, self.n_out_enc - 1, logits, self.LDH, ctx.lens, ids, lens)
         return ids, lens
 
+    # ------------------------------------------------------------------------------------------------ incremental decoding
+    def greedy_cached(self, mem, mem_lens, B, Lm, max_seq_length, start_tok, eos_tok, check_every=4):
+        """Greedy attention-decoder search with key/value caches: the decoder runs on ONE new position
+        per step; self-attention keys/values of earlier positions and the cross-attention keys/values of the memory are
+        computed once.  Equivalent to re-running the decoder on the whole prefix (greedy_search.py:19-38) as long as no PAD id
+        is generated (a PAD position is masked as a key AND as a query row there, which makes earlier rows depend on the
+        prefix length) -- the caller checks and falls back.  Arg-max, append and the stop test stay on the device; the host
+        looks at the `done` flags every `check_every` steps.  Returns the (B, n) int64 device tensor of prefixes."""
+        D, H = self.D, self.H
+        Tmax = max_seq_length - 1                                   # decoder input positions
+        tokens = torch.full((B, max_seq_length), PAD, dtype=torch.int64, device=self.dev)
+        tokens[:, 0] = start_tok
+        done = torch.zeros(B, dtype=torch.bool, device=self.dev)
+        cross, cache = [], []
+        for i in range(self.n_dec):
+            m = "transformerDecoder.layers.%d.multihead_attn" % i
+            cross.append(self._linear_fwd(mem, B * Lm, m + ".kv"))
+            cache.append(self.zeros(B * Tmax, 2 * D))
+        klen = torch.zeros(B, dtype=torch.int32, device=self.dev)
+        seeds = Engine._Seeds(0)
+        n = 1
+        for s in range(Tmax):
+            y = tokens[:, s:s + 1].contiguous()
+            t = self.empty(B, D)
+            L.embed_posenc_fwd(self.dt, y, self.P["embedding_tgt.weight"], self.Bf["pos_decoder.pe"], t, B, 1, D, 0.0, 0)
+            klen.fill_(s + 1)
+            for i in range(self.n_dec):
+                pfx = "transformerDecoder.layers.%d" % i
+                a, m = pfx + ".self_attn", pfx + ".multihead_attn"
+                qkv = self._linear_fwd(t, B, a + ".qkv")
+                kv_s = cache[i].view(B, Tmax, 2 * D)[:, s]          # rows b*Tmax + s
+                L.permute3_cast(qkv[:, D:], kv_s, (1, B, 2 * D), (0, 3 * D, 1), (0, Tmax * 2 * D, 1))
+                o1 = self.empty(B, D)
+                lse = self.empty(2 * B * H, dtype=torch.float32)
+                ad1 = self._attn_desc(B, 1, Tmax, 3 * D, 2 * D, 2 * D, False, False, 0, 0.0, 0)
+                L.attn_fwd(ad1, qkv, cache[i], cache[i][:, D:], None, None, klen, o1, lse)
+                y1 = self._linear_fwd(o1, B, a + ".o.T")
+                t1, _ = self._ln_fwd(t, y1, B, pfx + ".norm1", 0.0, 0)
+                q = self._linear_fwd(t1, B, m + ".q")
+                o2 = self.empty(B, D)
+                ad2 = self._attn_desc(B, 1, Lm, D, 2 * D, 2 * D, False, False, 0, 0.0, 0)
+                L.attn_fwd(ad2, q, cross[i], cross[i][:, D:], None, None, mem_lens, o2, lse)
+                y2 = self._linear_fwd(o2, B, m + ".o.T")
+                t2, _ = self._ln_fwd(t1, y2, B, pfx + ".norm2", 0.0, 0)
+                hid = self._linear_fwd(t2, B, pfx + ".linear1", bias=self.P[pfx + ".linear1.bias"], relu=True)
+                y3 = self._linear_fwd(hid, B, pfx + ".linear2", bias=self.P[pfx + ".linear2.bias"])
+                t, _ = self._ln_fwd(t2, y3, B, pfx + ".norm3", 0.0, 0)
+            logits = self.dec_head(t, B)
+            pred = torch.argmax(logits[:, :self.n_out_dec], dim=1)
+            tokens[:, s + 1] = pred
+            done |= pred == eos_tok
+            n = s + 2
+            if n >= max_seq_length or ((s + 1) % check_every == 0 and bool(done.all())):
+                break
+        return tokens[:, :n]
+
     def decode(self, y, tgt_lens, mem, mem_lens, B, Lm, training, seeds, ctx=None, tgt_pad=None):
         """y: (B, S) int64 CUDA; returns x_dec (B*S, D).  Target padding is either a suffix (`tgt_lens`, the training
         batches of pad_sequence) or an arbitrary per-position mask `tgt_pad` (uint8 (B, S); greedy prefixes, where a

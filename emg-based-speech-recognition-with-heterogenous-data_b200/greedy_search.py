@@ -49,10 +49,29 @@ def greedy_ids(model, length_raw_signal, X_raw, max_seq_length, device, start_to
     return dec_input.cpu()
 
 
-def run_greedy(model, length_raw_signal, X_raw, tgt, vocab_size, device):
+def greedy_ids_cached(model, length_raw_signal, X_raw, max_seq_length, device, start_tok=SOS):
+    """Same search with key/value caches (one new decoder position per step, stop test on the device).  Falls back to the
+    prefix re-run when a PAD id was generated, the one case where the two are not equivalent (Engine.greedy_cached)."""
+    memory, _ = model(length_raw_signal, device, mode='greedy_search', part='encoder', x_raw=X_raw)
+    eng = model._packed_engine()
+    B, Lm = model._mem_shape
+    with torch.no_grad():
+        ids = eng.greedy_cached(memory.reshape(B * Lm, eng.D), model._mem_lens, B, Lm, max_seq_length, start_tok, EOS)
+    ids = ids.cpu()
+    first_eos = torch.where((ids == EOS).any(1), (ids == EOS).float().argmax(1), torch.full((B,), ids.shape[1]))
+    pad_before_eos = ((ids == PAD) & (torch.arange(ids.shape[1])[None, :] <= first_eos[:, None])).any()
+    if bool(pad_before_eos):
+        return greedy_ids(model, length_raw_signal, X_raw, max_seq_length, device, start_tok)
+    # the prefix re-run stops as soon as every sample has produced </S>; the cached loop looks every few steps only
+    n = int(min(ids.shape[1], max(int(first_eos.max()) + 1, 2))) if bool((ids == EOS).any(1).all()) else ids.shape[1]
+    return ids[:, :n]
+
+
+def run_greedy(model, length_raw_signal, X_raw, tgt, vocab_size, device, cached=True):
     batch_len = tgt.shape[0]
     max_seq_length = tgt.shape[1] + 1                      # +1 for the removed <S> (greedy_search.py:11)
-    ids = greedy_ids(model, length_raw_signal, X_raw, max_seq_length, device, start_tok=vocab_size - 2)
+    search = greedy_ids_cached if cached else greedy_ids
+    ids = search(model, length_raw_signal, X_raw, max_seq_length, device, start_tok=vocab_size - 2)
     pt = PhoneTransform()
     seqs = []
     for b in range(batch_len):

@@ -41,7 +41,7 @@ def test_run_greedy_matches_oracle_bit_exact():
     margins = []
     seqs, out = O.greedy_decode(sd, cfg, X.clone(), batch["lengths"], max_len, margins)
     tgt = torch.zeros(3, max_len - 1, dtype=torch.int64)
-    phones, ids = run_greedy(model, batch["lengths"], X.to(DEV), tgt, 43, DEV)
+    phones, ids = run_greedy(model, batch["lengths"], X.to(DEV), tgt, 43, DEV, cached=False)
     m = torch.stack(margins, 1)                             # (B, steps)
     print("min top-2 logit margin along the oracle's path: %.3e" % float(m.min()))
     ids = ids.cpu()
@@ -56,6 +56,23 @@ def test_run_greedy_matches_oracle_bit_exact():
         if upto == max_len:
             assert phones[b] == " ".join(phoneme_inventory[t] for t in seqs[b])
     assert sum(int((m[b] >= 1e-3).all()) for b in range(3)) >= 2, "at least two samples must be compared in full"
+
+
+def test_kv_cached_search_equals_prefix_rerun():
+    """Engine.greedy_cached (one new position per step, cached keys/values) == re-running the decoder on the whole prefix:
+    identical ids in fp32 mode (every kernel is row-independent), and identical strings / id tensors from run_greedy."""
+    from sst_b200.greedy_search import run_greedy, greedy_ids, greedy_ids_cached
+    cfg, sd, model = _setup(1, 2, wseed=11)
+    batch = O.synthetic_batch(seed=5, ragged=[120, 200, 80], tgt_lens=[12, 12, 12])
+    X = O.combine_fixed_length(batch["raw_emg"])
+    full = greedy_ids(model, batch["lengths"], X.to(DEV), 14, DEV)
+    cached = greedy_ids_cached(model, batch["lengths"], X.to(DEV), 14, DEV)
+    n = min(full.shape[1], cached.shape[1])
+    assert torch.equal(full[:, :n], cached[:, :n])
+    tgt = torch.zeros(3, 13, dtype=torch.int64)
+    p1, i1 = run_greedy(model, batch["lengths"], X.to(DEV), tgt, 43, DEV, cached=True)
+    p2, i2 = run_greedy(model, batch["lengths"], X.to(DEV), tgt, 43, DEV, cached=False)
+    assert p1 == p2 and torch.equal(i1.cpu(), i2.cpu())
 
 
 def test_decoder_with_pad_token_inside_the_prefix():
