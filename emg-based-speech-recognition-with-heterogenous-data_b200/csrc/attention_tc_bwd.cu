@@ -56,7 +56,7 @@ __device__ __forceinline__ void tile_backward_row(const AttnTcParams& p, const R
                                                   int hf, float Lm, float Ll, float delta, float (&U)[Split<NSPLIT>::WIN_LD],
                                                   float (&W)[Split<NSPLIT>::CW]) {
   constexpr int CW = Split<NSPLIT>::CW;
-  tmem_load_cols(tDP + (uint32_t)(CW * hf), W);
+  if (tDP != 0xffffffffu) tmem_load_cols(tDP + (uint32_t)(CW * hf), W);      // 0xffffffff: W already holds the dP slice
   if (p.thr) {
     float keep[CW];
     dropout_keep<NSPLIT>(p, rc, j0, hf, keep);
@@ -98,47 +98,49 @@ __device__ __forceinline__ void store_zero_cols_global(__nv_bfloat16* dst) {
 // ------------------------------------------------------------------------------------------------------------------
 // kernel 1: dQ (and delta)
 // ------------------------------------------------------------------------------------------------------------------
+// Warp-specialised: 4*NSPLIT compute warps + 1 issuer warp.  Q and dO live in TMEM (A operands read from tensor memory,
+// 48 columns each) which leaves shared memory for double-buffered K / E_win / V stages; the compute warps release the
+// S / PB / dP accumulators as soon as their slices are in registers, so tile t+1's MMAs and tile t+2's TMA loads run under
+// tile t's per-element math.  TMEM: S 0-63 | PB 64-255 | dP 256-319 | dQ 320-415 | Q 416-463 | dO 464-511.
 template <int DH, int NSPLIT>
-__global__ void __launch_bounds__(128 * NSPLIT, 1)
-attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmE,
-                      const __grid_constant__ CUtensorMap tmDO, const attn_tc::AttnTcParams p) {
+__global__ void __launch_bounds__(128 * NSPLIT + 32, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                      const __grid_constant__ CUtensorMap tmE, const attn_tc::AttnTcParams p, const __nv_bfloat16* __restrict__ qg) {
   using namespace attn_tc;
   using SP = Split<NSPLIT>;
   constexpr int CW = SP::CW;
+  constexpr int NW = 4 * NSPLIT;
+  constexpr int KS = DH / 16;
   constexpr int NATOM = (DH + 63) / 64;
   constexpr int Q_ATOM = BM * 128, K_ATOM = BN * 128, E_ATOM = PBW * 128;
   constexpr int REL_ATOMS = PBW / 64;
   constexpr int OC = DH / NSPLIT;
-  constexpr uint32_t TM_S = 0, TM_PB = 64, TM_DP = 256, TM_DQ = 320;
+  constexpr uint32_t TM_S = 0, TM_PB = 64, TM_DP = 256, TM_DQ = 320, TM_Q = 416, TM_DO = TM_Q + DH / 2;
+  static_assert(TM_DO + DH / 2 <= 512 && NSPLIT >= 2, "TMEM budget / roles");
+  static_assert(NATOM * K_ATOM == BM * 128, "the dS tile must fit one V buffer");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sDO = sQ + NATOM * Q_ATOM;
-  uint8_t* sK = sDO + NATOM * Q_ATOM;
-  uint8_t* sE = sK + NATOM * K_ATOM;
-  uint8_t* sV = sE + NATOM * E_ATOM;              // two buffers; buffer (t & 1) is reused for the dS tile once dP is done
+  uint8_t* sK = smem;                             // [2]
+  uint8_t* sE = sK + 2 * NATOM * K_ATOM;          // [2]
+  uint8_t* sV = sE + 2 * NATOM * E_ATOM;          // [2]; buffer (t & 1) is reused for the dS tile once dP(t) is done
   uint8_t* sRel = sV + 2 * NATOM * K_ATOM;        // (128 x 192) dS in relative coordinates, K-major, 3 swizzle atoms
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRel + REL_ATOMS * Q_ATOM);
-  uint64_t* bar_q = bars, *bar_ke = bars + 1, *bar_v = bars + 2 /* [2] */, *bar_s = bars + 4, *bar_dq = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-  float* sdelta = reinterpret_cast<float*>(bars + 8);       // [128]
-  static_assert(NATOM * K_ATOM == BM * 128, "the dS tile must fit one V buffer");
+  uint64_t* bar_ke = bars /* [2] */, *bar_v = bars + 2 /* [2] */, *bar_s = bars + 4, *bar_dq = bars + 5, *bar_sfree = bars + 6,
+           *bar_p = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* sdelta = reinterpret_cast<float*>(bars + 10);      // [128]
 
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = w & 3, hf = w >> 2;
-  const int li = 32 * q + lane;
   const int i0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
-  const int i = i0 + li;
-  const bool leader = threadIdx.x == 0;
-  const bool valid = i < p.Lq;
 
   if (w == 0) {
     if (lane == 0) {
-      ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmDO);
+      ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
       if (p.R > 0) ptx::prefetch_tmap(&tmE);
       for (int k = 0; k < 6; ++k) ptx::mbar_init(&bars[k], 1);
+      ptx::mbar_init(bar_sfree, NW);
+      ptx::mbar_init(bar_p, NW);
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -149,182 +151,226 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
 
   int t_lo, t_hi;
   key_tile_range(p, i0, t_lo, t_hi);
 
   const uint32_t ke_bytes = NATOM * K_ATOM + (p.R > 0 ? NATOM * E_ATOM : 0);
   auto load_ke = [&](int t) {
-    ptx::mbar_arrive_expect_tx(bar_ke, ke_bytes);
+    const int st = (t - t_lo) & 1;
+    ptx::mbar_arrive_expect_tx(&bar_ke[st], ke_bytes);
 #pragma unroll
-    for (int a = 0; a < NATOM; ++a) ptx::tma_load_2d(sK + a * K_ATOM, &tmK, bar_ke, h * DH + a * 64, b * p.Lk + t * BN);
+    for (int a = 0; a < NATOM; ++a)
+      ptx::tma_load_2d(sK + (st * NATOM + a) * K_ATOM, &tmK, &bar_ke[st], h * DH + a * 64, b * p.Lk + t * BN);
     if (p.R > 0) {
       const int e0 = (t * BN - i0) - (BM - 1) + (p.R - 1);
 #pragma unroll
-      for (int a = 0; a < NATOM; ++a) ptx::tma_load_2d(sE + a * E_ATOM, &tmE, bar_ke, a * 64, h * (2 * p.R - 1) + e0);
+      for (int a = 0; a < NATOM; ++a)
+        ptx::tma_load_2d(sE + (st * NATOM + a) * E_ATOM, &tmE, &bar_ke[st], a * 64, h * (2 * p.R - 1) + e0);
     }
   };
   auto load_v = [&](int t) {
-    const int buf = (t - t_lo) & 1;
-    ptx::mbar_arrive_expect_tx(&bar_v[buf], NATOM * K_ATOM);
+    const int st = (t - t_lo) & 1;
+    ptx::mbar_arrive_expect_tx(&bar_v[st], NATOM * K_ATOM);
 #pragma unroll
     for (int a = 0; a < NATOM; ++a)
-      ptx::tma_load_2d(sV + (buf * NATOM + a) * K_ATOM, &tmV, &bar_v[buf], h * DH + a * 64, b * p.Lk + t * BN);
+      ptx::tma_load_2d(sV + (st * NATOM + a) * K_ATOM, &tmV, &bar_v[st], h * DH + a * 64, b * p.Lk + t * BN);
   };
-
-  if (leader) {
-    ptx::mbar_arrive_expect_tx(bar_q, 2 * NATOM * Q_ATOM);
-#pragma unroll
-    for (int a = 0; a < NATOM; ++a) {
-      ptx::tma_load_2d(sQ + a * Q_ATOM, &tmQ, bar_q, h * DH + a * 64, b * p.Lq + i0);
-      ptx::tma_load_2d(sDO + a * Q_ATOM, &tmDO, bar_q, h * DH + a * 64, b * p.Lq + i0);
-    }
+  const bool issuer = (w == NW);
+  if (issuer && lane == 0) {        // the first loads do not depend on anything the compute warps set up
     load_ke(t_lo);
     load_v(t_lo);
+    if (t_lo < t_hi) { load_ke(t_lo + 1); load_v(t_lo + 1); }
   }
-  __syncwarp();
 
-  // zero the relative-coordinate dS tile once: a row only ever writes its own 64 columns [127 - li, 191 - li)
-  {
+  // ---- one-time setup by the compute warps: Q and dO rows into TMEM, delta, zeroed dS_rel tile ----
+  const int q = w & 3, hf = w >> 2;
+  const int li = 32 * q + lane;
+  const int i = i0 + li;
+  const bool valid = !issuer && i < p.Lq;
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+  const RowCtx rc = make_row_ctx(p, b, h, issuer ? 0 : i);
+  float Lm = 0.f, Ll = 3.0e38f, delta = 0.f;       // rows that do not exist: p = exp(-inf) = 0
+  if (!issuer) {
     const uint32_t rb = ptx::smem_u32(sRel);
     for (int k = threadIdx.x; k < REL_ATOMS * Q_ATOM / 16; k += SP::THREADS) ptx::st_shared_v4(rb + k * 16, 0u, 0u, 0u, 0u);
-  }
-  // delta_i = dO_i . O_i (column group 0 computes and shares it), saved softmax statistics
-  const RowCtx rc = make_row_ctx(p, b, h, i);
-  float Lm = 0.f, Ll = 3.0e38f, delta = 0.f;       // rows that do not exist: p = exp(-inf) = 0
-  if (valid) {
-    const long nrows = (long)p.B * p.H * p.Lq;
-    Lm = p.lse[rc.row_id];
-    Ll = p.lse[nrows + rc.row_id];
-    if (hf == 0) {
+    if (valid) {
+      const long nrows = (long)p.B * p.H * p.Lq;
+      Lm = p.lse[rc.row_id];
+      Ll = p.lse[nrows + rc.row_id];
+    }
+    if (hf < 2) {                                   // column group 0 moves the Q row, group 1 the dO row (and forms delta)
+      const __nv_bfloat16* src = (hf == 0 ? qg + ((long)b * p.Lq + i) * p.ldq : p.dO + ((long)b * p.Lq + i) * p.ldo) + h * DH;
       const __nv_bfloat16* orow = p.o + ((long)b * p.Lq + i) * p.ldo + h * DH;
-      const __nv_bfloat16* drow = p.dO + ((long)b * p.Lq + i) * p.ldo + h * DH;
 #pragma unroll
-      for (int c = 0; c < DH / 8; ++c) {
-        const uint4 a4 = *reinterpret_cast<const uint4*>(orow + c * 8), b4 = *reinterpret_cast<const uint4*>(drow + c * 8);
-        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a4);
-        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b4);
+      for (int c = 0; c < DH / 32; ++c) {           // 32 bf16 = 16 TMEM columns per store
+        uint32_t r[16];
 #pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          const float2 fa = __bfloat1622float2(a2[x]), fb = __bfloat1622float2(b2[x]);
-          delta = fmaf(fa.x, fb.x, delta);
-          delta = fmaf(fa.y, fb.y, delta);
+        for (int g = 0; g < 4; ++g) {
+          uint4 v4 = make_uint4(0u, 0u, 0u, 0u);
+          if (valid) v4 = *reinterpret_cast<const uint4*>(src + c * 32 + g * 8);
+          r[g * 4 + 0] = v4.x; r[g * 4 + 1] = v4.y; r[g * 4 + 2] = v4.z; r[g * 4 + 3] = v4.w;
+          if (hf == 1 && valid) {
+            const uint4 o4 = *reinterpret_cast<const uint4*>(orow + c * 32 + g * 8);
+            const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&o4);
+            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&v4);
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              const float2 fa = __bfloat1622float2(a2[x]), fb = __bfloat1622float2(b2[x]);
+              delta = fmaf(fa.x, fb.x, delta);
+              delta = fmaf(fa.y, fb.y, delta);
+            }
+          }
         }
+        ptx::tmem_st_32x32b_x16(tmem + (hf == 0 ? TM_Q : TM_DO) + c * 16 + lane_base, r);
       }
-      p.delta[rc.row_id] = delta;
+      ptx::tmem_st_wait();
+      if (hf == 1) {
+        sdelta[li] = delta;
+        if (valid) p.delta[rc.row_id] = delta;
+      }
     }
   }
-  if (hf == 0) sdelta[li] = delta;
+  ptx::tc_fence_before();
   __syncthreads();
-  delta = sdelta[li];
+  ptx::tc_fence_after();
 
-  const uint32_t qb = ptx::smem_u32(sQ), dob = ptx::smem_u32(sDO), kb = ptx::smem_u32(sK), eb = ptx::smem_u32(sE);
-  if (leader) {
-    ptx::mbar_wait(bar_q, 0);
-    ptx::mbar_wait(bar_ke, 0);
-    ptx::mbar_wait(&bar_v[0], 0);
-    ptx::tc_fence_after();
-    issue_s_pb_dp<DH>(tmem + TM_S, tmem + TM_PB, tmem + TM_DP, qb, dob, kb, ptx::smem_u32(sV), eb, p.R > 0);
-    ptx::umma_commit(bar_s);
-  }
-  __syncwarp();
-
-  // shared-memory address of this thread's CW relative columns c = (127 - li + CW*hf) + x in the swizzled dS_rel tile
-  uint32_t rel_addr[CW];
-  {
-    const uint32_t rb = ptx::smem_u32(sRel) + li * 128;
-    const int c0 = (BM - 1) - li + CW * hf;
+  if (issuer) {
+    // ============================================ issuer (one thread) ============================================
+    if (lane == 0) {
+      auto issue_s = [&](int st) {   // S = Q K^T, PB = Q E_win^T, dP = dO V^T from stage `st`; A operands from TMEM
+        const uint32_t kb = ptx::smem_u32(sK + st * NATOM * K_ATOM), eb = ptx::smem_u32(sE + st * NATOM * E_ATOM),
+                       vb = ptx::smem_u32(sV + st * NATOM * K_ATOM);
+        const uint32_t id_s = ptx::make_idesc_bf16(BM, BN, 0, 0), id_pb = ptx::make_idesc_bf16(BM, PBW, 0, 0);
 #pragma unroll
-    for (int x = 0; x < CW; ++x) {
-      const int c = c0 + x;
-      rel_addr[x] = rb + (uint32_t)(c >> 6) * Q_ATOM + ((uint32_t)(((c & 63) >> 3) ^ (li & 7)) << 4) + (uint32_t)(c & 7) * 2;
-    }
-  }
-  // this thread's slice (row li, columns [CW*hf, +CW)) of the query tile's first hand-off tile
-  const long tile0 = (((long)b * p.H + h) * p.nQT + blockIdx.x) * p.max_kt;
-  __nv_bfloat16* tile_p = p.ws_p + tile0 * BM * BN + li * BN + CW * hf;
-  __nv_bfloat16* tile_ds = p.ws_ds + tile0 * BM * BN + li * BN + CW * hf;
-  uint32_t ph_s = 0, ph_ke = 1, ph_dq = 0;
-  for (int t = t_lo; t <= t_hi; ++t) {
-    const int buf = (t - t_lo) & 1;
-    ptx::mbar_wait(bar_s, ph_s);
-    ph_s ^= 1u;
-    ptx::tc_fence_after();
-    if (leader && t < t_hi) load_v(t + 1);
-    __syncwarp();
-
-    const bool skip = block_out_of_band<NSPLIT>(p, i0 + 32 * q, t * BN + CW * hf);
-    if (!skip) {
-      float U[SP::WIN_LD], W[CW];
-      uint32_t mbits;
-      const bool simple = tile_is_simple(p, rc, t * BN);
-      tile_logits<NSPLIT>(p, rc, tmem + TM_S + lane_base, tmem + TM_PB + lane_base, q, hf, lane, t * BN, simple, U, mbits);
-      tile_backward_row<NSPLIT>(p, rc, tmem + TM_DP + lane_base, t * BN, hf, Lm, Ll, delta, U, W);
-      // bias term: dS at its relative column c = lj - li + 127 (zero outside the band); addresses are tile-independent
-      if (p.R > 0) {
-        const int d0 = t * BN + CW * hf - i + p.R - 1;
-        const uint32_t lim = (uint32_t)(2 * p.R - 1);
+        for (int ks = 0; ks < KS; ++ks) {
+          const uint32_t off = (ks >> 2), in = (ks & 3) * 32;
+          ptx::umma_bf16_ts(tmem + TM_S, tmem + TM_Q + ks * 8, ptx::make_smem_desc_sw128(kb + off * K_ATOM + in, 0, 1024), id_s, ks > 0);
+        }
+        if (p.R > 0) {
 #pragma unroll
-        for (int x = 0; x < CW; ++x) {
-          const float v = ((uint32_t)(d0 + x) < lim) ? W[x] : 0.f;
-          const __nv_bfloat16 hv = __float2bfloat16_rn(v);
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(rel_addr[x]), "h"(*reinterpret_cast<const uint16_t*>(&hv)) : "memory");
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint32_t off = (ks >> 2), in = (ks & 3) * 32;
+            ptx::umma_bf16_ts(tmem + TM_PB, tmem + TM_Q + ks * 8, ptx::make_smem_desc_sw128(eb + off * E_ATOM + in, 0, 1024), id_pb, ks > 0);
+          }
+        }
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const uint32_t off = (ks >> 2), in = (ks & 3) * 32;
+          ptx::umma_bf16_ts(tmem + TM_DP, tmem + TM_DO + ks * 8, ptx::make_smem_desc_sw128(vb + off * K_ATOM + in, 0, 1024), id_s, ks > 0);
+        }
+        ptx::umma_commit(bar_s);
+      };
+      ptx::mbar_wait(&bar_ke[0], 0);
+      ptx::mbar_wait(&bar_v[0], 0);
+      ptx::tc_fence_after();
+      issue_s(0);
+      for (int t = t_lo; t <= t_hi; ++t) {
+        const int k = t - t_lo, st = k & 1;
+        if (t < t_hi) {
+          ptx::mbar_wait(bar_sfree, (uint32_t)(k & 1));     // S / PB / dP slices are in registers
+          ptx::mbar_wait(&bar_ke[st ^ 1], (uint32_t)(((k + 1) >> 1) & 1));
+          ptx::mbar_wait(&bar_v[st ^ 1], (uint32_t)(((k + 1) >> 1) & 1));
+          ptx::tc_fence_after();
+          issue_s(st ^ 1);
+        }
+        ptx::mbar_wait(bar_p, (uint32_t)(k & 1));           // dS tile (in V buffer st) and dS_rel tile written
+        ptx::tc_fence_after();
+        const uint32_t dsb = ptx::smem_u32(sV + st * NATOM * K_ATOM), rb = ptx::smem_u32(sRel),
+                       kb = ptx::smem_u32(sK + st * NATOM * K_ATOM), eb = ptx::smem_u32(sE + st * NATOM * E_ATOM);
+        const uint32_t id_dq = ptx::make_idesc_bf16(BM, DH, 0, 1);
+#pragma unroll
+        for (int ks = 0; ks < BN / 16; ++ks)
+          ptx::umma_bf16(tmem + TM_DQ, ptx::make_smem_desc_sw128(dsb + ks * 32, 0, 1024),
+                         ptx::make_smem_desc_sw128(kb + ks * 2048, K_ATOM, 1024), id_dq, (k > 0 || ks > 0) ? 1u : 0u);
+        if (p.R > 0) {
+#pragma unroll
+          for (int ks = 0; ks < PBW / 16; ++ks)
+            ptx::umma_bf16(tmem + TM_DQ, ptx::make_smem_desc_sw128(rb + (ks >> 2) * Q_ATOM + (ks & 3) * 32, 0, 1024),
+                           ptx::make_smem_desc_sw128(eb + ks * 2048, E_ATOM, 1024), id_dq, 1u);
+        }
+        ptx::umma_commit(bar_dq);
+        if (t + 2 <= t_hi) {
+          ptx::mbar_wait(bar_dq, (uint32_t)(k & 1));        // stage st (K, E, dS-in-V) is free again
+          load_ke(t + 2);
+          load_v(t + 2);
         }
       }
-      // q.k term: scale * dS where the term was not masked
-#pragma unroll
-      for (int x = 0; x < CW; ++x) W[x] = ((mbits >> x) & 1u) ? 0.f : W[x] * p.scale;
-      store_cols_bf16_sw128<CW>(ptx::smem_u32(sV + buf * NATOM * K_ATOM), li, CW * hf, W);
-      store_cols_bf16_global<CW>(tile_p + (long)(t - t_lo) * BM * BN, U);
-      store_cols_bf16_global<CW>(tile_ds + (long)(t - t_lo) * BM * BN, W);
-    } else {
-      store_zero_cols_global<CW>(tile_p + (long)(t - t_lo) * BM * BN);
-      store_zero_cols_global<CW>(tile_ds + (long)(t - t_lo) * BM * BN);
-      if (p.R > 0) {
-#pragma unroll
-        for (int x = 0; x < CW; ++x) asm volatile("st.shared.u16 [%0], %1;" ::"r"(rel_addr[x]), "h"((uint16_t)0) : "memory");
-      }
-      store_zero_cols_sw128<CW>(ptx::smem_u32(sV + buf * NATOM * K_ATOM), li, CW * hf);
     }
+  } else {
+    // ============================================ compute warps ==================================================
+    delta = sdelta[li];
+    // shared-memory address of this thread's CW relative columns c = (127 - li + CW*hf) + x in the swizzled dS_rel tile
+    uint32_t rel_addr[CW];
+    {
+      const uint32_t rb = ptx::smem_u32(sRel) + li * 128;
+      const int c0 = (BM - 1) - li + CW * hf;
+#pragma unroll
+      for (int x = 0; x < CW; ++x) {
+        const int c = c0 + x;
+        rel_addr[x] = rb + (uint32_t)(c >> 6) * Q_ATOM + ((uint32_t)(((c & 63) >> 3) ^ (li & 7)) << 4) + (uint32_t)(c & 7) * 2;
+      }
+    }
+    // this thread's slice (row li, columns [CW*hf, +CW)) of the query tile's first hand-off tile
+    const long tile0 = (((long)b * p.H + h) * p.nQT + blockIdx.x) * p.max_kt;
+    __nv_bfloat16* tile_p = p.ws_p + tile0 * BM * BN + li * BN + CW * hf;
+    __nv_bfloat16* tile_ds = p.ws_ds + tile0 * BM * BN + li * BN + CW * hf;
 
-    ptx::fence_proxy_async();
-    ptx::tc_fence_before();
-    __syncthreads();
-    if (leader) {
+    for (int t = t_lo; t <= t_hi; ++t) {
+      const int k = t - t_lo, st = k & 1;
+      ptx::mbar_wait(bar_s, (uint32_t)(k & 1));
       ptx::tc_fence_after();
-      const uint32_t dsb = ptx::smem_u32(sV + buf * NATOM * K_ATOM), rb = ptx::smem_u32(sRel);
-      const uint32_t id_dq = ptx::make_idesc_bf16(BM, DH, 0, 1);
-#pragma unroll
-      for (int ks = 0; ks < BN / 16; ++ks)
-        ptx::umma_bf16(tmem + TM_DQ, ptx::make_smem_desc_sw128(dsb + ks * 32, 0, 1024),
-                       ptx::make_smem_desc_sw128(kb + ks * 2048, K_ATOM, 1024), id_dq, (t > t_lo || ks > 0) ? 1u : 0u);
-      if (p.R > 0) {
-#pragma unroll
-        for (int ks = 0; ks < PBW / 16; ++ks)
-          ptx::umma_bf16(tmem + TM_DQ, ptx::make_smem_desc_sw128(rb + (ks >> 2) * Q_ATOM + (ks & 3) * 32, 0, 1024),
-                         ptx::make_smem_desc_sw128(eb + ks * 2048, E_ATOM, 1024), id_dq, 1u);
+      const bool skip = block_out_of_band<NSPLIT>(p, i0 + 32 * q, t * BN + CW * hf);
+      float U[SP::WIN_LD], W[CW];
+      uint32_t mbits = 0;
+      if (!skip) {
+        const bool simple = tile_is_simple(p, rc, t * BN);
+        tile_logits<NSPLIT>(p, rc, tmem + TM_S + lane_base, tmem + TM_PB + lane_base, q, hf, lane, t * BN, simple, U, mbits);
+        tmem_load_cols(tmem + TM_DP + lane_base + (uint32_t)(CW * hf), W);
       }
-      ptx::umma_commit(bar_dq);
-      if (t < t_hi) {
-        ptx::mbar_wait(bar_dq, ph_dq);             // K, E, dS and dS_rel tiles are free again
-        load_ke(t + 1);
-        ptx::mbar_wait(bar_ke, ph_ke);
-        ph_ke ^= 1u;
-        ptx::mbar_wait(&bar_v[buf ^ 1], ((t + 1 - t_lo) >> 1) & 1);
-        ptx::tc_fence_after();
-        issue_s_pb_dp<DH>(tmem + TM_S, tmem + TM_PB, tmem + TM_DP, qb, dob, kb, ptx::smem_u32(sV + (buf ^ 1) * NATOM * K_ATOM), eb,
-                          p.R > 0);
-        ptx::umma_commit(bar_s);
-      }
-    }
-    ph_dq ^= 1u;
-    __syncwarp();
-  }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_sfree);    // the issuer may overwrite S / PB / dP with the next tile
 
-  ptx::mbar_wait(bar_dq, (uint32_t)((t_hi - t_lo) & 1));
-  ptx::tc_fence_after();
-  tmem_row_to_global<OC>(tmem + TM_DQ + hf * OC + lane_base, p.dq + ((long)b * p.Lq + i) * p.ldq + h * DH + hf * OC, 1.f, valid);
+      if (!skip) tile_backward_row<NSPLIT>(p, rc, 0xffffffffu, t * BN, hf, Lm, Ll, delta, U, W);
+      if (k > 0) ptx::mbar_wait(bar_dq, (uint32_t)((k - 1) & 1));     // dQ(t-1) has finished reading dS_rel / the dS tile
+      if (!skip) {
+        // bias term: dS at its relative column c = lj - li + 127 (zero outside the band); addresses are tile-independent
+        if (p.R > 0) {
+          const int d0 = t * BN + CW * hf - i + p.R - 1;
+          const uint32_t lim = (uint32_t)(2 * p.R - 1);
+#pragma unroll
+          for (int x = 0; x < CW; ++x) {
+            const float v = ((uint32_t)(d0 + x) < lim) ? W[x] : 0.f;
+            const __nv_bfloat16 hv = __float2bfloat16_rn(v);
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(rel_addr[x]), "h"(*reinterpret_cast<const uint16_t*>(&hv)) : "memory");
+          }
+        }
+        // q.k term: scale * dS where the term was not masked
+#pragma unroll
+        for (int x = 0; x < CW; ++x) W[x] = ((mbits >> x) & 1u) ? 0.f : W[x] * p.scale;
+        store_cols_bf16_sw128<CW>(ptx::smem_u32(sV + st * NATOM * K_ATOM), li, CW * hf, W);
+        store_cols_bf16_global<CW>(tile_p + (long)k * BM * BN, U);
+        store_cols_bf16_global<CW>(tile_ds + (long)k * BM * BN, W);
+      } else {
+        if (p.R > 0) {
+#pragma unroll
+          for (int x = 0; x < CW; ++x) asm volatile("st.shared.u16 [%0], %1;" ::"r"(rel_addr[x]), "h"((uint16_t)0) : "memory");
+        }
+        store_zero_cols_sw128<CW>(ptx::smem_u32(sV + st * NATOM * K_ATOM), li, CW * hf);
+        store_zero_cols_global<CW>(tile_p + (long)k * BM * BN);
+        store_zero_cols_global<CW>(tile_ds + (long)k * BM * BN);
+      }
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_p);
+    }
+
+    ptx::mbar_wait(bar_dq, (uint32_t)((t_hi - t_lo) & 1));
+    ptx::tc_fence_after();
+    tmem_row_to_global<OC>(tmem + TM_DQ + hf * OC + lane_base, p.dq + ((long)b * p.Lq + i) * p.ldq + h * DH + hf * OC, 1.f, valid);
+  }
   ptx::tc_fence_before();
   __syncthreads();
   if (w == 0) {
@@ -544,8 +590,8 @@ static int attn_bwd_tc_launch_n(const SstAttnDesc& d, const void* q, const void*
   CUtensorMap tmP, tmDS;
   if ((rc = make_tmap_bf16_2d(&tmP, p.ws_p, BN, tiles * BM, BN, 64, BM))) return rc;
   if ((rc = make_tmap_bf16_2d(&tmDS, p.ws_ds, BN, tiles * BM, BN, 64, BM))) return rc;
-  constexpr int SMEM_DQ = 2 * NATOM * BM * 128 + NATOM * BN * 128 + NATOM * PBW * 128 + 2 * NATOM * BN * 128 + (PBW / 64) * BM * 128 +
-                          1024 + 64 + 128 * 4;
+  constexpr int SMEM_DQ = 2 * NATOM * BN * 128 + 2 * NATOM * PBW * 128 + 2 * NATOM * BN * 128 + (PBW / 64) * BM * 128 + 1024 + 128 +
+                          128 * 4;
   constexpr int SMEM_DKV = 2 * (2 * NATOM * BM * 128 + 2 * BM * 128) + 2 * BN * DH * 2 + 1024 + 128;
   static bool attr_done = false;
   if (!attr_done) {
@@ -555,7 +601,8 @@ static int attn_bwd_tc_launch_n(const SstAttnDesc& d, const void* q, const void*
     SST_REQUIRE(e == cudaSuccess, SST_E_LAUNCH, "cudaFuncSetAttribute(attn_bwd_tc): %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  attn_bwd_dq_tc_kernel<DH, NSPLIT><<<dim3(cdiv(d.Lq, BM), d.H, d.B), 128 * NSPLIT, SMEM_DQ, st>>>(tmQ, tmK, tmV, tmE, tmDO, p);
+  attn_bwd_dq_tc_kernel<DH, NSPLIT><<<dim3(cdiv(d.Lq, BM), d.H, d.B), 128 * NSPLIT + 32, SMEM_DQ, st>>>(
+      tmK, tmV, tmE, p, reinterpret_cast<const __nv_bfloat16*>(q));
   {
     const int n_kt = cdiv(d.Lk, BN), n_items = n_kt * d.H * d.B;
     const int grid = n_items < num_sms() ? n_items : num_sms();
