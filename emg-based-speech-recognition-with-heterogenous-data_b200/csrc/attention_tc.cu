@@ -193,7 +193,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       float sum = 0.f;
       if (!skip) {
 #pragma unroll
-        for (int x = 0; x < CW; ++x) { U[x] = __expf(U[x] - m_new); sum += U[x]; }
+        for (int x = 0; x < CW; ++x) { U[x] = __expf(U[x] - m_new); sum += U[x]; }   // exact subtraction first: m can be -1e8
         if (p.thr) {
           float keep[CW];
           dropout_keep<NSPLIT>(p, rc, t * BN, hf, keep);

@@ -159,6 +159,16 @@ __device__ __forceinline__ void load_bias_window(uint32_t tPB /* incl. lane base
   shift_stage<16, CW>(U, s); shift_stage<8, CW>(U, s); shift_stage<4, CW>(U, s); shift_stage<2, CW>(U, s); shift_stage<1, CW>(U, s);
 }
 
+// bit x set  <=>  key jb + x lies inside the band of query rc.i: -R < (jb + x) - i < R  (one interval of x, built once per tile)
+template <int CW>
+__device__ __forceinline__ uint32_t band_bits(const AttnTcParams& p, const RowCtx& rc, int jb) {
+  const int d = jb - rc.i;                               // rel = d + x
+  const int lo = max(0, -p.R + 1 - d), hi = min(CW, p.R - d);       // x in [lo, hi)
+  if (hi <= lo) return 0u;
+  const uint32_t upto_hi = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
+  return upto_hi & ~((1u << lo) - 1u);
+}
+
 // logits of one query row against the thread's keys, exactly as MultiHeadAttention.forward builds them:
 //   s = masked ? -1e8 : q.k * scale;   s += |j - i| < R ? q.E[j-i+R-1] : -1e8   (transformer.py:177-204, Q3/Q9)
 // Bit x of `mbits` reports that the q.k term of key x was overwritten (its gradient is zero).
@@ -171,14 +181,13 @@ __device__ __forceinline__ void tile_logits(const AttnTcParams& p, const RowCtx&
   float sv[CW];
   tmem_load_cols(tS + (uint32_t)(CW * hf), sv);
   const int jb = j0 + CW * hf;                          // first key of this thread
-  const uint32_t lim = (uint32_t)(2 * p.R - 1);
-  const int d0 = jb - rc.i + p.R - 1;                   // in band  <=>  (unsigned)(d0 + x) < 2R-1
+  const uint32_t band = band_bits<CW>(p, rc, jb);       // bit x: key jb + x is inside the band |i - j| < R
   mbits = 0;
   if (simple) {
 #pragma unroll
     for (int x = 0; x < CW; ++x) {
       float s = sv[x] * p.scale;
-      if (p.R > 0) s += ((uint32_t)(d0 + x) < lim) ? U[x] : NEG_MASK;
+      if (p.R > 0) s += ((band >> x) & 1u) ? U[x] : NEG_MASK;
       U[x] = s;
     }
   } else {
@@ -187,7 +196,7 @@ __device__ __forceinline__ void tile_logits(const AttnTcParams& p, const RowCtx&
       const int j = jb + x;
       const bool masked = rc.rowmask || j >= rc.klen || (p.causal && j > rc.i) || (rc.kpad && j < p.Lk && rc.kpad[j]);
       float s = masked ? NEG_MASK : sv[x] * p.scale;
-      if (p.R > 0) s += ((uint32_t)(d0 + x) < lim) ? U[x] : NEG_MASK;
+      if (p.R > 0) s += ((band >> x) & 1u) ? U[x] : NEG_MASK;
       U[x] = j < p.Lk ? s : NEG_BIG;
       mbits |= (masked ? 1u : 0u) << x;
     }

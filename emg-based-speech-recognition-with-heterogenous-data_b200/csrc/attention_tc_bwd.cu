@@ -57,6 +57,7 @@ __device__ __forceinline__ void tile_backward_row(const AttnTcParams& p, const R
                                                   float (&W)[Split<NSPLIT>::CW]) {
   constexpr int CW = Split<NSPLIT>::CW;
   if (tDP != 0xffffffffu) tmem_load_cols(tDP + (uint32_t)(CW * hf), W);      // 0xffffffff: W already holds the dP slice
+  // p = exp((s - max) - logsum): two subtractions in fp32 (max can be -1e8, where max + logsum would swallow logsum)
   if (p.thr) {
     float keep[CW];
     dropout_keep<NSPLIT>(p, rc, j0, hf, keep);
@@ -337,11 +338,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
       if (!skip) {
         // bias term: dS at its relative column c = lj - li + 127 (zero outside the band); addresses are tile-independent
         if (p.R > 0) {
-          const int d0 = t * BN + CW * hf - i + p.R - 1;
-          const uint32_t lim = (uint32_t)(2 * p.R - 1);
+          const uint32_t band = band_bits<CW>(p, rc, t * BN + CW * hf);
 #pragma unroll
           for (int x = 0; x < CW; ++x) {
-            const float v = ((uint32_t)(d0 + x) < lim) ? W[x] : 0.f;
+            const float v = ((band >> x) & 1u) ? W[x] : 0.f;
             const __nv_bfloat16 hv = __float2bfloat16_rn(v);
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(rel_addr[x]), "h"(*reinterpret_cast<const uint16_t*>(&hv)) : "memory");
           }
