@@ -8,6 +8,7 @@ namespace sst {
 struct SimtParams {
   int M, N, K;
   int mode_mn;
+  int b_plain_mn;     // TN_BMN: B is a plain (K, N) row-major matrix
   long lda, ldb, ldc, ldaux;
   long a_rows, b_rows;
   int n_seg, kseg, nsegc;
@@ -38,6 +39,7 @@ __device__ __forceinline__ float load_a(const T* A, const SimtParams& p, int m, 
 template <typename T>
 __device__ __forceinline__ float load_b(const T* B, const SimtParams& p, int n, int k) {
   if (n >= p.N || k >= p.K) return 0.f;
+  if (p.b_plain_mn) return to_f32(B[(long)k * p.ldb + n]);
   if (!p.mode_mn) return to_f32(B[(long)n * p.ldb + k]);
   int s = n / p.nsegc;
   long row = (long)k + p.b_row_shift[s];
@@ -137,6 +139,7 @@ int launch_gemm_simt(const SstGemmDesc& d, const void* A, const void* B, void* C
   memset(&p, 0, sizeof(p));
   p.M = (int)d.M; p.N = (int)d.N; p.K = (int)d.K;
   p.mode_mn = d.layout == SST_GEMM_NT_MN;
+  p.b_plain_mn = d.layout == SST_GEMM_TN_BMN;
   p.lda = d.lda; p.ldb = d.ldb; p.ldc = d.ldc; p.ldaux = d.ldaux;
   p.a_rows = d.a_rows; p.b_rows = d.b_rows;
   p.n_seg = d.n_seg > 0 ? d.n_seg : 1;

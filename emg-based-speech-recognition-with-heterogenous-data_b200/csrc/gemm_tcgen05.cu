@@ -23,7 +23,8 @@ constexpr int G_A_BYTES = G_BM * G_BK * 2;   // 16 KiB
 
 struct GemmKParams {
   int M, N, K;
-  int mode_mn;
+  int mode_mn;        // A is MN-major (weight-gradient layout)
+  int b_mn;           // B is MN-major (NT_MN and TN_BMN layouts)
   int num_kb;
   int kb_per_seg;     // TN: k-blocks per A segment
   int nseg_cols;      // MN: columns of C per B segment
@@ -116,11 +117,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int seg = kb / p.kb_per_seg;
             int x = p.a_col0[seg] + (kb - seg * p.kb_per_seg) * G_BK;
             ptx::tma_load_2d(sA, &tmA, &full[stage], x, m0 + p.a_row_shift[seg]);
-            ptx::tma_load_2d(sB, &tmB, &full[stage], kb * G_BK, n0);
           } else {
             const int k0 = kb * G_BK;
 #pragma unroll
             for (int i = 0; i < G_BM / 64; ++i) ptx::tma_load_2d(sA + i * 8192, &tmA, &full[stage], m0 + i * 64, k0);
+          }
+          if (!p.b_mn) {
+            ptx::tma_load_2d(sB, &tmB, &full[stage], kb * G_BK, n0);
+          } else {
+            const int k0 = kb * G_BK;
             int seg = n0 / p.nseg_cols;
             int nin = n0 - seg * p.nseg_cols;
 #pragma unroll
@@ -133,7 +138,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    const uint32_t idesc = ptx::make_idesc_bf16(G_BM, BN, p.mode_mn, p.mode_mn);
+    const uint32_t idesc = ptx::make_idesc_bf16(G_BM, BN, p.mode_mn, p.b_mn);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
@@ -150,14 +155,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t b_base = a_base + G_A_BYTES;
 #pragma unroll
           for (int k = 0; k < G_BK / 16; ++k) {
-            uint64_t ad, bd;
-            if (!p.mode_mn) {
-              ad = ptx::make_smem_desc_sw128(a_base + k * 32, 0, 1024);
-              bd = ptx::make_smem_desc_sw128(b_base + k * 32, 0, 1024);
-            } else {
-              ad = ptx::make_smem_desc_sw128(a_base + k * 2048, 8192, 1024);
-              bd = ptx::make_smem_desc_sw128(b_base + k * 2048, 8192, 1024);
-            }
+            const uint64_t ad = !p.mode_mn ? ptx::make_smem_desc_sw128(a_base + k * 32, 0, 1024)
+                                           : ptx::make_smem_desc_sw128(a_base + k * 2048, 8192, 1024);
+            const uint64_t bd = !p.b_mn ? ptx::make_smem_desc_sw128(b_base + k * 32, 0, 1024)
+                                        : ptx::make_smem_desc_sw128(b_base + k * 2048, 8192, 1024);
             ptx::umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           ptx::umma_commit(&empty[stage]);
@@ -441,9 +442,12 @@ static int launch_bn(const SstGemmDesc& d, const void* A, const void* B, GemmKPa
   int rc;
   if (!p.mode_mn) {
     if ((rc = make_tmap_bf16_2d(&tmA, A, d.a_cols, d.a_rows, d.lda, G_BK, G_BM))) return rc;
-    if ((rc = make_tmap_bf16_2d(&tmB, B, d.K, d.N, d.ldb, G_BK, BN))) return rc;
   } else {
     if ((rc = make_tmap_bf16_2d(&tmA, A, d.a_cols, d.a_rows, d.lda, 64, G_BK))) return rc;
+  }
+  if (!p.b_mn) {
+    if ((rc = make_tmap_bf16_2d(&tmB, B, d.K, d.N, d.ldb, G_BK, BN))) return rc;
+  } else {
     if ((rc = make_tmap_bf16_2d(&tmB, B, d.b_cols, d.b_rows, d.ldb, 64, G_BK))) return rc;
   }
   static bool attr_done = false;
@@ -464,6 +468,7 @@ int launch_gemm_tcgen05(const SstGemmDesc& d, const void* A, const void* B, void
   memset(&p, 0, sizeof(p));
   p.M = (int)d.M; p.N = (int)d.N; p.K = (int)d.K;
   p.mode_mn = d.layout == SST_GEMM_NT_MN;
+  p.b_mn = d.layout != SST_GEMM_TN;
   p.num_kb = cdiv(d.K, G_BK);
   const int nseg = d.n_seg > 0 ? d.n_seg : 1;
   SST_REQUIRE(nseg <= 3, SST_E_ARG, "n_seg must be <= 3");
@@ -476,6 +481,7 @@ int launch_gemm_tcgen05(const SstGemmDesc& d, const void* A, const void* B, void
                 "segmented A needs K/n_seg to be a multiple of %d", G_BK);
     p.kb_per_seg = nseg == 1 ? p.num_kb : (int)(d.K / nseg / G_BK);
     p.nseg_cols = (int)d.N;
+    if (p.b_mn) { p.b_row_shift[0] = 0; p.b_col0[0] = 0; }      // TN_BMN: B is a plain (K, N) row-major matrix
   } else {
     p.kb_per_seg = p.num_kb;
     p.nseg_cols = (int)(d.N / nseg);

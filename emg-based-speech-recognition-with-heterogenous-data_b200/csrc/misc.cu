@@ -190,7 +190,8 @@ permute3_tiled_kernel(const TI* __restrict__ in, TO* __restrict__ out, long d1, 
 }
 
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
-                             float lr, float beta1, float beta2, float eps, float wd, float bc1, float sqrt_bc2) {
+                             float lr, float beta1, float beta2, float eps, float wd, float bc1, float sqrt_bc2,
+                             __nv_bfloat16* __restrict__ p_bf16) {
   for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long)gridDim.x * blockDim.x * 4) {
     if (i + 4 <= n) {
       float4 pp = *reinterpret_cast<float4*>(p + i), gg = *reinterpret_cast<const float4*>(g + i);
@@ -205,6 +206,13 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
         P[j] -= (lr / bc1) * (M[j] / denom);
       }
       *reinterpret_cast<float4*>(p + i) = pp; *reinterpret_cast<float4*>(m + i) = mm; *reinterpret_cast<float4*>(v + i) = vv;
+      if (p_bf16 != nullptr) {        // bf16 shadow of the updated parameters: the tensor-core GEMM operands, no separate cast pass
+        uint2 o;
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+        o2[0] = __floats2bfloat162_rn(pp.x, pp.y);
+        o2[1] = __floats2bfloat162_rn(pp.z, pp.w);
+        *reinterpret_cast<uint2*>(p_bf16 + i) = o;
+      }
     } else {
       for (long e = i; e < n; ++e) {
         float P = p[e] * (1.f - lr * wd);
@@ -212,6 +220,7 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
         float V = beta2 * v[e] + (1.f - beta2) * g[e] * g[e];
         P -= (lr / bc1) * (M / (sqrtf(V) / sqrt_bc2 + eps));
         p[e] = P; m[e] = M; v[e] = V;
+        if (p_bf16 != nullptr) p_bf16[e] = __float2bfloat16_rn(P);
       }
     }
   }
@@ -325,7 +334,7 @@ int sst_permute3_cast(int in_dtype, int out_dtype, const void* in, void* out, in
 }
 
 int sst_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, float wd,
-              int64_t step, void* stream) {
+              int64_t step, void* p_bf16, void* stream) {
   SST_REQUIRE(step >= 1, SST_E_ARG, "adamw: step is 1-based");
   SST_REQUIRE(((uintptr_t)p & 15) == 0 && ((uintptr_t)g & 15) == 0 && ((uintptr_t)m & 15) == 0 && ((uintptr_t)v & 15) == 0, SST_E_ARG,
               "adamw: buffers must be 16-byte aligned");
@@ -333,8 +342,9 @@ int sst_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr,
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   const int grid = ew_grid2((n + 3) / 4, 256);
+  SST_REQUIRE(p_bf16 == nullptr || ((uintptr_t)p_bf16 & 7) == 0, SST_E_ARG, "adamw: bf16 shadow must be 8-byte aligned");
   adamw_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, (float)bc1,
-                                                                         (float)sqrt(bc2));
+                                                                         (float)sqrt(bc2), reinterpret_cast<__nv_bfloat16*>(p_bf16));
   return check_launch("adamw");
 }
 

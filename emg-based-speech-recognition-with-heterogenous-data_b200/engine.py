@@ -50,6 +50,7 @@ class Engine:
         self.LDH = 64                      # pitch of the (padded) head-logit matrices
         self.pk = {}
         self.force_simt = False
+        self.shadow = {}                   # name -> bf16 view of the parameter kept current by the optimizer (optional)
         self._packed_version = None
         self._bn_scratch = torch.empty(3 * self.D, dtype=torch.float64, device=self.dev)
         self._side = None                  # side stream for work that can run under the decoder (CTC)
@@ -70,7 +71,7 @@ class Engine:
         N, K = w2d.shape
         if transpose:
             Np = N if N % 8 == 0 else (N + 63) // 64 * 64      # TMA needs 16-byte row pitches (44/43-class heads)
-            out = self.zeros(K, Np)[:, :N]
+            out = (self.zeros(K, Np) if Np != N else self.empty(K, Np))[:, :N]      # pad columns (if any) stay zero
             L.permute3_cast(w2d, out, (1, K, N), (0, 1, K), (0, Np, 1))
         else:
             if self.dtype == torch.float32:
@@ -79,9 +80,15 @@ class Engine:
             L.permute3_cast(w2d, out, (1, N, K), (0, K, 1), (0, K, 1))
         return out
 
-    def _pack_linear(self, key, w2d):
-        self.pk[key] = self._cast2d(w2d)
-        self.pk[key + ".T"] = self._cast2d(w2d, transpose=True)
+    def _pack_linear(self, key, w2d, name=None):
+        """GEMM operand of a (N_out, K_in) weight: the bf16 shadow view the optimizer maintains (train.FlatState) when there is
+        one, else a cast copy.  No transposed copy: input gradients read the same matrix MN-major (SST_GEMM_TN_BMN)."""
+        sh = self.shadow.get(name) if name is not None else None
+        self.pk[key] = sh.view(w2d.shape) if (sh is not None and self.dtype == torch.bfloat16) else self._cast2d(w2d)
+        # input gradients (and the out-projection forward) multiply by the transposed matrix.  SST_GEMM_TN_BMN could read the
+        # matrix above MN-major instead, but measured 20-25 % slower than a K-major operand on the big GEMMs (B200, cfg2), so
+        # a transposed copy is kept (tiled transpose from the bf16 matrix)
+        self.pk[key + ".T"] = self._cast2d(self.pk[key], transpose=True)
 
     def _pack_heads_in(self, key, ws):
         """ws: list of (H, D, dh) per-head projection weights -> W (len*H*dh, D) and its transpose."""
@@ -135,42 +142,48 @@ class Engine:
             p = "conv_blocks.%d" % i
             self._pack_conv3(p + ".conv1", P[p + ".conv1.weight"], 2)
             self._pack_conv3(p + ".conv2", P[p + ".conv2.weight"], 1)
-            self._pack_linear(p + ".res", P[p + ".residual_path.weight"].view(C, C))
-        self._pack_linear("w_raw_in", P["w_raw_in.weight"])
+            self._pack_linear(p + ".res", P[p + ".residual_path.weight"].view(C, C), p + ".residual_path.weight")
+        self._pack_linear("w_raw_in", P["w_raw_in.weight"], "w_raw_in.weight")
         for i in range(self.n_enc):
             p = "transformerEncoder.layers.%d" % i
             a = p + ".self_attn"
             self._pack_heads_in(a + ".qkv", [P[a + ".w_q"], P[a + ".w_k"], P[a + ".w_v"]])
-            self._pack_linear(a + ".o", P[a + ".w_o"].view(D, D))       # (H*dh, D): this IS W_o^T; ".T" is W_o
+            self._pack_linear(a + ".o", P[a + ".w_o"].view(D, D), a + ".w_o")       # (H*dh, D) = (K, N): read MN-major in forward
             E = P[a + ".relative_positional.embeddings"]
             self.pk[a + ".E"] = self._cast2d(E.view(-1, self.dh))
-            self._pack_linear(p + ".linear1", P[p + ".linear1.weight"])
-            self._pack_linear(p + ".linear2", P[p + ".linear2.weight"])
+            self._pack_linear(p + ".linear1", P[p + ".linear1.weight"], p + ".linear1.weight")
+            self._pack_linear(p + ".linear2", P[p + ".linear2.weight"], p + ".linear2.weight")
         for i in range(self.n_dec):
             p = "transformerDecoder.layers.%d" % i
             a = p + ".self_attn"
             self._pack_heads_in(a + ".qkv", [P[a + ".w_q"], P[a + ".w_k"], P[a + ".w_v"]])
-            self._pack_linear(a + ".o", P[a + ".w_o"].view(D, D))
+            self._pack_linear(a + ".o", P[a + ".w_o"].view(D, D), a + ".w_o")
             m = p + ".multihead_attn"
             self._pack_heads_in(m + ".q", [P[m + ".w_q"]])
             self._pack_heads_in(m + ".kv", [P[m + ".w_k"], P[m + ".w_v"]])
-            self._pack_linear(m + ".o", P[m + ".w_o"].view(D, D))
-            self._pack_linear(p + ".linear1", P[p + ".linear1.weight"])
-            self._pack_linear(p + ".linear2", P[p + ".linear2.weight"])
-        self._pack_linear("w_aux", P["w_aux.weight"])
-        self._pack_linear("w_out", P["w_out.weight"])
+            self._pack_linear(m + ".o", P[m + ".w_o"].view(D, D), m + ".w_o")
+            self._pack_linear(p + ".linear1", P[p + ".linear1.weight"], p + ".linear1.weight")
+            self._pack_linear(p + ".linear2", P[p + ".linear2.weight"], p + ".linear2.weight")
+        self._pack_linear("w_aux", P["w_aux.weight"], "w_aux.weight")
+        self._pack_linear("w_out", P["w_out.weight"], "w_out.weight")
         self._packed_version = version
 
     # ------------------------------------------------------------------------------------------------ building blocks
-    def _linear_fwd(self, x, M, key, bias=None, relu=False, drop_p=0.0, seed=0, out=None, out_dtype=None, N=None, ldc=None):
+    def _linear_fwd(self, x, M, key, bias=None, relu=False, drop_p=0.0, seed=0, out=None, out_dtype=None, N=None, ldc=None,
+                    w_kn=False):
+        """y = x W^T for a packed (N, K) weight; w_kn: the packed matrix is (K, N) (the out-projection w_o) and is read MN-major."""
         W = self.pk[key]
-        Nw, K = W.shape
+        if w_kn:
+            K, Nw = W.shape
+        else:
+            Nw, K = W.shape
         N = N or Nw
         ldc = ldc or N
         if out is None:
             out = self.empty(M, ldc, dtype=out_dtype)
         epi = (L.EPI_BIAS if bias is not None else 0) | (L.EPI_RELU if relu else 0) | (L.EPI_DROPOUT if drop_p > 0 else 0)
-        self.gemm(x, W, out, M, N, K, x.stride(0), K, ldc, bias=bias, epilogue=epi, drop_p=drop_p, seed=seed)
+        self.gemm(x, W, out, M, N, K, x.stride(0), W.stride(0), ldc, bias=bias, epilogue=epi, drop_p=drop_p, seed=seed,
+                  layout=L.GEMM_TN_BMN if w_kn else L.GEMM_TN)
         return out
 
     def _linear_bwd(self, dy, x, M, key, G, wname, bname=None, dx_out=None, accum_dx=False, aux=None, mask_scale=1.0,

@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsst.so")
 
 F32, BF16 = 0, 1
-GEMM_TN, GEMM_NT_MN = 0, 1
+GEMM_TN, GEMM_NT_MN, GEMM_TN_BMN = 0, 1, 2
 EPI_BIAS, EPI_RELU, EPI_DROPOUT, EPI_MULMASK, EPI_ACCUM = 1, 2, 4, 8, 16
 
 
@@ -134,6 +134,11 @@ def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, layout=GEMM_TN, bias=None, aux=None
         d.a_rows = a_rows if a_rows is not None else M
         d.a_cols = a_cols if a_cols is not None else K
         d.b_rows, d.b_cols = N, K
+    elif layout == GEMM_TN_BMN:
+        d.a_rows = a_rows if a_rows is not None else M
+        d.a_cols = a_cols if a_cols is not None else K
+        d.b_rows = b_rows if b_rows is not None else K
+        d.b_cols = b_cols if b_cols is not None else N
     else:
         d.a_rows = a_rows if a_rows is not None else K
         d.a_cols = a_cols if a_cols is not None else M
@@ -343,10 +348,10 @@ def permute3_cast(inp, out, dims, in_strides, out_strides, accumulate=False):
           "sst_permute3_cast")
 
 
-def adamw(p, g, m, v, n, lr, beta1, beta2, eps, wd, step):
-    with _scope("adamw", bytes=28.0 * n):          # read p, g, m, v; write p, m, v (fp32)
+def adamw(p, g, m, v, n, lr, beta1, beta2, eps, wd, step, p_bf16=None):
+    with _scope("adamw", bytes=(28.0 + (2.0 if p_bf16 is not None else 0.0)) * n):    # read p, g, m, v; write p, m, v (+ bf16 shadow)
         check(lib().sst_adamw(ptr(p), ptr(g), ptr(m), ptr(v), _i64(n), _f(lr), _f(beta1), _f(beta2), _f(eps), _f(wd), _i64(step),
-                              stream()), "sst_adamw")
+                              ptr(p_bf16), stream()), "sst_adamw")
 
 
 def launch_count():

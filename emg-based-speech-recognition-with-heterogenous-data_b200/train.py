@@ -80,7 +80,7 @@ class FlatState:
         names = [n for n in model._param_names if model._trainable[n]]
         self.names = backward_order(names, eng.n_enc, eng.n_dec)
         params = dict(model.named_parameters())
-        sizes = [(params[n].numel() + 3) // 4 * 4 for n in self.names]          # keep every view 16-byte aligned
+        sizes = [(params[n].numel() + 7) // 8 * 8 for n in self.names]          # every view 16-byte aligned, also in the bf16 shadow
         self.offsets, off = {}, 0
         for n, s in zip(self.names, sizes):
             self.offsets[n] = off
@@ -101,6 +101,15 @@ class FlatState:
             self.G[n] = self.g[o:o + k].view(prm.shape)
             prm.grad = self.G[n]
         model._engine = None                      # parameter storage moved: rebuild the engine's views
+        # bf16 shadow of the flat parameters, kept current by the fused AdamW kernel: the GEMM operands of every plain
+        # (N_out, K_in) weight are views into it, so the per-step re-packing touches only the per-head / conv permutations
+        self.pb = None
+        self.shadow = {}
+        if model.compute_dtype == torch.bfloat16:
+            self.pb = self.p.to(torch.bfloat16)
+            for n in self.names:
+                o, k = self.offsets[n], params[n].numel()
+                self.shadow[n] = self.pb[o:o + k].view(params[n].shape)
         self.step_count = 0
         # gradient sinks for the never-trained parameters (written by nobody, kept so Engine.backward can index them)
         self.G_all = dict(self.G)
@@ -189,6 +198,7 @@ class Trainer:
         model.engine()
         self.flat = FlatState(model)
         self.eng = model.engine()
+        self.eng.shadow = self.flat.shadow
         self.eng.pack()
         self.sync = GradSync(self.flat, self.eng.n_enc, self.eng.n_dec, bucket_bytes) if distributed else None
         self.batch_idx = 0
@@ -247,7 +257,7 @@ class Trainer:
             eng.backward(ctx, flat.G_all)
         if will_step:                                               # recognition_model.py:115-118
             flat.step_count += 1
-            L.adamw(flat.p, flat.g, flat.m, flat.v, flat.numel, self.lr, 0.9, 0.999, 1e-8, self.wd, flat.step_count)
+            L.adamw(flat.p, flat.g, flat.m, flat.v, flat.numel, self.lr, 0.9, 0.999, 1e-8, self.wd, flat.step_count, flat.pb)
             flat.zero_grad()
             self.sum_batch_size = 0
             eng.pack()

@@ -47,6 +47,8 @@ int sst_device_check(void);
  *        A(m,k) = Amat[(m + a_row_shift[s]) * lda + a_col0[s] + (k - s*Kseg)],  s = k / Kseg,  Kseg = K / n_seg
  *        (rows outside [0, a_rows) read as zero).  n_seg = 3 expresses the three taps of a k=3 convolution over a
  *        time-padded channels-last activation; n_seg = 1 is a plain GEMM.
+ *   layout SST_GEMM_TN_BMN (input gradients):  as TN, but B is read as a (K, N) row-major matrix, B(k,n) = Bmat[k*ldb + n]:
+ *        dx = dy . W multiplies by the weight in ITS OWN (N_out, K_in) layout -- no transposed copy of W is ever built.
  *   layout SST_GEMM_NT_MN (weight gradients):  C[m,n] (+)= sum_k A[k*lda + m] * B(k,n)
  *        B(k,n) = Bmat[(k + b_row_shift[s]) * ldb + b_col0[s] + (n - s*Nseg)],  s = n / Nseg,  Nseg = N / n_seg
  *        (rows outside [0, b_rows) read as zero).
@@ -59,6 +61,7 @@ int sst_device_check(void);
  * ---------------------------------------------------------------------------------------------------------- */
 #define SST_GEMM_TN 0
 #define SST_GEMM_NT_MN 1
+#define SST_GEMM_TN_BMN 2
 
 #define SST_EPI_BIAS 1
 #define SST_EPI_RELU 2
@@ -201,7 +204,8 @@ int sst_ce_sumexp_loss(int logits_dtype, int grad_dtype, int64_t rows, int S, in
  *  sst_embed_posenc_fwd : embedding_tgt(y) + pe[b]/D, dropout                             (architecture.py:126-127, Q10)
  *  sst_embed_bwd        : dW[y] += dout, skipping padding_idx rows (fp32 atomics)
  *  sst_permute3_cast    : out[i*o0+j*o1+k*o2] (+)= in[i*s0+j*s1+k*s2] with dtype conversion (weight packing / grad unpacking)
- *  sst_adamw            : torch.optim.AdamW step over a flat fp32 buffer, `step` 1-based  (recognition_model.py:293)
+ *  sst_adamw            : torch.optim.AdamW step over a flat fp32 buffer, `step` 1-based  (recognition_model.py:293);
+ *                         p_bf16 (nullable): same-shape bf16 buffer that receives the updated parameters (the GEMM operands)
  * ---------------------------------------------------------------------------------------------------------- */
 int sst_shift_left(float* x, int64_t n_chunks, int T, int Cc, int r, void* stream);
 int sst_im2col_first(int out_dtype, const float* x, void* col, int64_t n_chunks, int Tin, void* stream);
@@ -216,7 +220,7 @@ int sst_embed_bwd(int dtype, const int64_t* y, const void* dout, float* dW, int 
 int sst_permute3_cast(int in_dtype, int out_dtype, const void* in, void* out, int64_t d0, int64_t d1, int64_t d2, int64_t s0,
                       int64_t s1, int64_t s2, int64_t o0, int64_t o1, int64_t o2, int accumulate, void* stream);
 int sst_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, float wd,
-              int64_t step, void* stream);
+              int64_t step, void* p_bf16, void* stream);
 
 #ifdef __cplusplus
 }

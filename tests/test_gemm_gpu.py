@@ -56,6 +56,28 @@ def test_tn_tensor_core(L, M, N, K, epi_name):
         assert rel(C, ref) < tol_for(torch.bfloat16, out_dtype), (out_dtype, epi_name)
 
 
+@pytest.mark.parametrize("M,N,K", [(800, 768, 3072), (7744, 768, 2304), (333, 768, 44), (1000, 200, 136)])
+@pytest.mark.parametrize("simt", [False, True])
+def test_tn_with_mn_major_b(L, M, N, K, simt):
+    """SST_GEMM_TN_BMN: C = A[M,K] . B[K,N] with B row-major (K, N) -- dx = dy . W on the weight's own layout; K = 44 is the
+    CTC head (dy pitch 64, rows of W beyond K zero-filled by TMA)."""
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    lda = (K + 63) // 64 * 64
+    Aw = (torch.randn(M, lda, device=DEV, generator=g) * 0.5).bfloat16()
+    B = (torch.randn(K, N, device=DEV, generator=g) * 0.5).bfloat16()
+    aux = torch.randn(M, N, device=DEV, generator=g).bfloat16()
+    for epi in (0, L.EPI_ACCUM, L.EPI_MULMASK):
+        C = torch.full((M, N), 2.0, device=DEV, dtype=torch.bfloat16)
+        L.gemm(Aw, B, C, M, N, K, lda, N, N, layout=L.GEMM_TN_BMN, a_cols=K, aux=aux if epi == L.EPI_MULMASK else None, ldaux=N,
+               epilogue=epi, mask_scale=1.25, force_simt=simt)
+        ref = Aw[:, :K].float() @ B.float()
+        if epi == L.EPI_ACCUM:
+            ref = ref + 2.0
+        if epi == L.EPI_MULMASK:
+            ref = ref * torch.where(aux.float() > 0, 1.25, 0.0)
+        assert rel(C, ref) < 2e-2, (epi, simt)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_tn_cuda_core(L, dtype):
     M, N, K = 300, 136, 72

@@ -341,7 +341,9 @@ def test_embed_gather_shift_permute_adamw(L):
     for step in (1, 2, 3):
         pt.grad = gr.clone() * step
         opt.step()
-        L.adamw(p, gr * step, m, v, n, 2e-7, 0.9, 0.999, 1e-8, 0.01, step)
+        shadow = torch.zeros(n, device=DEV, dtype=torch.bfloat16)
+        L.adamw(p, gr * step, m, v, n, 2e-7, 0.9, 0.999, 1e-8, 0.01, step, shadow)
+        assert torch.equal(shadow, p.bfloat16())              # bf16 shadow of the UPDATED parameters
     assert float((p - pt.detach()).abs().max()) < 1e-7
 
 
