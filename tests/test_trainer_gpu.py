@@ -1,0 +1,110 @@
+"""sst_b200.train.Trainer on a B200 against the oracle's restatement of the reference training step
+(recognition_model.py:57-64, :76-118, :293): loss values, the AdamW update of every parameter after one and two steps
+(fp32 mode, dropout 0, shift 0), summed gradient accumulation over micro-batches (Q12), and the bf16 shadow / re-packing
+of the GEMM operands after an optimizer step."""
+import random
+
+import pytest
+import torch
+
+import sst_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _model(cfg, sd, dtype):
+    import sst_b200  # noqa: F401
+    from sst_b200 import architecture as A
+    A.configure(model_size=768, feed_forward_layer_size=3072, num_layers_encoder=cfg["n_enc"], num_layers_decoder=cfg["n_dec"],
+                n_heads_encoder=8, n_heads_decoder=8, relative_distance=cfg["rel_dist"], dropout_model=0.0, dropout_pos_emb=0.0,
+                sst_dtype=dtype)
+    model = A.Model(112, 44, 43, DEV).to(DEV)
+    model.load_state_dict(sd)
+    return model
+
+
+def _oracle_steps(cfg, sd, batches, accumulate_every):
+    """Reference loop: loss.backward() sums into .grad, AdamW when the accumulated chunk count reaches batch_size_grad."""
+    sd = {k: v.clone() for k, v in sd.items()}
+    names = O.trainable_names(sd, cfg)
+    m = {n: torch.zeros_like(sd[n]) for n in names}
+    v = {n: torch.zeros_like(sd[n]) for n in names}
+    acc = {n: torch.zeros_like(sd[n]) for n in names}
+    losses, step = [], 0
+    for it, batch in enumerate(batches):
+        res, grads, stats = O.loss_and_grads(sd, cfg, batch, True, 0)
+        for k, val in stats.items():
+            sd[k] = val
+        losses.append(float(res["loss"]))
+        for n in names:
+            if n in grads:
+                acc[n] += grads[n]
+        if (it + 1) % accumulate_every == 0:
+            step += 1
+            lr = O.lr_schedule(it)
+            for n in names:
+                O.adamw_step(sd[n], acc[n], m[n], v[n], step, lr)
+                acc[n].zero_()
+    return sd, losses
+
+
+@pytest.mark.parametrize("accumulate_every", [1, 2])
+def test_trainer_matches_reference_loop(accumulate_every):
+    from sst_b200.train import Trainer
+    cfg = O.make_cfg(n_enc=1, n_dec=1, rel_dist=100, alpha=0.2)
+    sd0 = O.synthetic_state_dict(cfg, 7)
+    batches = [O.synthetic_batch(seed=40 + k, ragged=[70, 100, 30], tgt_lens=[9, 14, 5]) for k in range(2)]
+    ref_sd, ref_losses = _oracle_steps(cfg, sd0, batches, accumulate_every)
+    model = _model(cfg, sd0, "fp32")
+    # one batch = 1 chunk of 1600 samples: batch_size_grad = accumulate_every chunks
+    tr = Trainer(model, alpha_loss=cfg["alpha"], batch_size_grad=accumulate_every, learning_rate_warmup=1500)
+    got_losses = []
+    for batch in batches:
+        dev = tr.to_device(tr.prepare(batch))
+        losses = tr.step_device(dev, shift_r=0)
+        tr.fetch_losses(losses)
+        got_losses.append(tr.wait_losses()[0])
+    for a, b in zip(got_losses, ref_losses):
+        assert abs(a - b) < 1e-4 * abs(b), (got_losses, ref_losses)
+    # parameters after the update(s): AdamW's first steps move every weight by ~lr regardless of the gradient scale, so
+    # compare the UPDATE (new - old) against the reference's update
+    new = dict(model.named_parameters())
+    worst = 0.0
+    for n in O.trainable_names(sd0, cfg):
+        if n.startswith("conv_blocks.") and n.endswith(".bias") and ".bn" not in n and "res_norm" not in n:
+            continue      # conv biases in front of BatchNorm: the true gradient is exactly 0, AdamW amplifies rounding noise
+        upd_ref = (ref_sd[n] - sd0[n]).double()
+        upd = (new[n].detach().cpu() - sd0[n]).double()
+        denom = float(upd_ref.abs().max()) + 1e-12
+        frac_bad = float(((upd - upd_ref).abs() > 0.05 * denom).double().mean())
+        worst = max(worst, frac_bad)
+        # sign(g)-like first updates flip where |g| ~ 0: allow a small fraction of elements to differ
+        assert frac_bad < 0.02, "%s: %.3f of the elements moved differently from the reference" % (n, frac_bad)
+    print("largest fraction of deviating update elements: %.4f" % worst)
+    for k in ref_sd:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            buf = dict(model.named_buffers())[k].cpu()
+            assert float((buf - ref_sd[k]).abs().max()) < 1e-4 * (float(ref_sd[k].abs().max()) + 1e-6), k
+
+
+def test_bf16_shadow_and_repack_follow_the_optimizer():
+    """After a step the packed bf16 operands must equal a fresh cast of the updated fp32 masters."""
+    from sst_b200.train import Trainer
+    cfg = O.make_cfg(n_enc=1, n_dec=1, rel_dist=100, alpha=0.2)
+    sd0 = O.synthetic_state_dict(cfg, 8)
+    model = _model(cfg, sd0, "bf16")
+    tr = Trainer(model, alpha_loss=0.2, batch_size_grad=1)
+    batch = O.synthetic_batch(seed=50, ragged=[70, 100, 30], tgt_lens=[9, 14, 5])
+    random.seed(0)
+    tr.step(batch)
+    torch.cuda.synchronize()
+    eng = tr.eng
+    P = dict(model.named_parameters())
+    w1 = P["transformerEncoder.layers.0.linear1.weight"].detach()
+    assert torch.equal(eng.pk["transformerEncoder.layers.0.linear1"], w1.bfloat16())
+    assert torch.equal(eng.pk["transformerEncoder.layers.0.linear1.T"], w1.bfloat16().t().contiguous())
+    assert not torch.equal(w1.cpu(), sd0["transformerEncoder.layers.0.linear1.weight"])      # the step did move it
+    wq = P["transformerEncoder.layers.0.self_attn.w_q"].detach()                                # (H, D, dh) -> rows (h, a), cols f
+    packed = eng.pk["transformerEncoder.layers.0.self_attn.qkv"][:768]
+    assert torch.equal(packed, wq.permute(0, 2, 1).reshape(768, 768).bfloat16())
