@@ -237,12 +237,16 @@ def run_ours(args, w):
     # ---- end to end from host buffers ---------------------------------------------------------------------------------
     for i in range(2):
         e2e_step(i)
+    for _ in trainer.run(host[i % n_batches] for i in range(2)):      # warm the pipelined entry (copy stream, pinned buffers)
+        pass
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    for i in range(args.steps):
-        e2e_step(i)
+    # Trainer.run: every step uploads its batch from pinned host memory and reads its losses back to the host; the upload of
+    # step i+1 and the read-back of step i overlap step i+1's compute
+    n_read = sum(1 for _ in trainer.run(host[i % n_batches] for i in range(args.steps)))
+    assert n_read == args.steps
     e1.record()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3

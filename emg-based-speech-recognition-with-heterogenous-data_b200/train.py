@@ -271,6 +271,67 @@ class Trainer:
         losses = self.step_device(dev_batch)
         return self.fetch_losses(losses)
 
+    def run(self, host_batches):
+        """Pipelined public entry for a stream of prepared (pinned) host batches, the way a training loop would drive it:
+        the H2D copy of batch i+1 is issued on a copy stream while batch i computes, and the loss of step i is read back
+        (async D2H + event) while step i+1 is already enqueued -- every step still uploads its inputs and downloads its
+        result, but neither sits on the critical path.  Yields (loss, loss_dec, loss_enc) per step, in order."""
+        if self.dev.type != "cuda":
+            for h in host_batches:
+                yield self.step_host(h)
+            return
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+            self._pinned_losses = [torch.zeros(3, dtype=torch.float32).pin_memory() for _ in range(2)]
+        copy_stream, pinned = self._copy_stream, self._pinned_losses
+        main = torch.cuda.current_stream()
+        it = iter(host_batches)
+
+        def upload(h):
+            # allocated from the copy stream's own pool; record_stream(main) below keeps the blocks alive until the step that
+            # consumes them has run, so the upload never has to wait for the compute stream
+            with torch.cuda.stream(copy_stream):
+                d = self.to_device(h)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return d, ev
+
+        nxt = next(it, None)
+        cur = upload(nxt) if nxt is not None else None
+        pending = None                              # (slot, event) of the previous step's loss read-back
+        k = 0
+        while cur is not None:
+            nxt = next(it, None)
+            d, ev = cur
+            main.wait_event(ev)
+            for v in d.values():
+                if torch.is_tensor(v):
+                    v.record_stream(main)
+            losses = self.step_device(d)
+            cur = upload(nxt) if nxt is not None else None
+            slot = k & 1
+            pinned[slot].copy_(losses, non_blocking=True)
+            lev = torch.cuda.Event()
+            lev.record(main)
+            if pending is not None:
+                yield self._read_losses(*pending)
+            pending = (pinned[slot], lev)
+            k += 1
+        if pending is not None:
+            yield self._read_losses(*pending)
+
+    def _read_losses(self, buf, ev):
+        ev.synchronize()
+        loss_dec, loss_enc = float(buf[1]), float(buf[2])
+        if self.eng.n_dec > 0:
+            return (1 - self.alpha) * loss_dec + self.alpha * loss_enc, loss_dec, loss_enc
+        return loss_enc, 0.0, loss_enc
+
+    def step_host(self, host):
+        losses = self.step_device(self.to_device(host))
+        self.fetch_losses(losses)
+        return self.wait_losses()
+
     def fetch_losses(self, losses):
         if self.dev.type == "cuda":
             self._host_loss.copy_(losses, non_blocking=True)
