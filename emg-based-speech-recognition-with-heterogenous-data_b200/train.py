@@ -209,6 +209,33 @@ class Trainer:
         self._loss_event = None
         self.launch_count = 0
 
+    # ---- checkpoint / resume (the reference saves model.state_dict() only, recognition_model.py:310-312; optimizer, step and
+    #      accumulation state are added so that a resumed run continues bit-for-bit) -------------------------------------
+    def state_dict(self, dataparallel_prefix=False):
+        """{'model': reference-named state_dict (optionally with the 'module.' prefix nn.DataParallel checkpoints carry,
+        SURVEY.md section 5), 'optim': flat Adam moments + counters}.  Tensors are copies on the host."""
+        pre = "module." if dataparallel_prefix else ""
+        model_sd = {pre + k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()}
+        return {"model": model_sd,
+                "optim": {"names": list(self.flat.names), "m": self.flat.m.cpu().clone(), "v": self.flat.v.cpu().clone(),
+                          "step_count": self.flat.step_count, "batch_idx": self.batch_idx, "sum_batch_size": self.sum_batch_size,
+                          "g": self.flat.g.cpu().clone(), "lr": self.lr}}
+
+    def load_state_dict(self, sd):
+        model_sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in sd["model"].items()}
+        self.model.load_state_dict(model_sd)                     # copies into the flat fp32 views (storage is unchanged)
+        o = sd.get("optim")
+        if o is not None:
+            if list(o["names"]) != list(self.flat.names):
+                raise L.SstError("optimizer state belongs to a different model configuration")
+            self.flat.m.copy_(o["m"]); self.flat.v.copy_(o["v"]); self.flat.g.copy_(o["g"])
+            self.flat.step_count, self.batch_idx, self.sum_batch_size = o["step_count"], o["batch_idx"], o["sum_batch_size"]
+            self.lr = o["lr"]
+        if self.flat.pb is not None:
+            self.flat.pb.copy_(self.flat.p)                      # refresh the bf16 shadow of the GEMM operands
+        self.eng.pack()
+        self.model._weights_version += 1
+
     def schedule_lr(self, iteration):
         """recognition_model.py:57-64."""
         iteration = iteration + 1

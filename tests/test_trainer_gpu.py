@@ -108,3 +108,41 @@ def test_bf16_shadow_and_repack_follow_the_optimizer():
     wq = P["transformerEncoder.layers.0.self_attn.w_q"].detach()                                # (H, D, dh) -> rows (h, a), cols f
     packed = eng.pk["transformerEncoder.layers.0.self_attn.qkv"][:768]
     assert torch.equal(packed, wq.permute(0, 2, 1).reshape(768, 768).bfloat16())
+
+
+def test_checkpoint_resume_continues_the_run():
+    """Two steps straight through vs one step, save, fresh Trainer, load, one step (dropout on: the seeds derive from the
+    step counter that the checkpoint carries).  fp32 atomics (split-K weight gradients, bias sums) make two runs agree
+    to rounding, not bitwise, so the comparison is to 1e-3 of the moment / update scale."""
+    from sst_b200.train import Trainer
+    from sst_b200 import architecture as A
+    cfg = O.make_cfg(n_enc=1, n_dec=1, rel_dist=100, alpha=0.2)
+    sd0 = O.synthetic_state_dict(cfg, 9)
+    batches = [O.synthetic_batch(seed=60 + k, ragged=[70, 100, 30], tgt_lens=[9, 14, 5]) for k in range(2)]
+
+    def fresh():
+        model = _model(cfg, sd0, "bf16")
+        A.configure(dropout_model=0.2, dropout_pos_emb=0.2)
+        model.cfg["dropout"], model.cfg["dropout_pos"] = 0.2, 0.2
+        return Trainer(model, alpha_loss=0.2, batch_size_grad=1, seed=3)
+
+    t1 = fresh()
+    for b in batches:
+        l1 = t1.step_device(t1.to_device(t1.prepare(b)), shift_r=2)
+    t2 = fresh()
+    t2.step_device(t2.to_device(t2.prepare(batches[0])), shift_r=2)
+    ck = t2.state_dict(dataparallel_prefix=True)
+    assert all(k.startswith("module.") for k in ck["model"])
+    t3 = fresh()
+    t3.load_state_dict(ck)
+    assert (t3.flat.step_count, t3.batch_idx) == (1, 1)
+    l3 = t3.step_device(t3.to_device(t3.prepare(batches[1])), shift_r=2)
+    torch.cuda.synchronize()
+    assert (t3.flat.step_count, t3.batch_idx) == (t1.flat.step_count, t1.batch_idx) == (2, 2)
+    assert float((l1 - l3).abs().max()) < 1e-3 * float(l1.abs().max())              # same dropout masks, same weights
+    assert float((t1.flat.m - t3.flat.m).abs().max()) < 1e-3 * float(t1.flat.m.abs().max())
+    assert float((t1.flat.p - t3.flat.p).abs().max()) < 2.1 * t1.lr                   # at most one AdamW step apart anywhere
+    assert float(((t1.flat.p - t3.flat.p).abs() > 0.05 * t1.lr).float().mean()) < 0.02
+    b1, b3 = dict(t1.model.named_buffers()), dict(t3.model.named_buffers())
+    for k in b1:
+        assert float((b1[k].float() - b3[k].float()).abs().max()) <= 1e-4 * (float(b1[k].float().abs().max()) + 1e-6), k
