@@ -3,6 +3,11 @@
 // warp 1 = MMA issuer (one thread) + TMEM owner, warps 2-17 = epilogue (TMEM lane quarter = warp & 3, four warps per
 // quarter splitting the tile's columns).
 //
+// CTAS = 2 runs the same roles as a CTA PAIR (cluster of two, tcgen05 cta_group::2): one 256 x BN tile per pair, each CTA
+// stages its 128 rows of A and its BN/2 rows of B (a third less shared-memory fill per flop than two independent
+// 128 x BN tiles), rank 0 issues the 256-row MMAs for both, the accumulator rows land in each CTA's own TMEM and each
+// CTA runs the epilogue of its 128 rows.
+//
 // One kernel covers every dense contraction of the hot path (include/sst.h, "GEMM family"):
 //   TN     : C = A[M,K] * B[N,K]^T, both K-major.  A may be read as up to three row-shifted column windows
 //            ("taps"): a k=3 Conv1d over a time-padded channels-last activation is a GEMM whose K blocks come
@@ -46,28 +51,31 @@ struct GemmKParams {
   int remap_P, remap_T, remap_j0;
 };
 
-template <int BN> struct GemmCfg {
-  static constexpr int B_BYTES = BN * G_BK * 2;
+template <int BN, int CTAS> struct GemmCfg {
+  static constexpr int B_ROWS = BN / CTAS;                        // rows of the B tile this CTA stages
+  static constexpr int B_BYTES = B_ROWS * G_BK * 2;
   static constexpr int STAGE_BYTES = G_A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int TMEM_COLS = 2 * BN;                       // two accumulator buffers
   static constexpr int STAGING_BYTES = G_EPI_WARPS * 2048;        // per epilogue warp: 32 rows x 64 B of bf16 output
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STAGING_BYTES;
+  static constexpr int STAGES_FIT = (227 * 1024 - 1024 - 512 - STAGING_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;  // 4 (256,1) / 6 (256,2), (128,1) / 8 (128,2)
+  static constexpr int TMEM_COLS = 2 * BN;                        // two accumulator buffers
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + STAGING_BYTES;
 };
 
-__device__ __forceinline__ void decode_unit(const GemmKParams& p, int u, int& m0, int& n0, int& kb0, int& kb1) {
+template <int CTAS>
+__device__ __forceinline__ void decode_unit(const GemmKParams& p, int u, int rank, int& m0, int& n0, int& kb0, int& kb1) {
   int tile = u / p.splits, split = u - tile * p.splits;
   int mb = tile / p.n_blks, nb = tile - mb * p.n_blks;
-  m0 = mb * G_BM;
+  m0 = (mb * CTAS + rank) * G_BM;
   n0 = nb;   // caller multiplies by BN
   kb0 = split * p.kb_per_split;
   kb1 = min(kb0 + p.kb_per_split, p.num_kb);
 }
 
-template <int BN>
+template <int BN, int CTAS>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTAS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -75,9 +83,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull = empty + Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256;
+  uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 512;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = CTAS == 2 ? (int)ptx::cluster_ctarank() : 0;        // rank 0 of a pair issues the MMAs
+  const int unit0 = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -86,15 +97,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-      for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], G_EPI_WARPS); }
+      for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], G_EPI_WARPS * CTAS); }
       ptx::fence_barrier_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    ptx::tmem_relinquish();
+    if (CTAS == 2) { ptx::tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS); ptx::tmem_relinquish_pair(); }
+    else { ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) ptx::cluster_sync(); else __syncthreads();       // the peer's barriers exist before anything signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -104,33 +115,39 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ================================ TMA producer ================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      // pair mode: both CTAs' loads are counted on the LEADER's full barrier (it waits for 2 x STAGE_BYTES)
+      auto load = [&](void* dst, const CUtensorMap* tm, int st, int x, int y) {
+        if (CTAS == 2) ptx::tma_load_2d_pair(dst, tm, ptx::map_to_cta(&full[st], 0), x, y);
+        else ptx::tma_load_2d(dst, tm, &full[st], x, y);
+      };
+      for (int u = unit0; u < total_units; u += unit_stride) {
         int m0, nb, kb0, kb1;
-        decode_unit(p, u, m0, nb, kb0, kb1);
+        decode_unit<CTAS>(p, u, rank, m0, nb, kb0, kb1);
         const int n0 = nb * BN;
+        const int nB = n0 + rank * Cfg::B_ROWS;                  // this CTA's slice of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1u);
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + G_A_BYTES;
-          ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], CTAS * Cfg::STAGE_BYTES);
           if (!p.mode_mn) {
             int seg = kb / p.kb_per_seg;
             int x = p.a_col0[seg] + (kb - seg * p.kb_per_seg) * G_BK;
-            ptx::tma_load_2d(sA, &tmA, &full[stage], x, m0 + p.a_row_shift[seg]);
+            load(sA, &tmA, stage, x, m0 + p.a_row_shift[seg]);
           } else {
             const int k0 = kb * G_BK;
 #pragma unroll
-            for (int i = 0; i < G_BM / 64; ++i) ptx::tma_load_2d(sA + i * 8192, &tmA, &full[stage], m0 + i * 64, k0);
+            for (int i = 0; i < G_BM / 64; ++i) load(sA + i * 8192, &tmA, stage, m0 + i * 64, k0);
           }
           if (!p.b_mn) {
-            ptx::tma_load_2d(sB, &tmB, &full[stage], kb * G_BK, n0);
+            load(sB, &tmB, stage, kb * G_BK, nB);
           } else {
             const int k0 = kb * G_BK;
             int seg = n0 / p.nseg_cols;
-            int nin = n0 - seg * p.nseg_cols;
+            int nin = nB - seg * p.nseg_cols;
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              ptx::tma_load_2d(sB + j * 8192, &tmB, &full[stage], p.b_col0[seg] + nin + j * 64, k0 + p.b_row_shift[seg]);
+            for (int j = 0; j < Cfg::B_ROWS / 64; ++j)
+              load(sB + j * 8192, &tmB, stage, p.b_col0[seg] + nin + j * 64, k0 + p.b_row_shift[seg]);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -138,12 +155,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    const uint32_t idesc = ptx::make_idesc_bf16(G_BM, BN, p.mode_mn, p.b_mn);
+    const uint32_t idesc = ptx::make_idesc_bf16(G_BM * CTAS, BN, p.mode_mn, p.b_mn);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+    for (int u = unit0; u < total_units && rank == 0; u += unit_stride) {
       int m0, nb, kb0, kb1;
-      decode_unit(p, u, m0, nb, kb0, kb1);
+      decode_unit<CTAS>(p, u, rank, m0, nb, kb0, kb1);
       ptx::mbar_wait(&tempty[acc], acc_phase ^ 1u);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -159,10 +176,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                            : ptx::make_smem_desc_sw128(a_base + k * 2048, 8192, 1024);
             const uint64_t bd = !p.b_mn ? ptx::make_smem_desc_sw128(b_base + k * 32, 0, 1024)
                                         : ptx::make_smem_desc_sw128(b_base + k * 2048, 8192, 1024);
-            ptx::umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CTAS == 2) ptx::umma_bf16_pair(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else ptx::umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          ptx::umma_commit(&empty[stage]);
-          if (kb == kb1 - 1) ptx::umma_commit(&tfull[acc]);
+          if (CTAS == 2) {                                       // both CTAs' producers / epilogues are released
+            ptx::umma_commit_pair(&empty[stage]);
+            if (kb == kb1 - 1) ptx::umma_commit_pair(&tfull[acc]);
+          } else {
+            ptx::umma_commit(&empty[stage]);
+            if (kb == kb1 - 1) ptx::umma_commit(&tfull[acc]);
+          }
         }
         __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
@@ -175,55 +198,90 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
     const int cg = (warp - 2) >> 2;               // column group: chunks [cg * CPW, (cg + 1) * CPW)
     int acc = 0; uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+    for (int u = unit0; u < total_units; u += unit_stride) {
       int m0, nb, kb0, kb1;
-      decode_unit(p, u, m0, nb, kb0, kb1);
+      decode_unit<CTAS>(p, u, rank, m0, nb, kb0, kb1);
       const int n0 = nb * BN;
       const int m = m0 + q * 32 + lane;
       // Epilogue inputs that do not depend on the accumulator are produced BEFORE waiting for it, i.e. under the MMA
       // main loop: the dropout keep bits (Philox, eight 16-bit lanes per block) and the ReLU/dropout mask bits of `aux`.
       constexpr int CPW = BN / 32 / G_CGROUPS;      // 32-column chunks per epilogue warp
-      uint32_t keep_bits[CPW], mask_bits[CPW];
-      if (p.epilogue & SST_EPI_DROPOUT) {
+      const uint32_t stg = ptx::smem_u32(staging) + (uint32_t)(warp - 2) * 2048;
+      Philox4 rnd[4];                               // 16-bit lane e of block i8 decides column i8 * 8 + e of a chunk
+      uint32_t mask_bits[CPW];
+      auto draw = [&](int lc) {                     // the four Philox blocks of chunk lc (kept in registers until used)
+        const int nbase = n0 + (cg * CPW + lc) * 32;
+        const unsigned long long e0 = (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)nbase;
 #pragma unroll
-        for (int lc = 0; lc < CPW; ++lc) {
-          const int nbase = n0 + (cg * CPW + lc) * 32;
-          const unsigned long long e0 = (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)nbase;
-          uint32_t bits = 0;
-#pragma unroll
-          for (int i8 = 0; i8 < 4; ++i8) {
-            const Philox4 rr = philox4x32_10(p.seed, (e0 >> 3) + i8);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) bits |= (philox_lane16(rr, e) >= p.drop_thr ? 1u : 0u) << (i8 * 8 + e);
-          }
-          keep_bits[lc] = bits;
-        }
-      }
+        for (int i8 = 0; i8 < 4; ++i8) rnd[i8] = philox4x32_10(p.seed, (e0 >> 3) + i8);
+      };
+      if (p.epilogue & SST_EPI_DROPOUT) draw(0);    // first chunk's bits are produced under the MMA main loop
       if (p.epilogue & SST_EPI_MULMASK) {
+        // bits of (aux > 0).  Fast path: the warp reads its 32 x 32 chunk of aux as 8 rows x 64 B per instruction
+        // (whole sectors), each lane turns its 8 values into a mask byte, and the bytes are transposed through the
+        // warp's staging slice so that lane l ends up with the 32-bit mask of row l.
+        const bool aux_vec = !p.aux_f32 && (p.ldaux & 7) == 0 && (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0;
+        const __nv_bfloat16* auxh = reinterpret_cast<const __nv_bfloat16*>(p.aux);
+        const int rl0 = lane >> 2, piece = lane & 3;
+        uint4 aw[CPW][4];
+#pragma unroll
+        for (int lc = 0; lc < CPW; ++lc) {                      // every load of the tile is in flight before the first use
+          const int nbase = n0 + (cg * CPW + lc) * 32;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int mr = m0 + q * 32 + it * 8 + rl0;
+            aw[lc][it] = make_uint4(0u, 0u, 0u, 0u);
+            if (aux_vec && nbase + 32 <= p.N && mr < p.M)
+              aw[lc][it] = __ldg(reinterpret_cast<const uint4*>(auxh + (long)mr * p.ldaux + nbase + piece * 8));
+          }
+        }
+        {                                                       // next tile's slice of aux: pull it into L2 meanwhile
+          const int un = u + unit_stride;
+          if (aux_vec && un < total_units) {
+            int m0n, nbn, k0n, k1n;
+            decode_unit<CTAS>(p, un, rank, m0n, nbn, k0n, k1n);
+#pragma unroll
+            for (int lc = 0; lc < CPW; ++lc) {
+              const int nbase = nbn * BN + (cg * CPW + lc) * 32;
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int mr = m0n + q * 32 + it * 8 + rl0;
+                if (nbase + 32 <= p.N && mr < p.M && piece == 0)
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(auxh + (long)mr * p.ldaux + nbase));
+              }
+            }
+          }
+        }
 #pragma unroll
         for (int lc = 0; lc < CPW; ++lc) {
           const int nbase = n0 + (cg * CPW + lc) * 32;
           uint32_t bits = 0;
-          if (m < p.M && nbase < p.N) {
+          if (aux_vec && nbase + 32 <= p.N) {                   // warp-uniform
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&aw[lc][it]);
+              uint32_t byte = 0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) byte |= (__bfloat162float(h[i]) > 0.f ? 1u : 0u) << i;
+              asm volatile("st.shared.u8 [%0], %1;" ::"r"(stg + lc * 128 + (it * 8 + rl0) * 4 + piece), "r"(byte) : "memory");
+            }
+            __syncwarp();
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(bits) : "r"(stg + lc * 128 + lane * 4) : "memory");
+          } else if (m < p.M && nbase < p.N) {
             const int ncols = min(32, p.N - nbase);
             const long ab = (long)m * p.ldaux + nbase;
-            if (!p.aux_f32 && ncols == 32 && (p.ldaux & 7) == 0) {
-              const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + ab);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 w = __ldg(ap + j);
-                const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&w);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) bits |= (__bfloat162float(h[i]) > 0.f ? 1u : 0u) << (j * 8 + i);
-              }
-            } else {
-              for (int i = 0; i < ncols; ++i)
-                bits |= (ld_as_f32(p.aux, ab + i, p.aux_f32 ? SST_F32 : SST_BF16) > 0.f ? 1u : 0u) << i;
-            }
+            for (int i = 0; i < ncols; ++i)
+              bits |= (ld_as_f32(p.aux, ab + i, p.aux_f32 ? SST_F32 : SST_BF16) > 0.f ? 1u : 0u) << i;
           }
           mask_bits[lc] = bits;
         }
+        __syncwarp();
       }
+      // scale folding: without a bias the mask scale commutes with everything in front of it
+      const bool fold_ms = (p.epilogue & SST_EPI_MULMASK) && !(p.epilogue & SST_EPI_BIAS);
+      const float alpha_eff = fold_ms ? p.alpha * p.mask_scale : p.alpha;
+      const uint32_t thr_hi = p.drop_thr << 16;
+      const bool bias_vec = (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
       bool row_ok = m < p.M;
@@ -246,7 +304,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         st_row[it] = __shfl_sync(0xffffffffu, out_row, src);
         st_ok[it] = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, src) != 0;
       }
-      const uint32_t stg = ptx::smem_u32(staging) + (uint32_t)(warp - 2) * 2048;
 #pragma unroll
       for (int lc0 = 0; lc0 < CPW; ++lc0) {
         const int c = cg * CPW + lc0;
@@ -258,26 +315,50 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const bool chunk_staged = staged && nbase + 32 <= p.N;          // warp-uniform
         if ((row_ok || chunk_staged) && nbase < p.N) {
           float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
           const int ncols = min(32, p.N - nbase);
-          if (p.epilogue & SST_EPI_BIAS) {
+          if (!(p.epilogue & SST_EPI_BIAS)) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += __ldg(p.bias + nbase + i);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha_eff;
+          } else if (bias_vec && ncols == 32) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + nbase);   // same address in every lane: one broadcast
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), alpha_eff, b.x);
+              v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), alpha_eff, b.y);
+              v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), alpha_eff, b.z);
+              v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), alpha_eff, b.w);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[i]), alpha_eff, i < ncols ? __ldg(p.bias + nbase + i) : 0.f);
           }
           if (p.epilogue & SST_EPI_RELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           }
           if (p.epilogue & SST_EPI_DROPOUT) {
-            const uint32_t kb = keep_bits[lc0];
+            // kept iff the element's 16-bit Philox lane >= thr16: the high half is compared in place, the low half after
+            // one shift (same decision as philox_keep16)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = ((kb >> i) & 1u) ? v[i] * p.drop_scale : 0.f;
+            for (int i = 0; i < 32; ++i) {
+              const Philox4& rr = rnd[i >> 3];
+              const int wi = (i & 7) >> 1;
+              const uint32_t w = wi == 0 ? rr.x : wi == 1 ? rr.y : wi == 2 ? rr.z : rr.w;
+              const bool keep = ((i & 1) ? w : (w << 16)) >= thr_hi;
+              v[i] = keep ? v[i] * p.drop_scale : 0.f;
+            }
+            if (lc0 + 1 < CPW) draw(lc0 + 1);
           }
           if (p.epilogue & SST_EPI_MULMASK) {
             const uint32_t mb = mask_bits[lc0];
+            if (fold_ms) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= ((mb >> i) & 1u) ? p.mask_scale : 0.f;
+              for (int i = 0; i < 32; ++i) v[i] = ((mb >> i) & 1u) ? v[i] : 0.f;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = ((mb >> i) & 1u) ? v[i] * p.mask_scale : 0.f;
+            }
           }
           const long cb = out_row * p.ldc + nbase;
           if (chunk_staged) {
@@ -361,17 +442,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (CTAS == 2) ptx::mbar_arrive_cluster(ptx::map_to_cta(&tempty[acc], 0));
+        else ptx::mbar_arrive(&tempty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
   }
 
+  __syncwarp();
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) ptx::cluster_sync(); else __syncthreads();       // the pair is done with each other's smem / barriers
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CTAS == 2) ptx::tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -412,9 +498,10 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, long cols, long rows, l
   return SST_OK;
 }
 
-template <int BN>
+template <int BN, int CTAS>
 static int launch_bn(const SstGemmDesc& d, const void* A, const void* B, GemmKParams& p, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTAS>;
+  p.m_blks = cdiv(d.M, G_BM * CTAS);
   p.n_blks = cdiv(d.N, BN);
   const int tiles = p.m_blks * p.n_blks;
   const int sms = num_sms();
@@ -422,7 +509,7 @@ static int launch_bn(const SstGemmDesc& d, const void* A, const void* B, GemmKPa
   if (p.mode_mn) {
     // split K (= tokens) until the machine is full, but keep >= 16 k-blocks per unit: every unit pays a pipeline fill and
     // a (BM x BN) fp32 atomic epilogue
-    splits = (2 * sms) / tiles;
+    splits = (2 * sms / CTAS) / tiles;
     const int max_by_k = p.num_kb / 16;
     if (splits > max_by_k) splits = max_by_k;
     if (splits < 1) splits = 1;
@@ -446,19 +533,32 @@ static int launch_bn(const SstGemmDesc& d, const void* A, const void* B, GemmKPa
     if ((rc = make_tmap_bf16_2d(&tmA, A, d.a_cols, d.a_rows, d.lda, 64, G_BK))) return rc;
   }
   if (!p.b_mn) {
-    if ((rc = make_tmap_bf16_2d(&tmB, B, d.K, d.N, d.ldb, G_BK, BN))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tmB, B, d.K, d.N, d.ldb, G_BK, Cfg::B_ROWS))) return rc;
   } else {
     if ((rc = make_tmap_bf16_2d(&tmB, B, d.b_cols, d.b_rows, d.ldb, 64, G_BK))) return rc;
   }
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     SST_REQUIRE(e == cudaSuccess, SST_E_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_done = true;
   }
   const int units = tiles * p.splits;
-  const int grid = units < sms ? units : sms;
-  gemm_tcgen05_kernel<BN><<<grid, G_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  const int slots = sms / CTAS;                                  // CTAs (or CTA pairs = TPCs) that can be resident
+  const int grid = (units < slots ? units : slots) * CTAS;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(G_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CTAS>, tmA, tmB, p);
+  SST_REQUIRE(le == cudaSuccess, SST_E_LAUNCH, "gemm_tcgen05 launch: %s", cudaGetErrorString(le));
   return check_launch("gemm_tcgen05");
 }
 
@@ -488,7 +588,6 @@ int launch_gemm_tcgen05(const SstGemmDesc& d, const void* A, const void* B, void
     SST_REQUIRE(nseg == 1 || (d.N % nseg == 0 && p.nseg_cols % 256 == 0), SST_E_ARG,
                 "segmented B needs N/n_seg to be a multiple of 256");
   }
-  p.m_blks = cdiv(d.M, G_BM);
   p.epilogue = d.epilogue;
   p.alpha = d.alpha; p.mask_scale = d.mask_scale;
   p.drop_thr = drop_threshold16(d.drop_p);
@@ -499,14 +598,21 @@ int launch_gemm_tcgen05(const SstGemmDesc& d, const void* A, const void* B, void
   p.C = C; p.ldc = d.ldc; p.out_f32 = d.out_dtype == SST_F32;
   p.remap_P = d.remap_P; p.remap_T = d.remap_T; p.remap_j0 = d.remap_j0;
   if (d.epilogue & SST_EPI_DROPOUT) SST_REQUIRE(d.N % 8 == 0, SST_E_ARG, "dropout epilogue needs N %% 8 == 0");
+  // CTA pairs (256-row tiles) whenever there are at least two row blocks; SST_GEMM_CTAS=1 forces single-CTA tiles
+  static const int ctas_env = [] { const char* e = getenv("SST_GEMM_CTAS"); return e ? atoi(e) : 2; }();
+  const int ctas = (ctas_env == 2 && d.M > G_BM) ? 2 : 1;
   // tile width by wave quantisation: time ~ waves * BN; 256-wide tiles reuse the A tile twice as long, so 128 must win by 10 %
-  if (d.N <= 128) return launch_bn<128>(d, A, B, p, st);
-  if (p.mode_mn) return (d.N % 256 == 0) ? launch_bn<256>(d, A, B, p, st) : launch_bn<128>(d, A, B, p, st);
-  const long sms = num_sms();
-  const long t256 = (long)p.m_blks * cdiv(d.N, 256), t128 = (long)p.m_blks * cdiv(d.N, 128);
-  const long c256 = ((t256 + sms - 1) / sms) * 256, c128 = ((t128 + sms - 1) / sms) * 128;
-  if (c128 * 10 < c256 * 9) return launch_bn<128>(d, A, B, p, st);
-  return launch_bn<256>(d, A, B, p, st);
+  bool wide = true;
+  if (d.N <= 128) wide = false;
+  else if (p.mode_mn) wide = d.N % 256 == 0;
+  else {
+    const long slots = num_sms() / ctas, mb = cdiv(d.M, G_BM * ctas);
+    const long t256 = mb * cdiv(d.N, 256), t128 = mb * cdiv(d.N, 128);
+    const long c256 = ((t256 + slots - 1) / slots) * 256, c128 = ((t128 + slots - 1) / slots) * 128;
+    wide = !(c128 * 10 < c256 * 9);
+  }
+  if (ctas == 2) return wide ? launch_bn<256, 2>(d, A, B, p, st) : launch_bn<128, 2>(d, A, B, p, st);
+  return wide ? launch_bn<256, 1>(d, A, B, p, st) : launch_bn<128, 1>(d, A, B, p, st);
 }
 
 }  // namespace sst
