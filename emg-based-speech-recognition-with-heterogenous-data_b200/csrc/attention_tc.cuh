@@ -232,9 +232,10 @@ __device__ __forceinline__ void dropout_keep(const AttnTcParams& p, const RowCtx
   const unsigned long long base = ((unsigned long long)rc.row_id * p.Lkp + j0 + CW * hf) >> 3;
 #pragma unroll
   for (int g = 0; g < CW / 8; ++g) {
-    const Philox4 r = philox4x32_10(p.seed, base + g);
+    const Philox4 r = philox4x32(p.seed, base + g);
+    const uint32_t thr_hi = p.thr << 16;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) keep[g * 8 + e] = philox_lane16(r, e) >= p.thr ? p.dscale : 0.f;
+    for (int e = 0; e < 8; ++e) keep[g * 8 + e] = philox_keep16_at(r, e, thr_hi) ? p.dscale : 0.f;
   }
 }
 

@@ -213,7 +213,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int nbase = n0 + (cg * CPW + lc) * 32;
         const unsigned long long e0 = (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)nbase;
 #pragma unroll
-        for (int i8 = 0; i8 < 4; ++i8) rnd[i8] = philox4x32_10(p.seed, (e0 >> 3) + i8);
+        for (int i8 = 0; i8 < 4; ++i8) rnd[i8] = philox4x32(p.seed, (e0 >> 3) + i8);
       };
       if (p.epilogue & SST_EPI_DROPOUT) draw(0);    // first chunk's bits are produced under the MMA main loop
       if (p.epilogue & SST_EPI_MULMASK) {
@@ -342,11 +342,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // one shift (same decision as philox_keep16)
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const Philox4& rr = rnd[i >> 3];
-              const int wi = (i & 7) >> 1;
-              const uint32_t w = wi == 0 ? rr.x : wi == 1 ? rr.y : wi == 2 ? rr.z : rr.w;
-              const bool keep = ((i & 1) ? w : (w << 16)) >= thr_hi;
-              v[i] = keep ? v[i] * p.drop_scale : 0.f;
+              v[i] = philox_keep16_at(rnd[i >> 3], i & 7, thr_hi) ? v[i] * p.drop_scale : 0.f;
             }
             if (lc0 + 1 < CPW) draw(lc0 + 1);
           }

@@ -11,9 +11,10 @@ constexpr int LN_MAXV = 8;   // up to 8 vectors of 8 per lane -> D <= 2048
 // 8 dropout keep decisions for elements idx .. idx+7 (idx % 8 == 0): ONE Philox block, eight 16-bit lanes
 // (sst_common.cuh philox_keep16 -- the same stream the host mirror in tests/helpers.py draws)
 __device__ __forceinline__ void keep8_16(unsigned long long seed, unsigned long long idx, uint32_t thr16, bool (&k)[8]) {
-  const Philox4 r = philox4x32_10(seed, idx >> 3);
+  const Philox4 r = philox4x32(seed, idx >> 3);
+  const uint32_t thr_hi = thr16 << 16;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) k[e] = philox_lane16(r, e) >= thr16;
+  for (int e = 0; e < 8; ++e) k[e] = philox_keep16_at(r, e, thr_hi);
 }
 
 // One warp per row, NV vectors of 8 columns per lane (column c = (i*32 + lane)*8, the same columns for every row the

@@ -47,9 +47,13 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// ---- Philox4x32-10 counter RNG: the one dropout stream shared by every kernel ---------------------
+// ---- Philox4x32 counter RNG: the one dropout stream shared by every kernel -------------------------
 // keep(seed, idx) is a pure function of (seed, element index) so forward and backward kernels (and the
 // SIMT and tensor-core variants of one op) regenerate identical masks without storing them.
+// Seven rounds: the smallest Philox4x32 variant that passes BigCrush (Salmon et al., SC'11, "Philox4x32-7");
+// the RNG is the largest per-element cost of the fused softmax and of the FFN dropout epilogue, and the three
+// extra rounds of the -10 default buy nothing a dropout mask can use.  tests/helpers.py mirrors it on the host.
+constexpr int PHILOX_ROUNDS = 7;
 struct Philox4 { uint32_t x, y, z, w; };
 __host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
 #ifdef __CUDA_ARCH__
@@ -58,11 +62,11 @@ __host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
   return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
 }
-__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint64_t seed, uint64_t ctr) {
+__host__ __device__ __forceinline__ Philox4 philox4x32(uint64_t seed, uint64_t ctr) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x5353542du, c3 = 0x62323030u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < PHILOX_ROUNDS; ++r) {
     uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
@@ -77,7 +81,7 @@ __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
   return t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
 }
 __host__ __device__ __forceinline__ bool philox_keep(uint64_t seed, uint64_t idx, uint32_t thr) {
-  Philox4 r = philox4x32_10(seed, idx >> 2);
+  Philox4 r = philox4x32(seed, idx >> 2);
   uint32_t v = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
   return v >= thr;
 }
@@ -93,7 +97,13 @@ __host__ __device__ __forceinline__ uint32_t philox_lane16(const Philox4& r, int
   return (sub & 1) ? (w >> 16) : (w & 0xffffu);
 }
 __host__ __device__ __forceinline__ bool philox_keep16(uint64_t seed, uint64_t idx, uint32_t thr16) {
-  return philox_lane16(philox4x32_10(seed, idx >> 3), (int)(idx & 7)) >= thr16;
+  return philox_lane16(philox4x32(seed, idx >> 3), (int)(idx & 7)) >= thr16;
+}
+// The same decision for a compile-time lane `sub` without extracting it: the high half of a word is compared in place
+// against thr16 << 16, the low half after one shift.
+__host__ __device__ __forceinline__ bool philox_keep16_at(const Philox4& r, int sub, uint32_t thr16_hi) {
+  const uint32_t w = (sub >> 1) == 0 ? r.x : (sub >> 1) == 1 ? r.y : (sub >> 1) == 2 ? r.z : r.w;
+  return ((sub & 1) ? w : (w << 16)) >= thr16_hi;
 }
 
 }  // namespace sst

@@ -37,7 +37,7 @@ __device__ __forceinline__ void load8_f32(const float* p, float (&v)[8]) { Vec8<
 
 // 8 dropout keep bits for elements idx .. idx+7 (idx % 4 == 0): two Philox blocks.
 __device__ __forceinline__ void keep8(unsigned long long seed, unsigned long long idx, uint32_t thr, bool (&k)[8]) {
-  Philox4 a = philox4x32_10(seed, idx >> 2), b = philox4x32_10(seed, (idx >> 2) + 1);
+  Philox4 a = philox4x32(seed, idx >> 2), b = philox4x32(seed, (idx >> 2) + 1);
   k[0] = a.x >= thr; k[1] = a.y >= thr; k[2] = a.z >= thr; k[3] = a.w >= thr;
   k[4] = b.x >= thr; k[5] = b.y >= thr; k[6] = b.z >= thr; k[7] = b.w >= thr;
 }

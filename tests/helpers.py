@@ -79,8 +79,11 @@ def check_grads_against_golden(z, meta, grads, tol, label="", slack=3.0, report=
     return worst
 
 
-def _philox4x32_10(seed, ctr):
-    """numpy Philox4x32-10 with the key/counter layout of csrc/sst_common.cuh; returns the four 32-bit outputs."""
+PHILOX_ROUNDS = 7      # csrc/sst_common.cuh PHILOX_ROUNDS
+
+
+def _philox4x32(seed, ctr):
+    """numpy Philox4x32-7 with the key/counter layout of csrc/sst_common.cuh; returns the four 32-bit outputs."""
     M32 = np.uint64(0xFFFFFFFF)
     c0 = ctr & M32
     c1 = ctr >> np.uint64(32)
@@ -88,7 +91,7 @@ def _philox4x32_10(seed, ctr):
     c3 = np.full_like(c0, 0x62323030)
     k0 = np.uint64(seed & 0xFFFFFFFF)
     k1 = np.uint64((seed >> 32) & 0xFFFFFFFF)
-    for _ in range(10):
+    for _ in range(PHILOX_ROUNDS):
         p0 = np.uint64(0xD2511F53) * c0
         p1 = np.uint64(0xCD9E8D57) * c2
         hi0, lo0 = p0 >> np.uint64(32), p0 & M32
@@ -103,7 +106,7 @@ def philox_keep_mask16(seed, n_elems, p):
     """Host mirror of csrc/sst_common.cuh philox_keep16(): eight 16-bit keep lanes per Philox block (LayerNorm residual
     dropout, GEMM dropout epilogue, attention probabilities)."""
     idx = np.arange(n_elems, dtype=np.uint64)
-    c = _philox4x32_10(seed, idx >> np.uint64(3))
+    c = _philox4x32(seed, idx >> np.uint64(3))
     sub = idx & np.uint64(7)
     word = sub >> np.uint64(1)
     w = np.where(word == 0, c[0], np.where(word == 1, c[1], np.where(word == 2, c[2], c[3])))
@@ -124,7 +127,7 @@ def philox_keep_mask(seed, n_elems, p):
     c3 = np.full_like(c0, 0x62323030)
     k0 = np.uint64(seed & 0xFFFFFFFF)
     k1 = np.uint64((seed >> 32) & 0xFFFFFFFF)
-    for _ in range(10):
+    for _ in range(PHILOX_ROUNDS):
         p0 = np.uint64(0xD2511F53) * c0
         p1 = np.uint64(0xCD9E8D57) * c2
         hi0, lo0 = p0 >> np.uint64(32), p0 & M32
