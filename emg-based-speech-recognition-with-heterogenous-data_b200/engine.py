@@ -292,9 +292,11 @@ class Engine:
         else:
             dyr = self.empty(n, T + 1, C)
             ld_dyr, lr, tr = C, 0, 1
-        L.bn_bwd(self.dt, n, T, C, dout, C, c.out, c.lead, c.lead, True,
+        # y=None: the ReLU mask is recomputed from the BN inputs instead of reading the block output back
+        L.bn_bwd(self.dt, n, T, C, dout, C, None, c.lead, c.lead, True,
                  c.yc2, C, c.bn2[0], c.bn2[1], c.bn2[2], dyc2p, C, 1, 1, G[pfx + ".bn2.weight"], G[pfx + ".bn2.bias"],
-                 c.yr, c.ldr, c.bnr[0], c.bnr[1], c.bnr[2], dyr, ld_dyr, lr, tr, G[pfx + ".res_norm.weight"], G[pfx + ".res_norm.bias"], red)
+                 c.yr, c.ldr, c.bnr[0], c.bnr[1], c.bnr[2], dyr, ld_dyr, lr, tr, G[pfx + ".res_norm.weight"], G[pfx + ".res_norm.bias"], red,
+                 beta_a=c.bn2[3], beta_b=c.bnr[3])
         # conv2 (k3, s1): weight gradient in packed (C, 3C) form, then unpack-accumulate into (C, C, 3)
         Pp = T + 2
         dW = self.empty(C, 3 * C, dtype=torch.float32)
@@ -310,9 +312,9 @@ class Engine:
         else:
             dyc1 = self.empty(n, T + 1, C)
             ld_dyc1, l1, t1 = C, 0, 1
-        L.bn_bwd(self.dt, n, T, C, dh1, C, c.h1p, 1, 1, True,
+        L.bn_bwd(self.dt, n, T, C, dh1, C, None, 1, 1, True,
                  c.yc1, c.ld1, c.bn1[0], c.bn1[1], c.bn1[2], dyc1, ld_dyc1, l1, t1, G[pfx + ".bn1.weight"], G[pfx + ".bn1.bias"],
-                 None, 0, None, None, None, None, 0, 0, 0, None, None, red)
+                 None, 0, None, None, None, None, 0, 0, 0, None, None, red, beta_a=c.bn1[3])
         if i == 0:
             dWc = self.empty(2 * C, 32, dtype=torch.float32)
             self.gemm(dycat, c.col, dWc, 2 * C, 32, rows, 2 * C, 32, 32, layout=L.GEMM_NT_MN, a_rows=rows, a_cols=2 * C,

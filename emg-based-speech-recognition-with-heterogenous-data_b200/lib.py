@@ -282,15 +282,16 @@ def bn_apply(dtype, n_chunks, T, Cc, xa, lda, sa, xb, ldb, sb, relu, out, lead, 
 
 def bn_bwd(dtype, n_chunks, T, Cc, dout, ld_dout, y, y_lead, y_trail, relu,
            xa, lda, mean_a, invstd_a, gamma_a, dxa, ld_dxa, lead_a, trail_a, dgamma_a, dbeta_a,
-           xb, ldb, mean_b, invstd_b, gamma_b, dxb, ld_dxb, lead_b, trail_b, dgamma_b, dbeta_b, red):
-    # two passes (reduce, apply): dout, y, xa (+xb) read twice; dxa (+dxb) written
-    with _scope("bn_bwd", bytes=(2.0 * (3.0 + (1.0 if xb is not None else 0.0)) + 1.0 + (1.0 if xb is not None else 0.0))
+           xb, ldb, mean_b, invstd_b, gamma_b, dxb, ld_dxb, lead_b, trail_b, dgamma_b, dbeta_b, red, beta_a=None, beta_b=None):
+    # two passes (reduce, apply): dout, xa (+xb) (+y when the ReLU mask is not recomputed) read twice; dxa (+dxb) written
+    n_in = 2.0 + (1.0 if xb is not None else 0.0) + (1.0 if (relu and y is not None) else 0.0)
+    with _scope("bn_bwd", bytes=(2.0 * n_in + 1.0 + (1.0 if xb is not None else 0.0))
                 * n_chunks * T * Cc * (2 if dtype == BF16 else 4), tag="T%d %s" % (T, "2br" if xb is not None else "1br")):
         check(lib().sst_bn_bwd(dtype, _i64(n_chunks), T, Cc, ptr(dout), _i64(ld_dout), ptr(y), y_lead, y_trail, int(relu),
-                               ptr(xa), _i64(lda), ptr(mean_a), ptr(invstd_a), ptr(gamma_a), ptr(dxa), _i64(ld_dxa), lead_a, trail_a,
-                               ptr(dgamma_a), ptr(dbeta_a),
-                               ptr(xb), _i64(ldb), ptr(mean_b), ptr(invstd_b), ptr(gamma_b), ptr(dxb), _i64(ld_dxb), lead_b, trail_b,
-                               ptr(dgamma_b), ptr(dbeta_b), ptr(red), stream()), "sst_bn_bwd")
+                               ptr(xa), _i64(lda), ptr(mean_a), ptr(invstd_a), ptr(gamma_a), ptr(beta_a), ptr(dxa), _i64(ld_dxa),
+                               lead_a, trail_a, ptr(dgamma_a), ptr(dbeta_a),
+                               ptr(xb), _i64(ldb), ptr(mean_b), ptr(invstd_b), ptr(gamma_b), ptr(beta_b), ptr(dxb), _i64(ld_dxb),
+                               lead_b, trail_b, ptr(dgamma_b), ptr(dbeta_b), ptr(red), stream()), "sst_bn_bwd")
 
 
 def ctc_loss(logits_dtype, grad_dtype, B, L, Cc, blank, logits, ld, targets, Smax, in_lens, tgt_lens, gcoef, lp_ws, alpha_ws,

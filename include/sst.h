@@ -122,11 +122,14 @@ int sst_bn_apply(int dtype, int64_t n_chunks, int T, int C, const void* xa, int6
                  const float* invstd_a, const float* gamma_a, const float* beta_a, const void* xb, int64_t ldb,
                  const float* mean_b, const float* invstd_b, const float* gamma_b, const float* beta_b, int relu, void* out,
                  int lead, int trail, void* stream);
+/* y may be NULL: the ReLU mask is then recomputed from xa / xb and the BN constants (bit-identical sign, one tensor less
+ * to read in each of the two passes); beta_* are only used for that. */
 int sst_bn_bwd(int dtype, int64_t n_chunks, int T, int C, const void* dout, int64_t ld_dout, const void* y, int y_lead,
                int y_trail, int relu, const void* xa, int64_t lda, const float* mean_a, const float* invstd_a,
-               const float* gamma_a, void* dxa, int64_t ld_dxa, int lead_a, int trail_a, float* dgamma_a, float* dbeta_a,
-               const void* xb, int64_t ldb, const float* mean_b, const float* invstd_b, const float* gamma_b, void* dxb,
-               int64_t ld_dxb, int lead_b, int trail_b, float* dgamma_b, float* dbeta_b, double* red /*[3*C]*/, void* stream);
+               const float* gamma_a, const float* beta_a, void* dxa, int64_t ld_dxa, int lead_a, int trail_a,
+               float* dgamma_a, float* dbeta_a, const void* xb, int64_t ldb, const float* mean_b, const float* invstd_b,
+               const float* gamma_b, const float* beta_b, void* dxb, int64_t ld_dxb, int lead_b, int trail_b,
+               float* dgamma_b, float* dbeta_b, double* red /*[3*C]*/, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Attention.  Replaces MultiHeadAttention.forward between the projections (transformer.py:177-208) together

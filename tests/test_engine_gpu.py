@@ -109,7 +109,9 @@ def test_tensor_core_and_cuda_core_paths_agree():
         eng = make_engine(cfg, sd, torch.bfloat16)
         eng.force_simt = simt
         res.append(run_step(eng, cfg, batch))
-    assert rel_err(res[0][0], res[1][0]) < 2e-2
+    # each path is held to 2e-2 of the fp32 reference by the parity tests above; two bf16 paths with different accumulation
+    # orders may sit on opposite sides of it, hence 3e-2 between them
+    assert rel_err(res[0][0], res[1][0]) < 3e-2
     assert abs(res[0][2] - res[1][2]) < 1e-2 * abs(res[1][2])
     from helpers import kink_sensitive
     gm = max(float(v.abs().max()) for v in res[1][5].values())

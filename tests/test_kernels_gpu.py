@@ -124,6 +124,15 @@ def test_batchnorm_two_branch_fwd_bwd(L, dtype):
     assert rel(dxb_wide[:, :T, C:].float().reshape(n * T, C), xb_l.grad) < tolg
     for got, want in ((dga, ga_l.grad), (dba, ba_l.grad), (dgb, gb_l.grad), (dbb, bb_l.grad)):
         assert rel(got, want) < tolg
+    # y = None: the ReLU mask recomputed from xa / xb and the BN constants must be the stored one bit for bit
+    dxa2 = torch.full_like(dxa, 5.0); dxb2 = torch.full_like(dxb_wide, 5.0)
+    dga2, dba2, dgb2, dbb2 = (torch.zeros(C, device=DEV) for _ in range(4))
+    L.bn_bwd(L.dt(xa), n, T, C, dout, C, None, lead, trail, True,
+             xa, C, res["a"][0], res["a"][1], ga, dxa2, C, 1, 1, dga2, dba2,
+             xb, 2 * C, res["b"][0], res["b"][1], gb, dxb2[:, :, C:], 2 * C, 0, 1, dgb2, dbb2, red, beta_a=ba, beta_b=bb)
+    assert torch.equal(dxa2, dxa) and torch.equal(dxb2[:, :, C:], dxb_wide[:, :, C:])
+    for got, want in ((dga2, dga), (dba2, dba), (dgb2, dgb), (dbb2, dbb)):
+        assert rel(got, want) < 1e-6
 
 
 def ref_attention(q, k, v, E, R, scale, causal, q_lens, k_lens, mask_q_rows):
