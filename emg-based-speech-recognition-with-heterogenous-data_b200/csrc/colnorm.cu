@@ -15,42 +15,23 @@ namespace sst {
 
 // ---- per-thread cp.async ring ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g, bool valid) {
-  const int sz = valid ? 16 : 0;                       // 0: nothing is read, the 16 bytes are zero-filled
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(sz) : "memory");
+  if (valid) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");   // invalid rows are never read back
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-constexpr int COL_MAX_STAGES = 16;
-__device__ __forceinline__ void cp_async_wait_upto(int pending) {      // at most `pending` groups still in flight
-  switch (pending) {                                                   // the operand is an immediate
-#define SST_WAIT_CASE(N) case N: asm volatile("cp.async.wait_group " #N ";" ::: "memory"); break;
-    SST_WAIT_CASE(1) SST_WAIT_CASE(2) SST_WAIT_CASE(3) SST_WAIT_CASE(4) SST_WAIT_CASE(5) SST_WAIT_CASE(6) SST_WAIT_CASE(7)
-    SST_WAIT_CASE(8) SST_WAIT_CASE(9) SST_WAIT_CASE(10) SST_WAIT_CASE(11) SST_WAIT_CASE(12) SST_WAIT_CASE(13) SST_WAIT_CASE(14)
-    SST_WAIT_CASE(15)
-#undef SST_WAIT_CASE
-    default: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-  }
-}
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// nt tensors, U rows per step; slot (stage, u, t) of thread `tid` sits at ((stage*U + u)*nt + t) * nthreads + tid.
-template <typename T, int U>
-struct ColRing {
-  static constexpr int SLOT = (int)sizeof(T) * 8;      // 8 elements: 16 B (bf16) or 32 B (fp32)
-  uint32_t base, plane;
-  int nt;
-  __device__ __forceinline__ void init(void* smem, int tid, int nthreads, int nt_) {
-    base = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)tid * SLOT;
-    plane = (uint32_t)nthreads * SLOT;
-    nt = nt_;
-  }
-  __device__ __forceinline__ uint32_t addr(int stage, int u, int t) const { return base + (uint32_t)((stage * U + u) * nt + t) * plane; }
-  __device__ __forceinline__ void issue(int stage, int u, int t, const T* g, bool valid) const {
-    const uint32_t a = addr(stage, u, t);
+constexpr int COL_STAGES = 8;                          // ring depth: 7 steps in flight per thread
+
+// One 8-element slot: 16 B (bf16) or 32 B (fp32).  Slot (stage, u, t) of a thread lives at
+//   ring + stage * stage_bytes + (u * nt + t) * plane + tid * SLOT,     plane = nthreads * SLOT, stage_bytes = U * nt * plane.
+template <typename T> struct ColSlot {
+  static constexpr int BYTES = (int)sizeof(T) * 8;
+  static __device__ __forceinline__ void issue(uint32_t a, const T* g, bool valid) {
     cp_async16(a, g, valid);
-    if (SLOT == 32) cp_async16(a + 16, reinterpret_cast<const char*>(g) + 16, valid);
+    if (BYTES == 32) cp_async16(a + 16, reinterpret_cast<const char*>(g) + 16, valid);
   }
-  __device__ __forceinline__ void read(int stage, int u, int t, float (&v)[8]) const {
-    const uint32_t a = addr(stage, u, t);
-    if (SLOT == 16) {
+  static __device__ __forceinline__ void read(uint32_t a, float (&v)[8]) {
+    if (BYTES == 16) {
       uint4 w;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(a));
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
@@ -63,41 +44,62 @@ struct ColRing {
   }
 };
 
-// The loop every kernel below runs: thread (tx, ty) owns rows first + k*TY (k = 0, 1, ...) below `end`, U of them per
-// step.  `issue(stage, u, row, valid)` queues the copies of one row, `use(stage, u, row)` consumes a landed VALID row.
+struct ColGeom {
+  uint32_t ring, plane, stage_bytes; int nt;
+  __device__ __forceinline__ uint32_t slot(uint32_t slot0, int u, int t) const { return slot0 + (uint32_t)(u * nt + t) * plane; }
+};
+template <typename T>
+__device__ __forceinline__ ColGeom col_geom(void* ring_smem, int U, int nt) {
+  ColGeom g;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nth = blockDim.x * blockDim.y;
+  g.plane = (uint32_t)nth * ColSlot<T>::BYTES;
+  g.ring = (uint32_t)__cvta_generic_to_shared(ring_smem) + (uint32_t)tid * ColSlot<T>::BYTES;
+  g.stage_bytes = (uint32_t)(U * nt) * g.plane;
+  g.nt = nt;
+  return g;
+}
+
+// The loop every kernel below runs: this thread owns rows first + k*stride (k = 0, 1, ...) below `end`, U of them per
+// step.  `issue(slot0, u, row, valid)` queues the copies of one row into the step's slots (slot0 = the thread's slot of
+// (stage, u = 0, t = 0)), `use(slot0, u, row)` consumes a landed, valid row.  All state is a handful of running
+// counters: the loop body is a few instructions beside the kernel's own work.
 template <int U, typename Issue, typename Use>
-__device__ __forceinline__ void stream_rows(long first, long end, long TY, int stages, Issue&& issue, Use&& use) {
-  const long mine = first < end ? (end - first + TY - 1) / TY : 0;
-  const long nsteps = (mine + U - 1) / U;
-  const long stride = (long)U * TY;
-  long rq = first;                                      // first row of the next step to queue
-  long qstep = 0;
-  int qs = 0;                                           // its stage
+__device__ __forceinline__ void stream_rows(int first, int end, int stride, uint32_t ring, uint32_t stage_bytes, Issue&& issue, Use&& use) {
+  constexpr int S = COL_STAGES;
+  const int mine = first < end ? (end - first + stride - 1) / stride : 0;
+  const int nsteps = (mine + U - 1) / U;
+  const int step_rows = U * stride;
+  int rq = first, sq = 0, left = nsteps;
+  uint32_t aq = ring;
   auto queue = [&]() {
-    if (qstep < nsteps) {
+    if (left > 0) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const long r = rq + (long)u * TY;
-        issue(qs, u, r, r < end);
+        const int r = rq + u * stride;
+        issue(aq, u, r, r < end);
       }
+      --left;
     }
     cp_async_commit();                                  // one group per step, empty ones included: the wait counts groups
-    rq += stride; ++qstep;
-    if (++qs == stages) qs = 0;
+    rq += step_rows;
+    aq += stage_bytes;
+    if (++sq == S) { sq = 0; aq = ring; }
   };
-  for (int s = 0; s < stages - 1; ++s) queue();
-  long ru = first;
-  int us = 0;
-  for (long step = 0; step < nsteps; ++step) {
+#pragma unroll
+  for (int s = 0; s < S - 1; ++s) queue();
+  int ru = first, su = 0;
+  uint32_t au = ring;
+  for (int step = 0; step < nsteps; ++step) {
     queue();
-    cp_async_wait_upto(stages - 1);
+    cp_async_wait<S - 1>();
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long r = ru + (long)u * TY;
-      if (r < end) use(us, u, r);
+      const int r = ru + u * stride;
+      if (r < end) use(au, u, r);
     }
-    ru += stride;
-    if (++us == stages) us = 0;
+    ru += step_rows;
+    au += stage_bytes;
+    if (++su == S) { su = 0; au = ring; }
   }
 }
 
@@ -119,7 +121,7 @@ __device__ __forceinline__ void reduce_over_ty(A (&v)[8], A* buf) {
 }
 
 // Dynamic shared memory of these kernels: [reduction scratch | sign constants | ring]; sizes are passed by the launcher.
-struct ColSmem { int red_bytes, sgn_bytes, stages, nt; };
+struct ColSmem { int red_bytes, sgn_bytes, nt; };
 
 // ---- stats[0][c] += sum x, stats[1][c] += sum x^2 (double; fp32 partials over <= 64 rows) --------------------------
 template <typename T>
@@ -128,21 +130,18 @@ colstats_kernel(const T* __restrict__ x, long rows, int C, long ld, double* __re
   extern __shared__ __align__(16) uint8_t smem_raw[];
   double* dbuf = reinterpret_cast<double*>(smem_raw);
   constexpr int U = 2;
-  ColRing<T, U> ring;
-  ring.init(smem_raw + sm.red_bytes, threadIdx.y * blockDim.x + threadIdx.x, blockDim.x * blockDim.y, sm.nt);
+  const ColGeom cg = col_geom<T>(smem_raw + sm.red_bytes, U, sm.nt);
   const int c = threadIdx.x * 8, TY = blockDim.y;
-  const long r0 = (long)blockIdx.x * rows_per_block;
-  const long r1 = min(rows, r0 + rows_per_block);
   double s[8], q[8];
   float fs[8], fq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.0; q[j] = 0.0; fs[j] = 0.f; fq[j] = 0.f; }
   int pending = 0;
-  stream_rows<U>((long)blockIdx.x * TY + threadIdx.y, rows, (long)gridDim.x * TY, sm.stages,
-      [&](int sg, int u, long r, bool valid) { ring.issue(sg, u, 0, valid ? x + r * ld + c : x, valid); },
-      [&](int sg, int u, long) {
+  stream_rows<U>((int)blockIdx.x * TY + (int)threadIdx.y, (int)rows, (int)gridDim.x * TY, cg.ring, cg.stage_bytes,
+      [&](uint32_t a0, int u, int r, bool valid) { ColSlot<T>::issue(cg.slot(a0, u, 0), valid ? x + (long)r * ld + c : x, valid); },
+      [&](uint32_t a0, int u, int) {
         float v[8];
-        ring.read(sg, u, 0, v);
+        ColSlot<T>::read(cg.slot(a0, u, 0), v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { fs[j] += v[j]; fq[j] = fmaf(v[j], v[j], fq[j]); }
         if (++pending == 64) {
@@ -168,19 +167,16 @@ colsum_kernel(const T* __restrict__ x, long rows, int C, long ld, float* __restr
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* fbuf = reinterpret_cast<float*>(smem_raw);
   constexpr int U = 2;
-  ColRing<T, U> ring;
-  ring.init(smem_raw + sm.red_bytes, threadIdx.y * blockDim.x + threadIdx.x, blockDim.x * blockDim.y, sm.nt);
+  const ColGeom cg = col_geom<T>(smem_raw + sm.red_bytes, U, sm.nt);
   const int c = threadIdx.x * 8, TY = blockDim.y;
-  const long r0 = (long)blockIdx.x * rows_per_block;
-  const long r1 = min(rows, r0 + rows_per_block);
   float s[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = 0.f;
-  stream_rows<U>((long)blockIdx.x * TY + threadIdx.y, rows, (long)gridDim.x * TY, sm.stages,
-      [&](int sg, int u, long r, bool valid) { ring.issue(sg, u, 0, valid ? x + r * ld + c : x, valid); },
-      [&](int sg, int u, long) {
+  stream_rows<U>((int)blockIdx.x * TY + (int)threadIdx.y, (int)rows, (int)gridDim.x * TY, cg.ring, cg.stage_bytes,
+      [&](uint32_t a0, int u, int r, bool valid) { ColSlot<T>::issue(cg.slot(a0, u, 0), valid ? x + (long)r * ld + c : x, valid); },
+      [&](uint32_t a0, int u, int) {
         float v[8];
-        ring.read(sg, u, 0, v);
+        ColSlot<T>::read(cg.slot(a0, u, 0), v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s[j] += v[j];
       });
@@ -226,14 +222,11 @@ __global__ void __launch_bounds__(512)
 bn_apply_kernel(BnBranch a, BnBranch b, int has_b, int relu, T* __restrict__ out, long n_chunks, int Tlen, int C, int lead,
                 int trail, long prows_per_block, ColSmem sm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  constexpr int U = 2;
-  ColRing<T, U> ring;
-  ring.init(smem_raw, threadIdx.y * blockDim.x + threadIdx.x, blockDim.x * blockDim.y, sm.nt);
+  constexpr int U = 1;
+  const ColGeom cg = col_geom<T>(smem_raw, U, sm.nt);
   const int c = threadIdx.x * 8, TY = blockDim.y;
   const unsigned P = Tlen + lead + trail;
   const long prows = n_chunks * (long)P;
-  const long p0 = (long)blockIdx.x * prows_per_block;
-  const long p1 = min(prows, p0 + prows_per_block);
   const T* xa = reinterpret_cast<const T*>(a.x);
   const T* xb = reinterpret_cast<const T*>(b.x);
   float ma[8], sa[8], ha[8], mb[8], sb[8], hb[8];        // out = (x - mean) * (invstd * gamma) + beta, per branch
@@ -248,33 +241,33 @@ bn_apply_kernel(BnBranch a, BnBranch b, int has_b, int relu, T* __restrict__ out
       for (int j = 0; j < 8; ++j) sb[j] = is[j] * g[j];
     }
   }
-  auto row_of = [&](long prow, long& row) {              // padded row -> data row; false on a halo row
-    const unsigned chunk = (unsigned)(prow / P);
-    const int t = (int)(prow - (long)chunk * P) - lead;
-    row = (long)chunk * Tlen + t;
+  auto row_of = [&](int prow, int& row) {                // padded row -> data row; false on a halo row
+    const unsigned chunk = (unsigned)prow / P;
+    const int t = (int)((unsigned)prow - chunk * P) - lead;
+    row = (int)chunk * Tlen + t;
     return t >= 0 && t < Tlen;
   };
-  stream_rows<U>((long)blockIdx.x * TY + threadIdx.y, prows, (long)gridDim.x * TY, sm.stages,
-      [&](int sg, int u, long prow, bool valid) {
-        long row = 0;
+  stream_rows<U>((int)blockIdx.x * TY + (int)threadIdx.y, (int)prows, (int)gridDim.x * TY, cg.ring, cg.stage_bytes,
+      [&](uint32_t a0, int u, int prow, bool valid) {
+        int row = 0;
         const bool real = valid && row_of(prow, row);
-        ring.issue(sg, u, 0, real ? xa + row * a.ld + c : xa, real);
-        if (has_b) ring.issue(sg, u, 1, real ? xb + row * b.ld + c : xb, real);
+        ColSlot<T>::issue(cg.slot(a0, u, 0), real ? xa + (long)row * a.ld + c : xa, real);
+        if (has_b) ColSlot<T>::issue(cg.slot(a0, u, 1), real ? xb + (long)row * b.ld + c : xb, real);
       },
-      [&](int sg, int u, long prow) {
-        long row;
+      [&](uint32_t a0, int u, int prow) {
+        int row;
         float o[8];
         if (!row_of(prow, row)) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = 0.f;
         } else {
           float va[8];
-          ring.read(sg, u, 0, va);
+          ColSlot<T>::read(cg.slot(a0, u, 0), va);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = fmaf(va[j] - ma[j], sa[j], ha[j]);
           if (has_b) {
             float vb[8];
-            ring.read(sg, u, 1, vb);
+            ColSlot<T>::read(cg.slot(a0, u, 1), vb);
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] += fmaf(vb[j] - mb[j], sb[j], hb[j]);
           }
@@ -283,7 +276,7 @@ bn_apply_kernel(BnBranch a, BnBranch b, int has_b, int relu, T* __restrict__ out
             for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
           }
         }
-        Vec8<T>::store(out + prow * C + c, o);
+        Vec8<T>::store(out + (long)prow * C + c, o);
       });
 }
 
@@ -333,13 +326,10 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, long ld_dout, const T* __restri
                      double* __restrict__ red, long rows_per_block, ColSmem sm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   double* dbuf = reinterpret_cast<double*>(smem_raw);
-  constexpr int U = 2;
-  ColRing<T, U> ring;
-  ring.init(smem_raw + sm.red_bytes + sm.sgn_bytes, threadIdx.y * blockDim.x + threadIdx.x, blockDim.x * blockDim.y, sm.nt);
+  constexpr int U = 1;
+  const ColGeom cg = col_geom<T>(smem_raw + sm.red_bytes + sm.sgn_bytes, U, sm.nt);
   const int c = threadIdx.x * 8, TY = blockDim.y;
   const long rows = n_chunks * Tlen;
-  const long r0 = (long)blockIdx.x * rows_per_block;
-  const long r1 = min(rows, r0 + rows_per_block);
   const int Py = Tlen + y_lead + y_trail;
   const T* xa = reinterpret_cast<const T*>(a.x);
   const T* xb = reinterpret_cast<const T*>(b.x);
@@ -360,25 +350,25 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, long ld_dout, const T* __restri
   float f0[8], f1[8], f2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { f0[j] = f1[j] = f2[j] = 0.f; }
-  stream_rows<U>((long)blockIdx.x * TY + threadIdx.y, rows, (long)gridDim.x * TY, sm.stages,
-      [&](int sgi, int u, long r, bool valid) {
-        ring.issue(sgi, u, 0, valid ? dout + r * ld_dout + c : dout, valid);
-        ring.issue(sgi, u, 1, valid ? xa + r * a.ld + c : xa, valid);
-        if (has_b) ring.issue(sgi, u, 2, valid ? xb + r * b.ld + c : xb, valid);
+  stream_rows<U>((int)blockIdx.x * TY + (int)threadIdx.y, (int)rows, (int)gridDim.x * TY, cg.ring, cg.stage_bytes,
+      [&](uint32_t a0, int u, int r, bool valid) {
+        ColSlot<T>::issue(cg.slot(a0, u, 0), valid ? dout + (long)r * ld_dout + c : dout, valid);
+        ColSlot<T>::issue(cg.slot(a0, u, 1), valid ? xa + (long)r * a.ld + c : xa, valid);
+        if (has_b) ColSlot<T>::issue(cg.slot(a0, u, 2), valid ? xb + (long)r * b.ld + c : xb, valid);
         if (use_y) {
-          const long chunk = r / Tlen;
-          const long prow = chunk * Py + (r - chunk * Tlen) + y_lead;
-          ring.issue(sgi, u, has_b ? 3 : 2, valid ? y + prow * C + c : y, valid);
+          const int chunk = r / Tlen;
+          const long prow = (long)chunk * Py + (r - chunk * Tlen) + y_lead;
+          ColSlot<T>::issue(cg.slot(a0, u, has_b ? 3 : 2), valid ? y + prow * C + c : y, valid);
         }
       },
-      [&](int sgi, int u, long) {
+      [&](uint32_t a0, int u, int) {
         float g[8], da[8], db[8];
-        ring.read(sgi, u, 0, g);
-        ring.read(sgi, u, 1, da);
+        ColSlot<T>::read(cg.slot(a0, u, 0), g);
+        ColSlot<T>::read(cg.slot(a0, u, 1), da);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { da[j] -= ma[j]; db[j] = 0.f; }
         if (has_b) {
-          ring.read(sgi, u, 2, db);
+          ColSlot<T>::read(cg.slot(a0, u, 2), db);
 #pragma unroll
           for (int j = 0; j < 8; ++j) db[j] -= mb[j];
         }
@@ -386,7 +376,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, long ld_dout, const T* __restri
         if (resign) pos = sg.positive8(c, da, db, has_b);
         else if (use_y) {
           float yv[8];
-          ring.read(sgi, u, has_b ? 3 : 2, yv);
+          ColSlot<T>::read(cg.slot(a0, u, has_b ? 3 : 2), yv);
           pos = 0;
 #pragma unroll
           for (int j = 0; j < 8; ++j) pos |= (yv[j] > 0.f ? 1u : 0u) << j;
@@ -432,9 +422,8 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, long ld_dout, const T* __restric
                     int relu, BnBranch a, BnBranch b, int has_b, BnGradOut ga, BnGradOut gb, long n_chunks,
                     int Tlen, int C, const double* __restrict__ red, long rows_per_block, ColSmem sm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  constexpr int U = 2;
-  ColRing<T, U> ring;
-  ring.init(smem_raw + sm.sgn_bytes, threadIdx.y * blockDim.x + threadIdx.x, blockDim.x * blockDim.y, sm.nt);
+  constexpr int U = 1;
+  const ColGeom cg = col_geom<T>(smem_raw + sm.sgn_bytes, U, sm.nt);
   const int c = threadIdx.x * 8, TY = blockDim.y;
   const long rows = n_chunks * Tlen;
   const double invN = 1.0 / (double)rows;
@@ -479,28 +468,26 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, long ld_dout, const T* __restric
   const int Pa = Tlen + ga.lead + ga.trail, Pb = Tlen + gb.lead + gb.trail;
   T* dxa = reinterpret_cast<T*>(ga.dx);
   T* dxb = reinterpret_cast<T*>(gb.dx);
-  const long r0 = (long)blockIdx.x * rows_per_block;
-  const long r1 = min(rows, r0 + rows_per_block);
-  stream_rows<U>((long)blockIdx.x * TY + threadIdx.y, rows, (long)gridDim.x * TY, sm.stages,
-      [&](int sgi, int u, long r, bool valid) {
-        ring.issue(sgi, u, 0, valid ? dout + r * ld_dout + c : dout, valid);
-        ring.issue(sgi, u, 1, valid ? xa + r * a.ld + c : xa, valid);
-        if (has_b) ring.issue(sgi, u, 2, valid ? xb + r * b.ld + c : xb, valid);
+  stream_rows<U>((int)blockIdx.x * TY + (int)threadIdx.y, (int)rows, (int)gridDim.x * TY, cg.ring, cg.stage_bytes,
+      [&](uint32_t a0, int u, int r, bool valid) {
+        ColSlot<T>::issue(cg.slot(a0, u, 0), valid ? dout + (long)r * ld_dout + c : dout, valid);
+        ColSlot<T>::issue(cg.slot(a0, u, 1), valid ? xa + (long)r * a.ld + c : xa, valid);
+        if (has_b) ColSlot<T>::issue(cg.slot(a0, u, 2), valid ? xb + (long)r * b.ld + c : xb, valid);
         if (use_y) {
-          const long chunk = r / Tlen;
-          ring.issue(sgi, u, has_b ? 3 : 2, valid ? y + (chunk * Py + (r - chunk * Tlen) + y_lead) * C + c : y, valid);
+          const int chunk = r / Tlen;
+          ColSlot<T>::issue(cg.slot(a0, u, has_b ? 3 : 2), valid ? y + ((long)chunk * Py + (r - chunk * Tlen) + y_lead) * C + c : y, valid);
         }
       },
-      [&](int sgi, int u, long r) {
+      [&](uint32_t a0, int u, int r) {
         const long chunk = r / Tlen;
-        const int t = (int)(r - chunk * Tlen);
+        const int t = r - (int)chunk * Tlen;
         float g[8], da[8], db[8];
-        ring.read(sgi, u, 0, g);
-        ring.read(sgi, u, 1, da);
+        ColSlot<T>::read(cg.slot(a0, u, 0), g);
+        ColSlot<T>::read(cg.slot(a0, u, 1), da);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { da[j] -= Mn[0][j]; db[j] = 0.f; }
         if (has_b) {
-          ring.read(sgi, u, 2, db);
+          ColSlot<T>::read(cg.slot(a0, u, 2), db);
 #pragma unroll
           for (int j = 0; j < 8; ++j) db[j] -= Mn[1][j];
         }
@@ -509,7 +496,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, long ld_dout, const T* __restric
           if (resign) pos = sg.positive8(c, da, db, has_b);
           else {
             float yv[8];
-            ring.read(sgi, u, has_b ? 3 : 2, yv);
+            ColSlot<T>::read(cg.slot(a0, u, has_b ? 3 : 2), yv);
             pos = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) pos |= (yv[j] > 0.f ? 1u : 0u) << j;
@@ -545,37 +532,34 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, long ld_dout, const T* __restric
 // hides latency, not occupancy), contiguous row ranges of `rpb` rows per block; as many ring stages (2..4) as fit.
 struct ColLaunch { dim3 block; int grid; long rpb; ColSmem sm; size_t smem; };
 static ColLaunch col_launch(long rows, int tx, size_t red_elem_bytes, size_t sgn_bytes, int U, int nt, size_t elem_bytes,
-                            long max_rpb = 1L << 40) {
-  const size_t per_thread_stage = (size_t)U * nt * 8 * elem_bytes;
+                            long max_rows_per_thread = 1L << 40) {
+  const size_t per_thread = (size_t)COL_STAGES * U * nt * 8 * elem_bytes;        // ring bytes per thread
   int ty = 512 / tx; if (ty < 1) ty = 1; if (ty > 16) ty = 16;
   int blocks_per_sm = 512 / (tx * ty); if (blocks_per_sm < 1) blocks_per_sm = 1; if (blocks_per_sm > 4) blocks_per_sm = 4;
-  const size_t budget = (size_t)216 * 1024 / blocks_per_sm;
-  auto fixed = [&](int ty_) { return (size_t)(ty_ - 1) * tx * 8 * red_elem_bytes + sgn_bytes; };
-  while (ty > 1 && fixed(ty) + 2 * per_thread_stage * tx * ty > budget) --ty;
-  int stages = COL_MAX_STAGES;
-  while (stages > 2 && fixed(ty) + (size_t)stages * per_thread_stage * tx * ty > budget) --stages;
+  const size_t budget = (size_t)224 * 1024 / blocks_per_sm;
+  auto total = [&](int ty_) { return (size_t)(ty_ - 1) * tx * 8 * red_elem_bytes + sgn_bytes + per_thread * tx * ty_; };
+  while (ty > 1 && total(ty) > budget) --ty;
   long nblk = (long)num_sms() * blocks_per_sm;
-  long rpb = (rows + nblk - 1) / nblk;
-  if (rpb > max_rpb) rpb = max_rpb;
-  rpb = (rpb + ty - 1) / ty * ty;
-  nblk = (rows + rpb - 1) / rpb;
+  const long min_blk = (rows + max_rows_per_thread * ty - 1) / (max_rows_per_thread * ty);   // fp32 partials stay short
+  if (nblk < min_blk) nblk = min_blk;
+  const long max_blk = (rows + ty - 1) / ty;
+  if (nblk > max_blk) nblk = max_blk;
   ColLaunch cl;
   cl.block = dim3(tx, ty);
   cl.grid = (int)(nblk > 0 ? nblk : 1);
-  cl.rpb = rpb;
+  cl.rpb = 0;
   cl.sm.red_bytes = (int)((size_t)(ty - 1) * tx * 8 * red_elem_bytes);
   cl.sm.sgn_bytes = (int)sgn_bytes;
-  cl.sm.stages = stages;
   cl.sm.nt = nt;
-  cl.smem = fixed(ty) + (size_t)stages * per_thread_stage * tx * ty;
+  cl.smem = total(ty);
   return cl;
 }
 
 template <typename K>
 static int opt_in_smem(K kernel, size_t bytes) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024));
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
   SST_REQUIRE(e == cudaSuccess, SST_E_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  SST_REQUIRE(bytes <= 224 * 1024, SST_E_ARG, "column kernel needs %zu bytes of shared memory", bytes);
+  SST_REQUIRE(bytes <= 227 * 1024, SST_E_ARG, "column kernel needs %zu bytes of shared memory", bytes);
   return SST_OK;
 }
 
@@ -638,7 +622,7 @@ int sst_bn_apply(int dtype, int64_t n_chunks, int T, int C, const void* xa, int6
   SST_REQUIRE(C / 8 <= 512, SST_E_ARG, "bn_apply: C=%d too wide", C);
   const size_t esz = dtype == SST_F32 ? 4 : 2;
   const int has_b = xb != nullptr;
-  const ColLaunch cl = col_launch(prows, C / 8, 0, 0, 2, 1 + has_b, esz);
+  const ColLaunch cl = col_launch(prows, C / 8, 0, 0, 1, 1 + has_b, esz);
   if (dtype == SST_F32) SST_COL_LAUNCH(bn_apply_kernel, float, a, b, has_b, relu, (float*)out, n_chunks, T, C, lead, trail, cl.rpb, cl.sm);
   else SST_COL_LAUNCH(bn_apply_kernel, __nv_bfloat16, a, b, has_b, relu, (__nv_bfloat16*)out, n_chunks, T, C, lead, trail, cl.rpb, cl.sm);
   return check_launch("bn_apply");
@@ -668,7 +652,7 @@ int sst_bn_bwd(int dtype, int64_t n_chunks, int T, int C, const void* dout, int6
   const size_t sgn_bytes = (relu && y == nullptr) ? (size_t)4 * C * sizeof(float) : 0;
   const int nt = 2 + has_b + ((relu && y != nullptr) ? 1 : 0);      // dout, xa, [xb], [y]
   {
-    const ColLaunch cl = col_launch(rows, C / 8, sizeof(double), sgn_bytes, 2, nt, esz, 2560);   // <= 512 rows per fp32 partial
+    const ColLaunch cl = col_launch(rows, C / 8, sizeof(double), sgn_bytes, 1, nt, esz, 512);    // <= 512 rows per fp32 partial
     if (dtype == SST_F32)
       SST_COL_LAUNCH(bn_bwd_reduce_kernel, float, (const float*)dout, ld_dout, (const float*)y, y_lead, y_trail, relu, a, b, has_b,
                      n_chunks, T, C, red, cl.rpb, cl.sm);
@@ -677,7 +661,7 @@ int sst_bn_bwd(int dtype, int64_t n_chunks, int T, int C, const void* dout, int6
                      relu, a, b, has_b, n_chunks, T, C, red, cl.rpb, cl.sm);
   }
   {
-    const ColLaunch cl = col_launch(rows, C / 8, 0, sgn_bytes, 2, nt, esz);
+    const ColLaunch cl = col_launch(rows, C / 8, 0, sgn_bytes, 1, nt, esz);
     if (dtype == SST_F32)
       SST_COL_LAUNCH(bn_bwd_apply_kernel, float, (const float*)dout, ld_dout, (const float*)y, y_lead, y_trail, relu, a, b, has_b, ga, gb,
                      n_chunks, T, C, red, cl.rpb, cl.sm);
