@@ -9,40 +9,11 @@
 // streams its own 16-byte pieces through shared memory with cp.async (LDGSTS): a ring of S stages of U rows per tensor, so
 // (S-1)*U rows per tensor are in flight per thread whatever the register pressure -- ~100 KB per SM, enough to cover
 // HBM latency at full bandwidth.  A thread only ever reads back what it copied itself, so the ring needs no block barrier.
-#include "vec.cuh"
+#include "colstream.cuh"
 
 namespace sst {
 
-// ---- per-thread cp.async ring ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g, bool valid) {
-  if (valid) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");   // invalid rows are never read back
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 constexpr int COL_STAGES = 8;                          // ring depth: 7 steps in flight per thread
-
-// One 8-element slot: 16 B (bf16) or 32 B (fp32).  Slot (stage, u, t) of a thread lives at
-//   ring + stage * stage_bytes + (u * nt + t) * plane + tid * SLOT,     plane = nthreads * SLOT, stage_bytes = U * nt * plane.
-template <typename T> struct ColSlot {
-  static constexpr int BYTES = (int)sizeof(T) * 8;
-  static __device__ __forceinline__ void issue(uint32_t a, const T* g, bool valid) {
-    cp_async16(a, g, valid);
-    if (BYTES == 32) cp_async16(a + 16, reinterpret_cast<const char*>(g) + 16, valid);
-  }
-  static __device__ __forceinline__ void read(uint32_t a, float (&v)[8]) {
-    if (BYTES == 16) {
-      uint4 w;
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(a));
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
-    } else {
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a + 16));
-    }
-  }
-};
 
 struct ColGeom {
   uint32_t ring, plane, stage_bytes; int nt;
@@ -57,50 +28,6 @@ __device__ __forceinline__ ColGeom col_geom(void* ring_smem, int U, int nt) {
   g.stage_bytes = (uint32_t)(U * nt) * g.plane;
   g.nt = nt;
   return g;
-}
-
-// The loop every kernel below runs: this thread owns rows first + k*stride (k = 0, 1, ...) below `end`, U of them per
-// step.  `issue(slot0, u, row, valid)` queues the copies of one row into the step's slots (slot0 = the thread's slot of
-// (stage, u = 0, t = 0)), `use(slot0, u, row)` consumes a landed, valid row.  All state is a handful of running
-// counters: the loop body is a few instructions beside the kernel's own work.
-template <int U, typename Issue, typename Use>
-__device__ __forceinline__ void stream_rows(int first, int end, int stride, uint32_t ring, uint32_t stage_bytes, Issue&& issue, Use&& use) {
-  constexpr int S = COL_STAGES;
-  const int mine = first < end ? (end - first + stride - 1) / stride : 0;
-  const int nsteps = (mine + U - 1) / U;
-  const int step_rows = U * stride;
-  int rq = first, sq = 0, left = nsteps;
-  uint32_t aq = ring;
-  auto queue = [&]() {
-    if (left > 0) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int r = rq + u * stride;
-        issue(aq, u, r, r < end);
-      }
-      --left;
-    }
-    cp_async_commit();                                  // one group per step, empty ones included: the wait counts groups
-    rq += step_rows;
-    aq += stage_bytes;
-    if (++sq == S) { sq = 0; aq = ring; }
-  };
-#pragma unroll
-  for (int s = 0; s < S - 1; ++s) queue();
-  int ru = first, su = 0;
-  uint32_t au = ring;
-  for (int step = 0; step < nsteps; ++step) {
-    queue();
-    cp_async_wait<S - 1>();
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int r = ru + u * stride;
-      if (r < end) use(au, u, r);
-    }
-    ru += step_rows;
-    au += stage_bytes;
-    if (++su == S) { su = 0; au = ring; }
-  }
 }
 
 // v[j] (ty == 0) += sum over ty > 0 of v[j];  buf: (blockDim.y - 1) * 8 * blockDim.x elements
@@ -137,7 +64,7 @@ colstats_kernel(const T* __restrict__ x, long rows, int C, long ld, double* __re
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.0; q[j] = 0.0; fs[j] = 0.f; fq[j] = 0.f; }
   int pending = 0;
-  stream_rows<U>((int)blockIdx.x * TY + (int)threadIdx.y, (int)rows, (int)gridDim.x * TY, cg.ring, cg.stage_bytes,
+  stream_rows<U, COL_STAGES>((int)blockIdx.x * TY + (int)threadIdx.y, (int)rows, (int)gridDim.x * TY, cg.ring, cg.stage_bytes,
       [&](uint32_t a0, int u, int r, bool valid) { ColSlot<T>::issue(cg.slot(a0, u, 0), valid ? x + (long)r * ld + c : x, valid); },
       [&](uint32_t a0, int u, int) {
         float v[8];
@@ -172,7 +99,7 @@ colsum_kernel(const T* __restrict__ x, long rows, int C, long ld, float* __restr
   float s[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = 0.f;
-  stream_rows<U>((int)blockIdx.x * TY + (int)threadIdx.y, (int)rows, (int)gridDim.x * TY, cg.ring, cg.stage_bytes,
+  stream_rows<U, COL_STAGES>((int)blockIdx.x * TY + (int)threadIdx.y, (int)rows, (int)gridDim.x * TY, cg.ring, cg.stage_bytes,
       [&](uint32_t a0, int u, int r, bool valid) { ColSlot<T>::issue(cg.slot(a0, u, 0), valid ? x + (long)r * ld + c : x, valid); },
       [&](uint32_t a0, int u, int) {
         float v[8];
@@ -247,7 +174,7 @@ bn_apply_kernel(BnBranch a, BnBranch b, int has_b, int relu, T* __restrict__ out
     row = (int)chunk * Tlen + t;
     return t >= 0 && t < Tlen;
   };
-  stream_rows<U>((int)blockIdx.x * TY + (int)threadIdx.y, (int)prows, (int)gridDim.x * TY, cg.ring, cg.stage_bytes,
+  stream_rows<U, COL_STAGES>((int)blockIdx.x * TY + (int)threadIdx.y, (int)prows, (int)gridDim.x * TY, cg.ring, cg.stage_bytes,
       [&](uint32_t a0, int u, int prow, bool valid) {
         int row = 0;
         const bool real = valid && row_of(prow, row);
@@ -350,7 +277,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, long ld_dout, const T* __restri
   float f0[8], f1[8], f2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { f0[j] = f1[j] = f2[j] = 0.f; }
-  stream_rows<U>((int)blockIdx.x * TY + (int)threadIdx.y, (int)rows, (int)gridDim.x * TY, cg.ring, cg.stage_bytes,
+  stream_rows<U, COL_STAGES>((int)blockIdx.x * TY + (int)threadIdx.y, (int)rows, (int)gridDim.x * TY, cg.ring, cg.stage_bytes,
       [&](uint32_t a0, int u, int r, bool valid) {
         ColSlot<T>::issue(cg.slot(a0, u, 0), valid ? dout + (long)r * ld_dout + c : dout, valid);
         ColSlot<T>::issue(cg.slot(a0, u, 1), valid ? xa + (long)r * a.ld + c : xa, valid);
@@ -468,7 +395,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, long ld_dout, const T* __restric
   const int Pa = Tlen + ga.lead + ga.trail, Pb = Tlen + gb.lead + gb.trail;
   T* dxa = reinterpret_cast<T*>(ga.dx);
   T* dxb = reinterpret_cast<T*>(gb.dx);
-  stream_rows<U>((int)blockIdx.x * TY + (int)threadIdx.y, (int)rows, (int)gridDim.x * TY, cg.ring, cg.stage_bytes,
+  stream_rows<U, COL_STAGES>((int)blockIdx.x * TY + (int)threadIdx.y, (int)rows, (int)gridDim.x * TY, cg.ring, cg.stage_bytes,
       [&](uint32_t a0, int u, int r, bool valid) {
         ColSlot<T>::issue(cg.slot(a0, u, 0), valid ? dout + (long)r * ld_dout + c : dout, valid);
         ColSlot<T>::issue(cg.slot(a0, u, 1), valid ? xa + (long)r * a.ld + c : xa, valid);

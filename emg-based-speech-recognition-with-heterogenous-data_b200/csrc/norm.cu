@@ -1,11 +1,21 @@
 // Bandwidth-bound normalisation kernels (128-bit vectorised HBM access, fp32 statistics):
 //   LayerNorm(x + dropout(r)) forward / backward      -- transformer.py:59-63, :124-133 (post-LN, eps 1e-5)
 // (the per-channel BatchNorm / column-sum kernels live in colnorm.cu)
-#include "vec.cuh"
+#include "colstream.cuh"
 
 namespace sst {
 
 constexpr int LN_MAXV = 8;   // up to 8 vectors of 8 per lane -> D <= 2048
+// cp.async ring (colstream.cuh).  D = 768 (EXACT): 4 stages = three rows per warp in flight, two 256-thread blocks per SM;
+// the generic variant (up to 8 vectors per lane) runs 2 stages in 128-thread blocks so that its ring still fits.
+template <bool EXACT> struct LnCfg { static constexpr int STAGES = EXACT ? 4 : 2; static constexpr int THREADS = EXACT ? 256 : 128; };
+
+// this lane's slot of (stage 0, tensor 0, vector 0); slot (t, i) of a stage sits (t * NV + i) planes further
+template <typename T>
+__device__ __forceinline__ uint32_t ln_ring(void* smem, uint32_t& plane) {
+  plane = blockDim.x * ColSlot<T>::BYTES;
+  return (uint32_t)__cvta_generic_to_shared(smem) + threadIdx.x * ColSlot<T>::BYTES;
+}
 
 // 8 dropout keep decisions for elements idx .. idx+7 (idx % 8 == 0): ONE Philox block, eight 16-bit lanes
 // (sst_common.cuh philox_keep16 -- the same stream the host mirror in tests/helpers.py draws)
@@ -23,9 +33,13 @@ __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ r, T* __restrict__ y, T* __restrict__ s_out,
               const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ mean_out,
               float* __restrict__ rstd_out, long rows, int D, float eps, uint32_t thr, float dscale, unsigned long long seed) {
+  extern __shared__ __align__(16) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31;
-  const long warp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+  const int warp = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  const int nwarps = (int)(gridDim.x * (blockDim.x >> 5));
+  const int NT = r != nullptr ? 2 : 1;
+  uint32_t plane;
+  const uint32_t ring = ln_ring<T>(ln_smem, plane);
   float g[NV][8], b[NV][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -33,14 +47,25 @@ ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ r, T* __restrict__ 
     if (EXACT || c < D) { load8_f32(gamma + c, g[i]); load8_f32(beta + c, b[i]); }
   }
   const float invD = 1.f / D;
-  for (long row = warp; row < rows; row += nwarps) {
+  stream_rows<1, LnCfg<EXACT>::STAGES>(warp, (int)rows, nwarps, ring, (uint32_t)(NT * NV) * plane,
+      [&](uint32_t a0, int, int row, bool valid) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = (i * 32 + lane) * 8;
+          if (EXACT || c < D) {
+            ColSlot<T>::issue(a0 + i * plane, x + (long)row * D + c, valid);
+            if (r != nullptr) ColSlot<T>::issue(a0 + (NV + i) * plane, r + (long)row * D + c, valid);
+          }
+        }
+      },
+      [&](uint32_t a0, int, int row) {
     float v[NV][8], rv[NV][8];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 8;
       if (EXACT || c < D) {
-        Vec8<T>::load(x + row * D + c, v[i]);
-        if (r != nullptr) Vec8<T>::load(r + row * D + c, rv[i]);
+        ColSlot<T>::read(a0 + i * plane, v[i]);
+        if (r != nullptr) ColSlot<T>::read(a0 + (NV + i) * plane, rv[i]);
       }
     }
     float sum = 0.f;
@@ -60,7 +85,7 @@ ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ r, T* __restrict__ 
         }
         if (s_out != nullptr) {
           // the saved pre-norm sum is what backward normalises: round it to T first so both see one value
-          Vec8<T>::store(s_out + row * D + c, v[i]);
+          Vec8<T>::store(s_out + (long)row * D + c, v[i]);
           if (sizeof(T) == 2) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[i][j] = __bfloat162float(__float2bfloat16_rn(v[i][j]));
@@ -89,10 +114,10 @@ ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ r, T* __restrict__ 
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[i][j] + b[i][j];
-        Vec8<T>::store(y + row * D + c, o);
+        Vec8<T>::store(y + (long)row * D + c, o);
       }
     }
-  }
+      });
 }
 
 // ds = rstd * (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat));  dr = ds * keep/(1-p);
@@ -103,10 +128,13 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ s, const float* __
               const float* __restrict__ rstd_in, const float* __restrict__ gamma, T* __restrict__ ds, T* __restrict__ dr,
               float* __restrict__ dgamma, float* __restrict__ dbeta, long rows, int D, uint32_t thr, float dscale,
               unsigned long long seed) {
-  extern __shared__ float red[];   // [2][D]
+  extern __shared__ __align__(16) uint8_t ln_smem[];   // [2][D] floats of column partials, then the ring
+  float* red = reinterpret_cast<float*>(ln_smem);
   const int lane = threadIdx.x & 31;
-  const long warp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+  const int warp = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  const int nwarps = (int)(gridDim.x * (blockDim.x >> 5));
+  uint32_t plane;
+  const uint32_t ring = ln_ring<T>(ln_smem + (size_t)2 * D * sizeof(float), plane);
   for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   float ag[NV][8], ab[NV][8], gm[NV][8];
@@ -118,13 +146,24 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ s, const float* __
     for (int j = 0; j < 8; ++j) { ag[i][j] = 0.f; ab[i][j] = 0.f; }
   }
   const float invD = 1.f / D;
-  for (long row = warp; row < rows; row += nwarps) {
+  stream_rows<1, LnCfg<EXACT>::STAGES>(warp, (int)rows, nwarps, ring, (uint32_t)(2 * NV) * plane,
+      [&](uint32_t a0, int, int row, bool valid) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = (i * 32 + lane) * 8;
+          if (EXACT || c < D) {
+            ColSlot<T>::issue(a0 + i * plane, dy + (long)row * D + c, valid);
+            ColSlot<T>::issue(a0 + (NV + i) * plane, s + (long)row * D + c, valid);
+          }
+        }
+      },
+      [&](uint32_t a0, int, int row) {
     const float mean = mean_in[row], rstd = rstd_in[row];
     float xh[NV][8], g[NV][8];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 8;
-      if (EXACT || c < D) { Vec8<T>::load(dy + row * D + c, g[i]); Vec8<T>::load(s + row * D + c, xh[i]); }
+      if (EXACT || c < D) { ColSlot<T>::read(a0 + i * plane, g[i]); ColSlot<T>::read(a0 + (NV + i) * plane, xh[i]); }
     }
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
@@ -151,17 +190,17 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ s, const float* __
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - c1 - xh[i][j] * c2);
-        Vec8<T>::store(ds + row * D + c, o);
+        Vec8<T>::store(ds + (long)row * D + c, o);
         if (dr != nullptr) {
           bool k[8];
           keep8_16(seed, (unsigned long long)row * D + c, thr, k);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = k[j] ? o[j] * dscale : 0.f;
-          Vec8<T>::store(dr + row * D + c, o);
+          Vec8<T>::store(dr + (long)row * D + c, o);
         }
       }
     }
-  }
+      });
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 8;
@@ -203,12 +242,25 @@ int sst_layernorm_fwd(int dtype, int64_t rows, int D, const void* x, const void*
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const uint32_t thr = (r != nullptr && drop_p > 0.f) ? drop_threshold16(drop_p) : 0u;
   const float dscale = drop_p < 1.f ? 1.f / (1.f - drop_p) : 0.f;
+  SST_REQUIRE(rows < (1L << 31), SST_E_ARG, "layernorm: too many rows");
   long blocks = (rows + 7) / 8;
-  const long cap = (long)num_sms() * 8;
+  const long cap = (long)num_sms() * 2;
   const int grid = (int)(blocks < cap ? blocks : cap);
+  // ring: LN_STAGES x (x [+ r]) x NV vectors x 256 threads
 #define SST_LN_FWD(T_, NV_, EX_)                                                                                             \
-  ln_fwd_kernel<T_, NV_, EX_><<<grid, 256, 0, st>>>((const T_*)x, (const T_*)r, (T_*)y, (T_*)s_out, gamma, beta, mean, rstd, rows, D, \
-                                                    eps, thr, dscale, seed)
+  do {                                                                                                                       \
+    constexpr int TH = LnCfg<EX_>::THREADS;                                                                                  \
+    const size_t smem = (size_t)LnCfg<EX_>::STAGES * (r != nullptr ? 2 : 1) * NV_ * TH * ColSlot<T_>::BYTES;                   \
+    static bool attr = false;                                                                                                \
+    if (!attr) {                                                                                                             \
+      cudaError_t e = cudaFuncSetAttribute(ln_fwd_kernel<T_, NV_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+      SST_REQUIRE(e == cudaSuccess, SST_E_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));                          \
+      attr = true;                                                                                                           \
+    }                                                                                                                        \
+    SST_REQUIRE(smem <= 227 * 1024, SST_E_ARG, "layernorm: D=%d needs %zu bytes of shared memory", D, smem);                  \
+    ln_fwd_kernel<T_, NV_, EX_><<<grid, TH, smem, st>>>((const T_*)x, (const T_*)r, (T_*)y, (T_*)s_out, gamma, beta, mean, rstd, rows, \
+                                                         D, eps, thr, dscale, seed);                                         \
+  } while (0)
   if (dtype == SST_F32) { if (D == 768) SST_LN_FWD(float, 3, true); else SST_LN_FWD(float, LN_MAXV, false); }
   else { if (D == 768) SST_LN_FWD(__nv_bfloat16, 3, true); else SST_LN_FWD(__nv_bfloat16, LN_MAXV, false); }
 #undef SST_LN_FWD
@@ -228,10 +280,21 @@ int sst_layernorm_bwd(int dtype, int64_t rows, int D, const void* dy, const void
   long blocks = (rows + 63) / 64;
   long cap = (long)num_sms() * 2;
   const int grid = (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
-  const size_t smem = (size_t)2 * D * sizeof(float);
+  SST_REQUIRE(rows < (1L << 31), SST_E_ARG, "layernorm: too many rows");
 #define SST_LN_BWD(T_, NV_, EX_)                                                                                             \
-  ln_bwd_kernel<T_, NV_, EX_><<<grid, 256, smem, st>>>((const T_*)dy, (const T_*)s, mean, rstd, gamma, (T_*)ds, (T_*)dr, dgamma, dbeta, \
-                                                       rows, D, thr, dscale, seed)
+  do {                                                                                                                       \
+    constexpr int TH = LnCfg<EX_>::THREADS;                                                                                  \
+    const size_t smem = (size_t)2 * D * sizeof(float) + (size_t)LnCfg<EX_>::STAGES * 2 * NV_ * TH * ColSlot<T_>::BYTES;        \
+    static bool attr = false;                                                                                                \
+    if (!attr) {                                                                                                             \
+      cudaError_t e = cudaFuncSetAttribute(ln_bwd_kernel<T_, NV_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+      SST_REQUIRE(e == cudaSuccess, SST_E_LAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));                          \
+      attr = true;                                                                                                           \
+    }                                                                                                                        \
+    SST_REQUIRE(smem <= 227 * 1024, SST_E_ARG, "layernorm: D=%d needs %zu bytes of shared memory", D, smem);                  \
+    ln_bwd_kernel<T_, NV_, EX_><<<grid, TH, smem, st>>>((const T_*)dy, (const T_*)s, mean, rstd, gamma, (T_*)ds, (T_*)dr, dgamma,   \
+                                                         dbeta, rows, D, thr, dscale, seed);                                 \
+  } while (0)
   if (dtype == SST_F32) { if (D == 768) SST_LN_BWD(float, 3, true); else SST_LN_BWD(float, LN_MAXV, false); }
   else { if (D == 768) SST_LN_BWD(__nv_bfloat16, 3, true); else SST_LN_BWD(__nv_bfloat16, LN_MAXV, false); }
 #undef SST_LN_BWD

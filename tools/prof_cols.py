@@ -53,3 +53,13 @@ timeit("bn_bwd 2br recomputed mask", lambda: L.bn_bwd(L.BF16, n, T, C, dout, C, 
                                                       xb, C, mean, invstd, gam, dxb, C, 0, 1, dg2, db2, red, beta_a=bet, beta_b=bet), 8 * E)
 timeit("bn_bwd 1br recomputed mask", lambda: L.bn_bwd(L.BF16, n, T, C, dout, C, None, 1, 1, True, xa, C, mean, invstd, gam, dxa, C, 1, 1, dg, db,
                                                       None, 0, None, None, None, None, 0, 0, 0, None, None, red, beta_a=bet), 5 * E)
+
+# LayerNorm(x + dropout(r)) forward / backward at the encoder token count
+R = 64000
+x = torch.randn(R, C, device=dev, generator=g).to(bf); r = torch.randn(R, C, device=dev, generator=g).to(bf)
+yl = torch.empty_like(x); sl = torch.empty_like(x); mu = torch.empty(R, device=dev); rs = torch.empty(R, device=dev)
+dsl = torch.empty_like(x); drl = torch.empty_like(x)
+EL = R * C * 2
+timeit("layernorm_fwd 64000x768 p0.2", lambda: L.layernorm_fwd(L.BF16, R, C, x, r, 0.2, 5, gam, bet, yl, sl, mu, rs), 4 * EL)
+timeit("layernorm_bwd 64000x768 p0.2", lambda: L.layernorm_bwd(L.BF16, R, C, x, sl, mu, rs, gam, dsl, drl, 0.2, 5, dg, db), 4 * EL)
+timeit("layernorm_bwd 64000x768 p0", lambda: L.layernorm_bwd(L.BF16, R, C, x, sl, mu, rs, gam, dsl, None, 0.0, 5, dg, db), 3 * EL)
