@@ -189,6 +189,64 @@ permute3_tiled_kernel(const TI* __restrict__ in, TO* __restrict__ out, long d1, 
   }
 }
 
+// ---- batched form: one launch walks a table of permutes (the whole weight repack of an optimizer step) -------------
+// Block b belongs to the item whose [first_block, first_block + nblocks) contains it (binary search over <= a few hundred
+// items).  mode 0: flat grid-stride over the item's elements with its own blocks; 1 / 2: the 32 x 32 tiled transposes
+// (input contiguous along j / along k), block -> (a, j tile, k tile).
+__device__ __forceinline__ float ld_any(const void* p, long i, int dtype) { return ld_as_f32(p, i, dtype); }
+__device__ __forceinline__ void st_any(void* p, long i, int dtype, float v) { st_from_f32(p, i, dtype, v); }
+
+__global__ void __launch_bounds__(256)
+permute3_batch_kernel(const SstPermuteItem* __restrict__ items, int n_items) {
+  __shared__ float tile[32][33];
+  __shared__ int s_item;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n_items - 1;
+    const int b = (int)blockIdx.x;
+    while (lo < hi) {                                       // last item with first_block <= b
+      const int mid = (lo + hi + 1) >> 1;
+      if (items[mid].first_block <= b) lo = mid; else hi = mid - 1;
+    }
+    s_item = lo;
+  }
+  __syncthreads();
+  const SstPermuteItem it = items[s_item];
+  const int lb = (int)blockIdx.x - it.first_block;
+  if (it.mode == 0) {
+    const long total = it.d0 * it.d1 * it.d2;
+    for (long i = (long)lb * 256 + threadIdx.x; i < total; i += (long)it.nblocks * 256) {
+      const long k = i % it.d2, j = (i / it.d2) % it.d1, a = i / (it.d2 * it.d1);
+      const long oi = a * it.o0 + j * it.o1 + k * it.o2;
+      float v = ld_any(it.in, a * it.s0 + j * it.s1 + k * it.s2, it.in_dtype);
+      if (it.accumulate) v += ld_any(it.out, oi, it.out_dtype);
+      st_any(it.out, oi, it.out_dtype, v);
+    }
+    return;
+  }
+  const bool in_j = it.mode == 1;
+  const int bx = (int)((it.d2 + 31) / 32), by = (int)((it.d1 + 31) / 32);
+  const long a = lb / (bx * by);
+  const int rem = lb - (int)a * bx * by;
+  const long j0 = (long)(rem / bx) * 32, k0 = (long)(rem % bx) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const long j = in_j ? j0 + tx : j0 + r, k = in_j ? k0 + r : k0 + tx;
+    if (j < it.d1 && k < it.d2) tile[in_j ? r : tx][in_j ? tx : r] = ld_any(it.in, a * it.s0 + j * it.s1 + k * it.s2, it.in_dtype);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const long j = in_j ? j0 + r : j0 + tx, k = in_j ? k0 + tx : k0 + r;
+    if (j < it.d1 && k < it.d2) {
+      const long oi = a * it.o0 + j * it.o1 + k * it.o2;
+      float v = tile[in_j ? tx : r][in_j ? r : tx];
+      if (it.accumulate) v += ld_any(it.out, oi, it.out_dtype);
+      st_any(it.out, oi, it.out_dtype, v);
+    }
+  }
+}
+
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
                              float lr, float beta1, float beta2, float eps, float wd, float bc1, float sqrt_bc2,
                              __nv_bfloat16* __restrict__ p_bf16) {
@@ -331,6 +389,36 @@ int sst_permute3_cast(int in_dtype, int out_dtype, const void* in, void* out, in
   else if (out_dtype == SST_F32) permute3_cast_kernel<bf, float><<<grid, 256, 0, st>>>((const bf*)in, (float*)out, d0, d1, d2, s0, s1, s2, o0, o1, o2, accumulate);
   else permute3_cast_kernel<bf, bf><<<grid, 256, 0, st>>>((const bf*)in, (bf*)out, d0, d1, d2, s0, s1, s2, o0, o1, o2, accumulate);
   return check_launch("permute3_cast");
+}
+
+int sst_permute3_plan(SstPermuteItem* items, int n_items, int* total_blocks) {
+  SST_REQUIRE(items != nullptr && total_blocks != nullptr && n_items > 0, SST_E_ARG, "permute3_plan: empty table");
+  long nb = 0;
+  for (int i = 0; i < n_items; ++i) {
+    SstPermuteItem& it = items[i];
+    const long total = it.d0 * it.d1 * it.d2;
+    SST_REQUIRE(total > 0, SST_E_ARG, "permute3_plan: item %d is empty", i);
+    const bool in_j = (it.s1 == 1 && it.o2 == 1 && it.s2 != 1), in_k = (it.s2 == 1 && it.o1 == 1 && it.o2 != 1);
+    it.first_block = (int)nb;
+    if ((in_j || in_k) && it.d1 >= 32 && it.d2 >= 32) {
+      it.mode = in_j ? 1 : 2;
+      it.nblocks = (int)(((it.d2 + 31) / 32) * ((it.d1 + 31) / 32) * it.d0);
+    } else {
+      it.mode = 0;
+      long b = (total + 2047) / 2048;                        // eight elements per thread
+      it.nblocks = (int)(b < 1 ? 1 : (b > 4096 ? 4096 : b));
+    }
+    nb += it.nblocks;
+    SST_REQUIRE(nb < (1L << 31), SST_E_ARG, "permute3_plan: too many blocks");
+  }
+  *total_blocks = (int)nb;
+  return SST_OK;
+}
+
+int sst_permute3_cast_batch(const SstPermuteItem* items_dev, int n_items, int total_blocks, void* stream) {
+  if (n_items <= 0 || total_blocks <= 0) return SST_OK;
+  permute3_batch_kernel<<<total_blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(items_dev, n_items);
+  return check_launch("permute3_cast_batch");
 }
 
 int sst_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, float wd,

@@ -342,7 +342,96 @@ def embed_bwd(dtype, y, dout, dW, B, S, D, pad_idx, drop_p, seed):
           "sst_embed_bwd")
 
 
+class PermuteItem(C.Structure):
+    _fields_ = [("inp", C.c_void_p), ("out", C.c_void_p),
+                ("d0", C.c_int64), ("d1", C.c_int64), ("d2", C.c_int64), ("s0", C.c_int64), ("s1", C.c_int64), ("s2", C.c_int64),
+                ("o0", C.c_int64), ("o1", C.c_int64), ("o2", C.c_int64),
+                ("in_dtype", C.c_int32), ("out_dtype", C.c_int32), ("accumulate", C.c_int32),
+                ("mode", C.c_int32), ("first_block", C.c_int32), ("nblocks", C.c_int32)]
+
+
+_permute_log = None          # list while a PermutePlan is recording
+
+
+class PermutePlan:
+    """Records every permute3_cast issued inside `with plan.record():` (they still run) and replays them as ONE launch
+    (sst_permute3_cast_batch) while the tensors they touched keep their addresses."""
+
+    def __init__(self):
+        self.calls, self.table, self.n, self.blocks, self.hazard = [], None, 0, 0, None
+
+    def record(self):
+        plan = self
+
+        class _Rec:
+            def __enter__(self_):
+                global _permute_log
+                plan.calls = []
+                _permute_log = plan.calls
+
+            def __exit__(self_, *exc):
+                global _permute_log
+                _permute_log = None
+                if exc[0] is None:
+                    plan._finish()
+        return _Rec()
+
+    def _finish(self):
+        n = len(self.calls)
+        arr = (PermuteItem * max(n, 1))()
+        for i, (inp, out, dims, si, so, acc) in enumerate(self.calls):
+            it = arr[i]
+            it.inp, it.out = inp.data_ptr(), out.data_ptr()
+            it.d0, it.d1, it.d2 = dims
+            it.s0, it.s1, it.s2 = si
+            it.o0, it.o1, it.o2 = so
+            it.in_dtype, it.out_dtype, it.accumulate = dt(inp), dt(out), int(acc)
+        self.n = n
+        if n == 0:
+            return
+        # one launch has no ordering between its items: a table in which one item reads (or accumulates into) what another
+        # writes cannot be replayed -- leave it unplanned (valid() stays False and the caller keeps issuing single launches)
+        def region(t, dims, strides):
+            st = [abs(x) for d, x in zip(dims, strides) if d > 1]
+            dm = [d for d in dims if d > 1]
+            ext = 1 + sum((d - 1) * x for d, x in zip(dm, st))
+            es = t.element_size()
+            pitch = max(st) if st else 1                                       # row pitch of a column-sliced matrix view
+            inner = 1 + sum((d - 1) * x for d, x in zip(dm, st) if x != pitch)  # elements a "row" of the view spans
+            return t.data_ptr(), t.data_ptr() + ext * es, pitch * es, inner * es
+
+        def disjoint(r1, r2):
+            if r1[1] <= r2[0] or r2[1] <= r1[0]:
+                return True
+            # same row pitch, each view narrower than a row, column windows apart: interleaved slices of one matrix
+            if r1[2] == r2[2] and r1[3] <= r1[2] and r2[3] <= r2[2]:
+                a0, b0 = r1[0] % r1[2], r2[0] % r2[2]
+                return a0 + r1[3] <= b0 or b0 + r2[3] <= a0
+            return False
+        ins = [region(c[0], c[2], c[3]) for c in self.calls]
+        outs = [region(c[1], c[2], c[4]) for c in self.calls]
+        for i in range(n):
+            for j in range(n):
+                if j != i and not (disjoint(ins[i], outs[j]) and (j < i or disjoint(outs[i], outs[j]))):
+                    self.hazard = (i, j)
+                    return
+        nb = C.c_int(0)
+        check(lib().sst_permute3_plan(arr, n, C.byref(nb)), "sst_permute3_plan")
+        self.blocks = nb.value
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self.table = host.to(self.calls[0][0].device)
+        self.ptrs = [(c[0], c[0].data_ptr(), c[1], c[1].data_ptr()) for c in self.calls]
+
+    def valid(self):
+        return self.table is not None and all(a.data_ptr() == pa and b.data_ptr() == pb for a, pa, b, pb in self.ptrs)
+
+    def replay(self):
+        check(lib().sst_permute3_cast_batch(ptr(self.table), self.n, self.blocks, stream()), "sst_permute3_cast_batch")
+
+
 def permute3_cast(inp, out, dims, in_strides, out_strides, accumulate=False):
+    if _permute_log is not None:
+        _permute_log.append((inp, out, tuple(dims), tuple(in_strides), tuple(out_strides), accumulate))
     check(lib().sst_permute3_cast(dt(inp), dt(out), ptr(inp), ptr(out), _i64(dims[0]), _i64(dims[1]), _i64(dims[2]),
                                   _i64(in_strides[0]), _i64(in_strides[1]), _i64(in_strides[2]),
                                   _i64(out_strides[0]), _i64(out_strides[1]), _i64(out_strides[2]), int(accumulate), stream()),

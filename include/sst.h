@@ -207,6 +207,10 @@ int sst_ce_sumexp_loss(int logits_dtype, int grad_dtype, int64_t rows, int S, in
  *  sst_embed_posenc_fwd : embedding_tgt(y) + pe[b]/D, dropout                             (architecture.py:126-127, Q10)
  *  sst_embed_bwd        : dW[y] += dout, skipping padding_idx rows (fp32 atomics)
  *  sst_permute3_cast    : out[i*o0+j*o1+k*o2] (+)= in[i*s0+j*s1+k*s2] with dtype conversion (weight packing / grad unpacking)
+ *  sst_permute3_plan / sst_permute3_cast_batch : the same for a whole TABLE of permutes in one launch (the weight repack
+ *                         after an optimizer step is ~230 of them).  The host fills in, out, dims, strides, dtypes and accumulate of
+ *                         every item, sst_permute3_plan (host-only, no GPU work) assigns mode/first_block/nblocks and the
+ *                         grid size, the table is copied to the device once and replayed while the pointers stay valid
  *  sst_adamw            : torch.optim.AdamW step over a flat fp32 buffer, `step` 1-based  (recognition_model.py:293);
  *                         p_bf16 (nullable): same-shape bf16 buffer that receives the updated parameters (the GEMM operands)
  * ---------------------------------------------------------------------------------------------------------- */
@@ -222,6 +226,14 @@ int sst_embed_bwd(int dtype, const int64_t* y, const void* dout, float* dW, int 
                   uint64_t seed, void* stream);
 int sst_permute3_cast(int in_dtype, int out_dtype, const void* in, void* out, int64_t d0, int64_t d1, int64_t d2, int64_t s0,
                       int64_t s1, int64_t s2, int64_t o0, int64_t o1, int64_t o2, int accumulate, void* stream);
+typedef struct SstPermuteItem {
+  const void* in; void* out;
+  int64_t d0, d1, d2, s0, s1, s2, o0, o1, o2;
+  int32_t in_dtype, out_dtype, accumulate;
+  int32_t mode, first_block, nblocks;          /* filled by sst_permute3_plan */
+} SstPermuteItem;
+int sst_permute3_plan(SstPermuteItem* items_host, int n_items, int* total_blocks);
+int sst_permute3_cast_batch(const SstPermuteItem* items_dev, int n_items, int total_blocks, void* stream);
 int sst_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, float wd,
               int64_t step, void* p_bf16, void* stream);
 

@@ -377,3 +377,46 @@ def test_first_resblock_conv_as_gemm(L, dtype):
     rr = F.conv1d(xr, wr.to(dtype).float(), br, stride=2).transpose(1, 2).reshape(-1, C)
     assert rel(out[:, :C].float(), r1) < TOL[dtype]
     assert rel(out[:, C:].float(), rr) < TOL[dtype]
+
+
+def test_permute3_batch_replays_recorded_permutes(L):
+    """sst_permute3_cast_batch: a recorded table of permutes (flat, both tiled-transpose modes, casts, accumulate) replayed in
+    one launch gives bit-identical results to the individual launches."""
+    g = torch.Generator(device=DEV).manual_seed(11)
+    w = torch.randn(8, 768, 96, device=DEV, generator=g)                       # (H, D, dh) head weights
+    a2 = torch.randn(300, 200, device=DEV, generator=g).to(torch.bfloat16)
+    small = torch.randn(5, 7, 3, device=DEV, generator=g)
+    acc_src = torch.randn(64, 96, device=DEV, generator=g)
+
+    def run(outs):
+        W, WT, A2T, S, ACC = outs
+        L.permute3_cast(w, W, (8, 96, 768), (768 * 96, 1, 96), (96 * 768, 768, 1))                # tiled, input contiguous along j
+        L.permute3_cast(w, WT, (8, 768, 96), (768 * 96, 96, 1), (96, 768, 1))                     # per-head transpose, 96-element runs
+        L.permute3_cast(a2, A2T, (1, 200, 300), (0, 1, 200), (0, 300, 1))                         # ragged tile edges, bf16 -> fp32
+        L.permute3_cast(small, S, (5, 3, 7), (21, 1, 3), (21, 7, 1))                              # flat path
+        L.permute3_cast(acc_src, ACC, (1, 96, 64), (0, 1, 96), (0, 64, 1), accumulate=True)       # += into existing values
+
+    def fresh():
+        return (torch.empty(768, 768, device=DEV, dtype=torch.bfloat16), torch.empty(768, 768, device=DEV, dtype=torch.bfloat16),
+                torch.empty(200, 300, device=DEV), torch.empty(5, 3, 7, device=DEV), torch.full((96, 64), 2.0, device=DEV))
+    ref = fresh()
+    run(ref)
+    outs = fresh()
+    plan = L.PermutePlan()
+    with plan.record():
+        run(outs)
+    for o in outs[:4]:
+        o.fill_(7)
+    outs[4].fill_(2.0)
+    assert plan.valid() and plan.n == 5
+    plan.replay()
+    torch.cuda.synchronize()
+    for o, r in zip(outs, ref):
+        assert torch.equal(o, r)
+    # a table in which one permute reads what another writes has no defined order inside one launch: it must not be planned
+    chained = L.PermutePlan()
+    with chained.record():
+        L.permute3_cast(w, outs[0], (8, 96, 768), (768 * 96, 1, 96), (96 * 768, 768, 1))
+        L.permute3_cast(outs[0], outs[1], (1, 768, 768), (0, 1, 768), (0, 768, 1))
+    assert chained.hazard == (0, 1) or chained.hazard == (1, 0)
+    assert not chained.valid()
