@@ -17,6 +17,10 @@
 // Pipeline: K/E/V tiles are double-buffered in shared memory; the compute warps release the S/PB accumulators as soon
 // as they have copied their slices to registers ("s_free"), so the issuer runs tile t+1's S/PB MMAs under tile t's
 // exp / dropout / P-store work; P(t) and the O rescale are handed back through "p_ready", PV(t) completion through "pv".
+// Persistent: one CTA per SM walks (batch, head, query tile) items.  All barrier phases and shared-memory stages are indexed
+// by the CTA's running tile counter, so the issuer starts the NEXT item's Q / K / E / V loads and its first S / PB MMAs while
+// the compute warps are still in the current item's last softmax and epilogue -- the ~2 us of TMA + MMA latency at the head
+// of every item (a quarter of the time of a 5-6 tile item) is no longer exposed.
 // Backward = two kernels of the same shape (dQ per query tile; dK/dV per key tile), see attention_tc_bwd.cu.
 #include "attention_tc.cuh"
 
@@ -48,10 +52,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* bar_q = bars, *bar_ke = bars + 1 /* [2] */, *bar_v = bars + 3 /* [2] */, *bar_s = bars + 5, *bar_sfree = bars + 6,
            *bar_p = bars + 7, *bar_pv = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-  float* sred = reinterpret_cast<float*>(bars + 10);         // [2][NSPLIT][128] row-statistic exchange between column groups
-
+  float* sred = reinterpret_cast<float*>(bars + 10);         // [3][NSPLIT][128] row-statistic exchange between column groups
+                                                              // (two alternate per tile, the third is the epilogue's)
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
+  const int nQT = (p.Lq + BM - 1) / BM;
+  const int n_items = nQT * p.H * p.B;                       // item = (b * H + h) * nQT + query tile
 
   if (w == 0) {
     if (lane == 0) {
@@ -72,15 +77,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  int t_lo, t_hi;
-  key_tile_range(p, i0, t_lo, t_hi);
-
   if (w == NW) {
     // ============================================ issuer (one thread) ============================================
     if (lane == 0) {
       const uint32_t ke_bytes = NATOM * K_ATOM + (p.R > 0 ? NATOM * E_ATOM : 0);
-      auto load_ke = [&](int t) {
-        const int st = (t - t_lo) & 1;
+      uint32_t g = 0, n_done = 0;                 // tiles / items this CTA has issued so far: every phase derives from them
+      int i0 = 0, h = 0, b = 0;
+      auto load_ke = [&](int t, uint32_t gt) {    // gt = running index of tile t
+        const int st = gt & 1;
         ptx::mbar_arrive_expect_tx(&bar_ke[st], ke_bytes);
 #pragma unroll
         for (int a = 0; a < NATOM; ++a)
@@ -92,8 +96,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             ptx::tma_load_2d(sE + (st * NATOM + a) * E_ATOM, &tmE, &bar_ke[st], a * 64, h * (2 * p.R - 1) + e0);
         }
       };
-      auto load_v = [&](int t) {
-        const int st = (t - t_lo) & 1;
+      auto load_v = [&](int t, uint32_t gt) {
+        const int st = gt & 1;
         ptx::mbar_arrive_expect_tx(&bar_v[st], NATOM * V_GRP);
 #pragma unroll
         for (int a = 0; a < NATOM; ++a)
@@ -119,58 +123,98 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         ptx::umma_commit(bar_s);
       };
 
-      ptx::mbar_arrive_expect_tx(bar_q, NATOM * Q_ATOM);
+      // Head of an item: Q, the first two K / E tiles and the first V tile.  `gh` = running index of the item's first tile.
+      // Issued while the PREVIOUS item's last tile is still in its softmax (see below), so the loads and the first S / PB
+      // MMAs are off the critical path of every item but a CTA's first.
+      auto decode = [&](int item, int& t_lo, int& t_hi) {
+        const int bh = item / nQT;
+        i0 = (item - bh * nQT) * BM; b = bh / p.H; h = bh - b * p.H;
+        key_tile_range(p, i0, t_lo, t_hi);
+      };
+      auto head_loads = [&](int t_lo, int t_hi, uint32_t gh) {
+        ptx::mbar_arrive_expect_tx(bar_q, NATOM * Q_ATOM);
 #pragma unroll
-      for (int a = 0; a < NATOM; ++a) ptx::tma_load_2d(sQ + a * Q_ATOM, &tmQ, bar_q, h * DH + a * 64, b * p.Lq + i0);
-      load_ke(t_lo);
-      load_v(t_lo);
-      if (t_lo < t_hi) { load_ke(t_lo + 1); load_v(t_lo + 1); }
-      ptx::mbar_wait(bar_q, 0);
-      ptx::mbar_wait(&bar_ke[0], 0);
-      ptx::tc_fence_after();
-      issue_s(0);
-      for (int t = t_lo; t <= t_hi; ++t) {
-        const int k = t - t_lo, st = k & 1;
-        if (k > 0 && t < t_hi) {                            // V(t-1)'s buffer is free once PV(t-1) has completed
-          ptx::mbar_wait(bar_pv, (uint32_t)((k - 1) & 1));
-          load_v(t + 1);
-        }
-        if (t < t_hi) {
-          ptx::mbar_wait(bar_sfree, (uint32_t)(k & 1));     // S / PB copied to registers by every compute warp
-          ptx::mbar_wait(&bar_ke[st ^ 1], (uint32_t)(((k + 1) >> 1) & 1));
-          ptx::tc_fence_after();
-          issue_s(st ^ 1);
-          if (t + 2 <= t_hi) load_ke(t + 2);                // stage `st`: its MMAs finished before bar_s(t) fired
-        }
-        ptx::mbar_wait(bar_p, (uint32_t)(k & 1));           // P(t) in shared memory, O rescaled
-        ptx::mbar_wait(&bar_v[st], (uint32_t)((k >> 1) & 1));
+        for (int a = 0; a < NATOM; ++a) ptx::tma_load_2d(sQ + a * Q_ATOM, &tmQ, bar_q, h * DH + a * 64, b * p.Lq + i0);
+        load_ke(t_lo, gh);
+        load_v(t_lo, gh);
+        if (t_lo < t_hi) load_ke(t_lo + 1, gh + 1);
+      };
+      int item = blockIdx.x, t_lo = 0, t_hi = -1;
+      if (item < n_items) { decode(item, t_lo, t_hi); head_loads(t_lo, t_hi, 0); }
+      bool sfree_seen = true;                     // bar_sfree(g - 1) already waited for (nothing to wait for at g = 0)
+      while (item < n_items) {
+        const int next = item + (int)gridDim.x;
+        ptx::mbar_wait(bar_q, n_done & 1u);
+        ptx::mbar_wait(&bar_ke[g & 1], (g >> 1) & 1u);
+        if (!sfree_seen) ptx::mbar_wait(bar_sfree, (g - 1) & 1u);   // the previous item's last S / PB are in registers
         ptx::tc_fence_after();
-        const uint32_t pb = ptx::smem_u32(sP), vb = ptx::smem_u32(sV + st * NATOM * V_GRP);
-        const uint32_t id_o = ptx::make_idesc_bf16(BM, DH, 0, 1);
+        issue_s(g & 1);
+        int nt_lo = 0, nt_hi = -1;
+        sfree_seen = false;
+        for (int t = t_lo; t <= t_hi; ++t) {
+          const uint32_t gt = g + (uint32_t)(t - t_lo);
+          const int st = gt & 1;
+          if (gt > 0) ptx::mbar_wait(bar_pv, (gt - 1) & 1u);  // PV(gt-1) done: its V stage (the one tile gt+1 uses) is free
+          if (t < t_hi) {
+            load_v(t + 1, gt + 1);
+            ptx::mbar_wait(bar_sfree, gt & 1u);               // S / PB copied to registers by every compute warp
+            ptx::mbar_wait(&bar_ke[st ^ 1], ((gt + 1) >> 1) & 1u);
+            ptx::tc_fence_after();
+            issue_s(st ^ 1);
+            if (t + 2 <= t_hi) load_ke(t + 2, gt + 2);        // stage `st`: its MMAs finished before bar_s(t) fired
+          } else if (next < n_items) {
+            // last tile of the item: once its S / PB are in registers, the Q buffer, both K / E stages and the V stage
+            // of tile gt + 1 are free -- start the next item's head now, under this tile's softmax
+            ptx::mbar_wait(bar_sfree, gt & 1u);
+            sfree_seen = true;
+            decode(next, nt_lo, nt_hi);                       // (i0, h, b now describe the next item; this one only needs st below)
+            head_loads(nt_lo, nt_hi, gt + 1);
+          }
+          ptx::mbar_wait(bar_p, gt & 1u);                     // P(t) in shared memory, O rescaled
+          ptx::mbar_wait(&bar_v[st], (gt >> 1) & 1u);
+          ptx::tc_fence_after();
+          const uint32_t pb = ptx::smem_u32(sP), vb = ptx::smem_u32(sV + st * NATOM * V_GRP);
+          const uint32_t id_o = ptx::make_idesc_bf16(BM, DH, 0, 1);
 #pragma unroll
-        for (int ks = 0; ks < BN / 16; ++ks)
-          ptx::umma_bf16(tmem + TM_O, ptx::make_smem_desc_sw128(pb + ks * 32, 0, 1024),
-                         ptx::make_smem_desc_sw128(vb + ks * 2048, V_GRP, 1024), id_o, (k > 0 || ks > 0) ? 1u : 0u);
-        ptx::umma_commit(bar_pv);
+          for (int ks = 0; ks < BN / 16; ++ks)
+            ptx::umma_bf16(tmem + TM_O, ptx::make_smem_desc_sw128(pb + ks * 32, 0, 1024),
+                           ptx::make_smem_desc_sw128(vb + ks * 2048, V_GRP, 1024), id_o, (t > t_lo || ks > 0) ? 1u : 0u);
+          ptx::umma_commit(bar_pv);
+        }
+        g += (uint32_t)(t_hi - t_lo + 1);
+        ++n_done;
+        item = next; t_lo = nt_lo; t_hi = nt_hi;
       }
     }
   } else {
     // ============================================ compute warps ==================================================
     const int q = w & 3, hf = w >> 2;
     const int li = 32 * q + lane;
-    const int i = i0 + li;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t g = 0;                                 // running tile counter, in step with the issuer's
+    // The O rows of a finished item are written out one tile late, from inside the NEXT item's first tile: the wait for the
+    // item's last PV (~0.3 us of MMA latency with nothing else to do) then falls behind that tile's logits / exp work.
+    bool o_pending = false, o_valid = false;
+    float o_scale = 0.f;
+    __nv_bfloat16* o_dst = nullptr;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int bh = item / nQT;
+    const int i0 = (item - bh * nQT) * BM, b = bh / p.H, h = bh - b * p.H;
+    int t_lo, t_hi;
+    key_tile_range(p, i0, t_lo, t_hi);
+    const int i = i0 + li;
     const RowCtx rc = make_row_ctx(p, b, h, i);
     float m_run = NEG_BIG, l_run = 0.f;             // l_run: this thread's share (its CW columns) of the row sum
 
     for (int t = t_lo; t <= t_hi; ++t) {
       const int k = t - t_lo;
-      ptx::mbar_wait(bar_s, (uint32_t)(k & 1));
+      const uint32_t gt = g + (uint32_t)k;
+      ptx::mbar_wait(bar_s, gt & 1u);
       ptx::tc_fence_after();
 
       float U[SP::WIN_LD];
       const bool skip = block_out_of_band<NSPLIT>(p, i0 + 32 * q, t * BN + CW * hf);
-      float* red = sred + (k & 1) * NSPLIT * 128;
+      float* red = sred + (gt & 1) * NSPLIT * 128;
       float mt = NEG_BIG;
       if (!skip) {
         uint32_t mbits;
@@ -203,9 +247,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       l_run = l_run * alpha + sum;
       m_run = m_new;
-      if (k > 0) {                                   // PV(t-1) done: the P buffer is free and O is complete
-        ptx::mbar_wait(bar_pv, (uint32_t)((k - 1) & 1));
+      if (gt > 0) {                                  // PV(gt-1) done: the P buffer is free and O is complete
+        ptx::mbar_wait(bar_pv, (gt - 1) & 1u);
         ptx::tc_fence_after();
+        if (o_pending) {                             // k == 0: the previous item's accumulator, before this item's first PV
+          tmem_row_to_global<OC>(tmem + TM_O + hf * OC + lane_base, o_dst, o_scale, o_valid);
+          o_pending = false;
+        }
       }
       if (!skip) store_cols_bf16_sw128<CW>(ptx::smem_u32(sP), li, CW * hf, U);
       else store_zero_cols_sw128<CW>(ptx::smem_u32(sP), li, CW * hf);
@@ -228,23 +276,30 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (lane == 0) ptx::mbar_arrive(bar_p);
     }
 
-    // row sum = sum of the column groups' shares
+    // row sum = sum of the column groups' shares (third exchange buffer: the next item's first tile reuses the per-tile ones
+    // while slower warps of this quarter may still be reading here)
     const int kl = t_hi - t_lo;
-    float* red = sred + ((kl + 1) & 1) * NSPLIT * 128;
+    float* red = sred + 2 * NSPLIT * 128;
     red[hf * 128 + li] = l_run;
     ptx::named_bar_sync(1 + q, 32 * NSPLIT);
     float l_tot = 0.f;
 #pragma unroll
     for (int g = 0; g < NSPLIT; ++g) l_tot += red[g * 128 + li];
 
-    ptx::mbar_wait(bar_pv, (uint32_t)(kl & 1));
-    ptx::tc_fence_after();
     const bool valid = i < p.Lq;
-    tmem_row_to_global<OC>(tmem + TM_O + hf * OC + lane_base, p.o + ((long)b * p.Lq + i) * p.ldo + h * DH + hf * OC, 1.f / l_tot, valid);
+    o_pending = true; o_valid = valid; o_scale = 1.f / l_tot;
+    o_dst = p.o + ((long)b * p.Lq + i) * p.ldo + h * DH + hf * OC;
     if (valid && hf == 0) {
       const long nrows = (long)p.B * p.H * p.Lq;
       p.lse[rc.row_id] = m_run;
       p.lse[nrows + rc.row_id] = __logf(l_tot);
+    }
+    g += (uint32_t)(kl + 1);
+    }  // items
+    if (o_pending) {                                // the CTA's last item
+      ptx::mbar_wait(bar_pv, (g - 1) & 1u);
+      ptx::tc_fence_after();
+      tmem_row_to_global<OC>(tmem + TM_O + hf * OC + lane_base, o_dst, o_scale, o_valid);
     }
   }
   ptx::tc_fence_before();
@@ -274,14 +329,15 @@ static int attn_fwd_tc_launch_n(const SstAttnDesc& d, const void* q, const void*
     tmE = tmK;
   }
   constexpr int NATOM = (DH + 63) / 64;
-  constexpr int SMEM = NATOM * (BM * 128 + 2 * BN * 128 + 2 * PBW * 128 + 2 * BN * 128) + BM * 128 + 1024 + 128 + 2 * NSPLIT * 128 * 4;
+  constexpr int SMEM = NATOM * (BM * 128 + 2 * BN * 128 + 2 * PBW * 128 + 2 * BN * 128) + BM * 128 + 1024 + 128 + 3 * NSPLIT * 128 * 4;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<DH, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     SST_REQUIRE(e == cudaSuccess, SST_E_LAUNCH, "cudaFuncSetAttribute(attn_fwd_tc): %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  dim3 grid(cdiv(d.Lq, BM), d.H, d.B);
+  const long n_items = (long)cdiv(d.Lq, BM) * d.H * d.B;
+  const int grid = (int)(n_items < num_sms() ? n_items : num_sms());       // persistent: one CTA per SM
   attn_fwd_tc_kernel<DH, NSPLIT><<<grid, 128 * NSPLIT + 32, SMEM, st>>>(tmQ, tmK, tmV, tmE, p);
   return check_launch("attn_fwd_tc");
 }
