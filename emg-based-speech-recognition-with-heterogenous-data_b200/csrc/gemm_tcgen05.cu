@@ -51,6 +51,21 @@ struct GemmKParams {
   int remap_P, remap_T, remap_j0;
 };
 
+// Debug timeline (-DSST_GEMM_TRACE, tools/gemm_trace.py): CTA 0 stamps %globaltimer at its pipeline events.
+#ifdef SST_GEMM_TRACE
+__device__ unsigned long long g_gemm_trace[64];
+__device__ __forceinline__ void trace_stamp(int slot) {
+  if (blockIdx.x == 0 && slot < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_gemm_trace[slot] = t;
+  }
+}
+#define SST_TRACE(slot) trace_stamp(slot)
+#else
+#define SST_TRACE(slot) do { } while (0)
+#endif
+
 template <int BN, int CTAS> struct GemmCfg {
   static constexpr int B_ROWS = BN / CTAS;                        // rows of the B tile this CTA stages
   static constexpr int B_BYTES = B_ROWS * G_BK * 2;
@@ -86,6 +101,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 512;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) SST_TRACE(0);                                  // kernel entry
   const int rank = CTAS == 2 ? (int)ptx::cluster_ctarank() : 0;        // rank 0 of a pair issues the MMAs
   const int unit0 = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int unit_stride = CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -108,6 +124,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (CTAS == 2) ptx::cluster_sync(); else __syncthreads();       // the peer's barriers exist before anything signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) SST_TRACE(1);                                  // barriers, TMEM, cluster sync done
 
   const int total_units = p.m_blks * p.n_blks * p.splits;
 
@@ -127,6 +144,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int nB = n0 + rank * Cfg::B_ROWS;                  // this CTA's slice of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1u);
+          if (u == unit0 && kb == kb0) SST_TRACE(2);                   // first TMA issue
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + G_A_BYTES;
           if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], CTAS * Cfg::STAGE_BYTES);
@@ -167,6 +185,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&full[stage], phase);
         ptx::tc_fence_after();
+        if (lane == 0 && u == unit0 && kb == kb0) SST_TRACE(3);        // first operands landed
         if (lane == 0) {
           const uint32_t a_base = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_base = a_base + G_A_BYTES;
@@ -284,6 +303,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool bias_vec = (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
+      if (warp == 2 && lane == 0) SST_TRACE(8 + 2 * ((u - unit0) / unit_stride));       // tile's accumulator ready
       bool row_ok = m < p.M;
       long out_row = m;
       if (p.remap_P > 0) {
@@ -438,6 +458,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       ptx::tc_fence_before();
       __syncwarp();
+      if (warp == 2 && lane == 0) SST_TRACE(9 + 2 * ((u - unit0) / unit_stride));       // tile's epilogue (this warp) done
       if (lane == 0) {
         if (CTAS == 2) ptx::mbar_arrive_cluster(ptx::map_to_cta(&tempty[acc], 0));
         else ptx::mbar_arrive(&tempty[acc]);
@@ -449,7 +470,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   __syncwarp();
   ptx::tc_fence_before();
+  if (threadIdx.x == 64) SST_TRACE(4);                                 // first epilogue warp at the final barrier
   if (CTAS == 2) ptx::cluster_sync(); else __syncthreads();       // the pair is done with each other's smem / barriers
+  if (threadIdx.x == 0) SST_TRACE(5);
   if (warp == 1) {
     ptx::tc_fence_after();
     if (CTAS == 2) ptx::tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
@@ -558,6 +581,12 @@ static int launch_bn(const SstGemmDesc& d, const void* A, const void* B, GemmKPa
   return check_launch("gemm_tcgen05");
 }
 
+#ifdef SST_GEMM_TRACE
+extern "C" int sst_debug_gemm_trace(unsigned long long* out_host) {
+  return cudaMemcpyFromSymbol(out_host, g_gemm_trace, sizeof(unsigned long long) * 64) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 int launch_gemm_tcgen05(const SstGemmDesc& d, const void* A, const void* B, void* C, const void* bias, const void* aux,
                         cudaStream_t st) {
   GemmKParams p;
@@ -597,16 +626,10 @@ int launch_gemm_tcgen05(const SstGemmDesc& d, const void* A, const void* B, void
   // CTA pairs (256-row tiles) whenever there are at least two row blocks; SST_GEMM_CTAS=1 forces single-CTA tiles
   static const int ctas_env = [] { const char* e = getenv("SST_GEMM_CTAS"); return e ? atoi(e) : 2; }();
   const int ctas = (ctas_env == 2 && d.M > G_BM) ? 2 : 1;
-  // tile width by wave quantisation: time ~ waves * BN; 256-wide tiles reuse the A tile twice as long, so 128 must win by 10 %
-  bool wide = true;
-  if (d.N <= 128) wide = false;
-  else if (p.mode_mn) wide = d.N % 256 == 0;
-  else {
-    const long slots = num_sms() / ctas, mb = cdiv(d.M, G_BM * ctas);
-    const long t256 = mb * cdiv(d.N, 256), t128 = mb * cdiv(d.N, 128);
-    const long c256 = ((t256 + slots - 1) / slots) * 256, c128 = ((t128 + slots - 1) / slots) * 128;
-    wide = !(c128 * 10 < c256 * 9);
-  }
+  // tile width: 256 columns whenever N has more than 128.  The main loop of these shapes is paced by operand delivery from
+  // L2 (measured with SST_GEMM_TRACE: ~0.45 us per 64-wide k-block of a pair tile whether it is 128 or 256 columns wide), so
+  // a 128-wide tile costs almost as much as a 256-wide one and an extra wave of them never pays.
+  const bool wide = p.mode_mn ? (d.N % 256 == 0) : (d.N > 128);
   if (ctas == 2) return wide ? launch_bn<256, 2>(d, A, B, p, st) : launch_bn<128, 2>(d, A, B, p, st);
   return wide ? launch_bn<256, 1>(d, A, B, p, st) : launch_bn<128, 1>(d, A, B, p, st);
 }

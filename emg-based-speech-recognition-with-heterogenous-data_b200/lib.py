@@ -5,7 +5,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsst.so")
+LIB_PATH = os.environ.get("SST_LIB", os.path.join(_HERE, "libsst.so"))      # SST_LIB: an instrumented build (tools/gemm_trace.py)
 
 F32, BF16 = 0, 1
 GEMM_TN, GEMM_NT_MN, GEMM_TN_BMN = 0, 1, 2

@@ -1,0 +1,35 @@
+"""Measurement driver (not a pytest file): timeline of CTA 0 inside one decoder-sized GEMM launch (needs the instrumented
+build tools/libsst_trace.so: gemm_tcgen05.cu compiled with -DSST_GEMM_TRACE; run with SST_LIB pointing at it)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import sst_b200  # noqa
+from sst_b200 import lib as L
+
+M = 7744
+for (N, K) in [(768, 64), (768, 768), (2304, 768)]:
+    x = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    y = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        L.gemm(x, w, y, M, N, K, K, K, N)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); L.gemm(x, w, y, M, N, K, K, K, N); e1.record()
+    torch.cuda.synchronize()
+    buf = (C.c_ulonglong * 64)()
+    assert L.lib().sst_debug_gemm_trace(buf) == 0
+    t = list(buf)
+    t0 = t[0]
+    names = {0: "entry", 1: "setup done", 2: "first TMA issued", 3: "first operands landed", 4: "epilogue warp at final barrier", 5: "after final barrier"}
+    print("GEMM %dx%dx%d: event-timed %.1f us" % (M, N, K, e0.elapsed_time(e1) * 1e3))
+    for k in sorted(names):
+        print("   %-32s +%6.2f us" % (names[k], (t[k] - t0) / 1e3))
+    for i in range(8, 20, 2):
+        if t[i] > t0 and t[i] - t0 < 10**9:
+            print("   tile %d: accumulator ready +%6.2f us, epilogue done +%6.2f us" % ((i - 8) // 2, (t[i] - t0) / 1e3, (t[i + 1] - t0) / 1e3))
