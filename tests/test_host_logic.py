@@ -22,7 +22,7 @@ from sst_b200.data_utils import combine_fixed_length, decollate_tensor  # noqa: 
 
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "sst.h")).read()
-    return re.findall(r"^(?:int|long long|const char\*) (sst_\w+)\(", src, re.M)
+    return re.findall(r"^(?:int|long long|size_t|const char\*) (sst_\w+)\(", src, re.M)
 
 
 def test_cabi_library_exports_every_declared_symbol():
