@@ -1,0 +1,85 @@
+"""Data-parallel parity on real GPUs: with one process per GPU, the gradient every rank applies after the
+bucketed NCCL all-reduce is the MEAN over ranks of the gradient each rank's own batch produces, and all ranks hold identical
+parameters afterwards.  fp32 mode, dropout 0.  Needs >= 2 GPUs (skipped on the single-GPU box; run with `gpurun --gpus 2`);
+the host-side bucket logic is covered on CPU by the gloo world-2 test in test_host_logic.py."""
+import os
+import socket
+import tempfile
+
+import pytest
+import torch
+
+import sst_oracle as O
+
+pytestmark = pytest.mark.gpu
+BETA1 = 0.9
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _make_trainer(cfg, sd, dev, distributed):
+    import sst_b200  # noqa: F401
+    from sst_b200 import architecture as A
+    from sst_b200.train import Trainer
+    A.configure(model_size=768, feed_forward_layer_size=3072, num_layers_encoder=cfg["n_enc"], num_layers_decoder=cfg["n_dec"],
+                n_heads_encoder=8, n_heads_decoder=8, relative_distance=cfg["rel_dist"], dropout_model=0.0, dropout_pos_emb=0.0,
+                sst_dtype="fp32")
+    model = A.Model(112, 44, 43, dev).to(dev)
+    model.load_state_dict(sd)
+    # tiny buckets: several all-reduces per stage, so bucket boundaries inside and across stages are exercised
+    return Trainer(model, alpha_loss=cfg["alpha"], batch_size_grad=1, seed=0, distributed=distributed, bucket_bytes=4 << 20)
+
+
+def _batch(rank):
+    return O.synthetic_batch(seed=90 + rank, ragged=[[70, 100, 30], [100, 55, 44]][rank], tgt_lens=[[9, 14, 5], [12, 6, 8]][rank])
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    cfg = O.make_cfg(n_enc=1, n_dec=1, rel_dist=100, alpha=0.2)
+    sd0 = O.synthetic_state_dict(cfg, 7)
+    tr = _make_trainer(cfg, sd0, dev, True)
+    from sst_b200.train import prepare_batch
+    d = tr.to_device(tr.prepare(_batch(rank)))
+    tr.step_device(d, shift_r=0)
+    torch.cuda.synchronize()
+    # first AdamW step: m = (1 - beta1) * g  ->  the gradient the optimizer consumed
+    torch.save({"g": (tr.flat.m / (1.0 - BETA1)).cpu(), "p": tr.flat.p.cpu(), "names": list(tr.flat.names)},
+               os.path.join(out_dir, "rank%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_allreduced_gradient_is_the_mean_of_the_per_rank_gradients():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    out_dir = tempfile.mkdtemp()
+    mp.spawn(_worker, args=(world, _free_port(), out_dir), nprocs=world, join=True)
+    res = [torch.load(os.path.join(out_dir, "rank%d.pt" % r)) for r in range(world)]
+    assert torch.equal(res[0]["p"], res[1]["p"]) and torch.equal(res[0]["g"], res[1]["g"])       # replicas stay identical
+    # single-process gradients of each rank's batch from the same initial weights
+    cfg = O.make_cfg(n_enc=1, n_dec=1, rel_dist=100, alpha=0.2)
+    sd0 = O.synthetic_state_dict(cfg, 7)
+    gs = []
+    for r in range(world):
+        tr = _make_trainer(cfg, sd0, torch.device("cuda", 0), False)
+        tr.step_device(tr.to_device(tr.prepare(_batch(r))), shift_r=0)
+        torch.cuda.synchronize()
+        gs.append((tr.flat.m / (1.0 - BETA1)).cpu())
+    want = (gs[0] + gs[1]) / world
+    got = res[0]["g"]
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) < 2e-5 * scale                                           # fp32, different summation order only
+    assert float((gs[0] - gs[1]).abs().max()) > 1e-2 * scale                                        # the two shards really differ
