@@ -135,6 +135,16 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
 
+  // The Q / dO / O rows the compute warps park in TMEM below were written by the forward pass long ago: pull them towards
+  // L2 now (no registers involved), so that their latency runs under the barrier / TMEM set-up and the first block barrier.
+  if (w < 12 && i0 + 32 * (w & 3) + lane < p.Lq) {
+    const long row = (long)b * p.Lq + i0 + 32 * (w & 3) + lane;
+    const int which = w >> 2;                       // 0: Q, 1: dO, 2: O
+    const char* rp = reinterpret_cast<const char*>(which == 0 ? qg + row * p.ldq : (which == 1 ? p.dO : p.o) + row * p.ldo) + h * DH * 2;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 128));      // DH * 2 = 192 bytes: two 128-byte lines cover a row
+  }
+
   if (w == 0) {
     if (lane == 0) {
       ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);

@@ -277,7 +277,7 @@ int sst_layernorm_bwd(int dtype, int64_t rows, int D, const void* dy, const void
   if (thr == 0) dr = nullptr;
   const float dscale = drop_p < 1.f ? 1.f / (1.f - drop_p) : 0.f;
   // two resident blocks per SM and no more blocks than that: every block ends with 2*D global atomics (dgamma, dbeta)
-  long blocks = (rows + 63) / 64;
+  long blocks = (rows + 7) / 8;                  // one row per warp at least: decoder-sized inputs spread over every SM
   long cap = (long)num_sms() * 2;
   const int grid = (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
   SST_REQUIRE(rows < (1L << 31), SST_E_ARG, "layernorm: too many rows");
