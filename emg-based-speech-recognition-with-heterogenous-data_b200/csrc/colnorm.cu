@@ -510,6 +510,7 @@ int sst_colstats(int dtype, const void* x, int64_t rows, int C, int64_t ld, doub
   cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st);
   SST_REQUIRE(e == cudaSuccess, SST_E_LAUNCH, "memset: %s", cudaGetErrorString(e));
   if (rows <= 0) return SST_OK;
+  SST_REQUIRE(rows < (1L << 31), SST_E_ARG, "colstats: too many rows");
   const size_t esz = dtype == SST_F32 ? 4 : 2;
   const ColLaunch cl = col_launch(rows, C / 8, sizeof(double), 0, 2, 1, esz);
   if (dtype == SST_F32) SST_COL_LAUNCH(colstats_kernel, float, (const float*)x, rows, C, ld, stats, cl.rpb, cl.sm);
@@ -520,6 +521,7 @@ int sst_colstats(int dtype, const void* x, int64_t rows, int C, int64_t ld, doub
 int sst_colsum_accum(int dtype, const void* x, int64_t rows, int C, int64_t ld, float* out, void* stream) {
   SST_REQUIRE(ld % 8 == 0 && C <= ld && (C + 7) / 8 <= 512, SST_E_ARG, "colsum: pitch %ld must be a multiple of 8 and >= C=%d", (long)ld, C);
   if (rows <= 0) return SST_OK;
+  SST_REQUIRE(rows < (1L << 31), SST_E_ARG, "colsum: too many rows");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int tx = (C + 7) / 8;
   const size_t esz = dtype == SST_F32 ? 4 : 2;
@@ -545,6 +547,7 @@ int sst_bn_apply(int dtype, int64_t n_chunks, int T, int C, const void* xa, int6
   BnBranch b{xb, ldb, mean_b, invstd_b, gamma_b, beta_b};
   const long prows = n_chunks * (long)(T + lead + trail);
   if (prows <= 0) return SST_OK;
+  SST_REQUIRE(prows < (1L << 31), SST_E_ARG, "bn_apply: too many rows");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   SST_REQUIRE(C / 8 <= 512, SST_E_ARG, "bn_apply: C=%d too wide", C);
   const size_t esz = dtype == SST_F32 ? 4 : 2;
@@ -575,6 +578,7 @@ int sst_bn_bwd(int dtype, int64_t n_chunks, int T, int C, const void* dout, int6
   SST_REQUIRE(e == cudaSuccess, SST_E_LAUNCH, "memset: %s", cudaGetErrorString(e));
   const long rows = n_chunks * T;
   if (rows <= 0) return SST_OK;
+  SST_REQUIRE(rows < (1L << 31) && n_chunks * (long)(T + 4) < (1L << 31), SST_E_ARG, "bn_bwd: too many rows");
   const size_t esz = dtype == SST_F32 ? 4 : 2;
   const size_t sgn_bytes = (relu && y == nullptr) ? (size_t)4 * C * sizeof(float) : 0;
   const int nt = 2 + has_b + ((relu && y != nullptr) ? 1 : 0);      // dout, xa, [xb], [y]
