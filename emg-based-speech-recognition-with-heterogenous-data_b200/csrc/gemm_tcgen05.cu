@@ -179,13 +179,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int u = unit0; u < total_units && rank == 0; u += unit_stride) {
       int m0, nb, kb0, kb1;
       decode_unit<CTAS>(p, u, rank, m0, nb, kb0, kb1);
+      if (lane == 0) SST_TRACE(40 + 2 * ((u - unit0) / unit_stride));          // issuer arrives at the tile
       ptx::mbar_wait(&tempty[acc], acc_phase ^ 1u);
+      if (lane == 0) SST_TRACE(41 + 2 * ((u - unit0) / unit_stride));          // accumulator buffer released by the epilogue
       ptx::tc_fence_after();
+      if (lane == 0) SST_TRACE(20 + 3 * ((u - unit0) / unit_stride));          // ... and fenced
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       for (int kb = kb0; kb < kb1; ++kb) {
-        ptx::mbar_wait(&full[stage], phase);
-        ptx::tc_fence_after();
+        ptx::mbar_wait(&full[stage], phase);      // TMA (async proxy) -> MMA (async proxy): the mbarrier is all the ordering
+                                                  // needed; a tcgen05 fence here would only stall the issuer
         if (lane == 0 && u == unit0 && kb == kb0) SST_TRACE(3);        // first operands landed
+        if (lane == 0 && kb == kb0) SST_TRACE(21 + 3 * ((u - unit0) / unit_stride));       // tile's first operands landed
+        if (lane == 0 && kb == kb1 - 1) SST_TRACE(22 + 3 * ((u - unit0) / unit_stride));   // tile's last operands landed
         if (lane == 0) {
           const uint32_t a_base = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_base = a_base + G_A_BYTES;
@@ -626,9 +631,9 @@ int launch_gemm_tcgen05(const SstGemmDesc& d, const void* A, const void* B, void
   // CTA pairs (256-row tiles) whenever there are at least two row blocks; SST_GEMM_CTAS=1 forces single-CTA tiles
   static const int ctas_env = [] { const char* e = getenv("SST_GEMM_CTAS"); return e ? atoi(e) : 2; }();
   const int ctas = (ctas_env == 2 && d.M > G_BM) ? 2 : 1;
-  // tile width: 256 columns whenever N has more than 128.  The main loop of these shapes is paced by operand delivery from
-  // L2 (measured with SST_GEMM_TRACE: ~0.45 us per 64-wide k-block of a pair tile whether it is 128 or 256 columns wide), so
-  // a 128-wide tile costs almost as much as a 256-wide one and an extra wave of them never pays.
+  // tile width: 256 columns whenever N has more than 128.  Measured with SST_GEMM_TRACE: a 64-wide k-block of a pair tile
+  // takes ~0.45 us whether the tile is 128 or 256 columns wide (MMA rate paces the wide tile, operand latency the narrow
+  // one), so a 128-wide tile costs almost as much as a 256-wide one and an extra wave of them never pays.
   const bool wide = p.mode_mn ? (d.N % 256 == 0) : (d.N > 128);
   if (ctas == 2) return wide ? launch_bn<256, 2>(d, A, B, p, st) : launch_bn<128, 2>(d, A, B, p, st);
   return wide ? launch_bn<256, 1>(d, A, B, p, st) : launch_bn<128, 1>(d, A, B, p, st);

@@ -32,4 +32,8 @@ for (N, K) in [(768, 64), (768, 768), (2304, 768)]:
         print("   %-32s +%6.2f us" % (names[k], (t[k] - t0) / 1e3))
     for i in range(8, 20, 2):
         if t[i] > t0 and t[i] - t0 < 10**9:
-            print("   tile %d: accumulator ready +%6.2f us, epilogue done +%6.2f us" % ((i - 8) // 2, (t[i] - t0) / 1e3, (t[i + 1] - t0) / 1e3))
+            k = (i - 8) // 2
+            m = 20 + 3 * k
+            print("   tile %d: issuer arrives +%6.2f, buffer released +%6.2f" % (k, (t[40 + 2 * k] - t0) / 1e3, (t[41 + 2 * k] - t0) / 1e3))
+            print("   tile %d: MMA warp: buffer free +%6.2f, first operands +%6.2f, last operands +%6.2f | epilogue: accumulator ready +%6.2f us, done +%6.2f us"
+                  % (k, (t[m] - t0) / 1e3, (t[m + 1] - t0) / 1e3, (t[m + 2] - t0) / 1e3, (t[i] - t0) / 1e3, (t[i + 1] - t0) / 1e3))
