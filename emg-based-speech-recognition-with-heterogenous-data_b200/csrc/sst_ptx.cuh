@@ -15,6 +15,9 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---- mbarrier --------------------------------------------------------------------------------------
+#ifndef SST_MBAR_HINT_NS
+#define SST_MBAR_HINT_NS 20000
+#endif
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -28,15 +31,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}"
-               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  // potentially-blocking form with a suspend-time hint (ns): a waiting warp sleeps in hardware instead of re-issuing the
+  // test every few cycles.  The idle epilogue warps of a long-K GEMM otherwise spin for the whole main loop; with the chip
+  // at its power cap that costs clock: weight-gradient GEMMs measured 6 % faster with the hint (same run, A/B).
+  asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, P;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)SST_MBAR_HINT_NS) : "memory");
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (kernel aborts with an error) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 23)) { __trap(); }
+    if (++spins > (1u << 20)) { __trap(); }          // each failed try may have slept up to SST_MBAR_HINT_NS
   }
 }
 
