@@ -1,5 +1,12 @@
-"""Measurement driver (not a pytest file): timeline of CTA 0 inside one decoder-sized GEMM launch (needs the instrumented
-build tools/libsst_trace.so: gemm_tcgen05.cu compiled with -DSST_GEMM_TRACE; run with SST_LIB pointing at it)."""
+"""Measurement driver (not a pytest file): timeline of CTA 0 inside one decoder-sized GEMM launch.  Needs an instrumented
+build of the library (gemm_tcgen05.cu compiled with -DSST_GEMM_TRACE, everything else as in csrc/build.sh):
+
+    cd <pkg>/csrc && mkdir -p /tmp/tr && for f in *.cu; do nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 \
+        -Xcompiler -fPIC --expt-relaxed-constexpr -DSST_GEMM_TRACE -c $f -o /tmp/tr/${f%.cu}.o; done && \
+        nvcc -gencode arch=compute_100a,code=sm_100a -shared -o <repo>/tools/libsst_trace.so /tmp/tr/*.o -lcudart
+    SST_LIB=<repo>/tools/libsst_trace.so python tools/gemm_trace.py
+
+The stamps (%globaltimer by one lane + a global store) cost ~0.1 us each: read differences of several stamps, not single gaps."""
 import ctypes as C
 import os
 import sys
