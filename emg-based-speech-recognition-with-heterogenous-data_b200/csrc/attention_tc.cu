@@ -129,7 +129,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       auto decode = [&](int item, int& t_lo, int& t_hi) {
         const int bh = item / nQT;
         i0 = (item - bh * nQT) * BM; b = bh / p.H; h = bh - b * p.H;
-        key_tile_range(p, i0, t_lo, t_hi);
+        key_tile_range_valid(p, i0, b, t_lo, t_hi);
       };
       auto head_loads = [&](int t_lo, int t_hi, uint32_t gh) {
         ptx::mbar_arrive_expect_tx(bar_q, NATOM * Q_ATOM);
@@ -201,7 +201,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int bh = item / nQT;
     const int i0 = (item - bh * nQT) * BM, b = bh / p.H, h = bh - b * p.H;
     int t_lo, t_hi;
-    key_tile_range(p, i0, t_lo, t_hi);
+    key_tile_range_valid(p, i0, b, t_lo, t_hi);
     const int i = i0 + li;
     const RowCtx rc = make_row_ctx(p, b, h, i);
     float m_run = NEG_BIG, l_run = 0.f;             // l_run: this thread's share (its CW columns) of the row sum

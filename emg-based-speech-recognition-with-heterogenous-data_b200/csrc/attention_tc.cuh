@@ -82,6 +82,19 @@ __device__ __forceinline__ void key_tile_range(const AttnTcParams& p, int i0, in
   t_lo = j_lo / BN;
   t_hi = j_hi / BN;
 }
+// The same range without the key tiles that lie entirely in utterance b's padding (j >= k_lens[b]): every key there is
+// masked, so its probability is exactly 0 in fp32 for any query row that has an unmasked key -- skipping those tiles changes
+// nothing.  Only done for query tiles without a masked row: a fully masked row spreads uniformly over ALL keys in the
+// reference (transformer.py:185-187), padding included, and stays bit-compatible with that here.
+__device__ __forceinline__ void key_tile_range_valid(const AttnTcParams& p, int i0, int b, int& t_lo, int& t_hi) {
+  key_tile_range(p, i0, t_lo, t_hi);
+  const bool rows_unmasked = !p.mask_q_rows || (p.q_pad == nullptr && (p.q_lens == nullptr || i0 + BM <= p.q_lens[b]));
+  if (p.k_lens != nullptr && rows_unmasked) {
+    const int klen = p.k_lens[b];
+    const int t_valid = (max(klen, 1) - 1) / BN;          // last tile that holds a real key
+    t_hi = max(t_lo, min(t_hi, t_valid));
+  }
+}
 // query tiles [q_lo, q_hi] (of BM rows) a key tile starting at j0 receives contributions from
 __device__ __forceinline__ void query_tile_range(const AttnTcParams& p, int j0, int& q_lo, int& q_hi) {
   int i_lo = 0, i_hi = p.Lq - 1;

@@ -163,8 +163,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  int t_lo, t_hi;
-  key_tile_range(p, i0, t_lo, t_hi);
+  int t_lo, t_hi, t_hi_full;
+  key_tile_range(p, i0, t_lo, t_hi_full);
+  key_tile_range_valid(p, i0, b, t_lo, t_hi);        // tiles (t_hi, t_hi_full] are pure padding: their hand-off tiles are zeros
 
   const uint32_t ke_bytes = NATOM * K_ATOM + (p.R > 0 ? NATOM * E_ATOM : 0);
   auto load_ke = [&](int t) {
@@ -377,6 +378,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
       if (lane == 0) ptx::mbar_arrive(bar_p);
     }
 
+    for (int t = t_hi + 1; t <= t_hi_full; ++t) {      // the dK/dV kernel walks the full range: padding tiles contribute nothing
+      store_zero_cols_global<CW>(tile_p + (long)(t - t_lo) * BM * BN);
+      store_zero_cols_global<CW>(tile_ds + (long)(t - t_lo) * BM * BN);
+    }
     ptx::mbar_wait(bar_dq, (uint32_t)((t_hi - t_lo) & 1));
     ptx::tc_fence_after();
     tmem_row_to_global<OC>(tmem + TM_DQ + hf * OC + lane_base, p.dq + ((long)b * p.Lq + i) * p.ldq + h * DH + hf * OC, 1.f, valid);
