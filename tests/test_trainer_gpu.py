@@ -146,3 +146,34 @@ def test_checkpoint_resume_continues_the_run():
     b1, b3 = dict(t1.model.named_buffers()), dict(t3.model.named_buffers())
     for k in b1:
         assert float((b1[k].float() - b3[k].float()).abs().max()) <= 1e-4 * (float(b1[k].float().abs().max()) + 1e-6), k
+
+
+def test_pipelined_run_gives_the_stepwise_losses():
+    """Trainer.run (upload of batch i+1 on a copy stream, deferred loss read-back: the path bench.py's `e2e` times) against
+    the plain step-by-step loop on the same batches: same losses per step, same parameters at the end (fp32 mode, dropout 0,
+    to the rounding of the fp32 atomics), and every step's loss is reported exactly once and in order."""
+    import random
+    from sst_b200.train import Trainer
+    cfg = O.make_cfg(n_enc=1, n_dec=1, rel_dist=100, alpha=0.2)
+    sd0 = O.synthetic_state_dict(cfg, 11)
+    batches = [O.synthetic_batch(seed=70 + k, ragged=[[70, 100, 30], [100, 64, 90], [55, 80, 100], [100, 100, 21]][k],
+                                 tgt_lens=[9, 14, 5]) for k in range(4)]
+
+    t1 = Trainer(_model(cfg, sd0, "fp32"), alpha_loss=0.2, batch_size_grad=1, seed=0)
+    random.seed(5)
+    want = []
+    for b in batches:
+        t1.step(b)
+        want.append(t1.wait_losses())
+
+    t2 = Trainer(_model(cfg, sd0, "fp32"), alpha_loss=0.2, batch_size_grad=1, seed=0)
+    random.seed(5)                                   # the same random input shifts (architecture.py:105)
+    got = list(t2.run(t2.prepare(b) for b in batches))
+    torch.cuda.synchronize()
+    assert len(got) == len(want) == 4
+    for a, b in zip(got, want):
+        for x, y in zip(a, b):
+            assert abs(float(x) - float(y)) < 1e-4 * max(1.0, abs(float(y)))
+    assert t2.batch_idx == 4 and t2.flat.step_count == 4
+    scale = float(t1.flat.p.abs().max())
+    assert float((t1.flat.p - t2.flat.p).abs().max()) < 1e-4 * scale
