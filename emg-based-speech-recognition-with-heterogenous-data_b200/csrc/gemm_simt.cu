@@ -23,6 +23,8 @@ struct SimtParams {
   void* C;
   int out_dtype;
   int remap_P, remap_T, remap_j0;
+  int out_seg_cols, out_grp_cols;
+  long out_seg_stride, out_grp_off[3];
 };
 
 template <typename T>
@@ -126,7 +128,12 @@ gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, const SimtPar
         v = philox_keep16(p.seed, (unsigned long long)m * (unsigned long long)p.N + n, p.drop_thr) ? v * p.drop_scale : 0.f;
       if (p.epilogue & SST_EPI_MULMASK)
         v *= (ld_as_f32(p.aux, (long)m * p.ldaux + n, p.aux_dtype) > 0.f) ? p.mask_scale : 0.f;
-      const long ci = out_row * p.ldc + n;
+      long ci = out_row * p.ldc + n;
+      if (p.out_seg_cols > 0) {
+        const int grp = n / p.out_grp_cols, nin = n - grp * p.out_grp_cols;
+        const int seg = nin / p.out_seg_cols;
+        ci = p.out_grp_off[grp] + (long)seg * p.out_seg_stride + out_row * p.ldc + (nin - seg * p.out_seg_cols);
+      }
       if (p.epilogue & SST_EPI_ACCUM) v += ld_as_f32(p.C, ci, p.out_dtype);
       st_from_f32(p.C, ci, p.out_dtype, v);
     }
@@ -161,6 +168,10 @@ int launch_gemm_simt(const SstGemmDesc& d, const void* A, const void* B, void* C
   p.aux = aux; p.aux_dtype = d.aux_dtype;
   p.C = C; p.out_dtype = d.out_dtype;
   p.remap_P = d.remap_P; p.remap_T = d.remap_T; p.remap_j0 = d.remap_j0;
+  p.out_seg_cols = (int)d.out_seg_cols; p.out_grp_cols = (int)d.out_grp_cols; p.out_seg_stride = d.out_seg_stride;
+  for (int s = 0; s < 3; ++s) p.out_grp_off[s] = d.out_grp_off[s];
+  if (d.out_seg_cols > 0)
+    SST_REQUIRE(d.out_grp_cols % d.out_seg_cols == 0 && cdiv(d.N, d.out_grp_cols) <= 3, SST_E_ARG, "segmented output: bad group / segment sizes");
   dim3 grid(cdiv(d.N, 64), cdiv(d.M, 64));
   if (d.dtype == SST_F32)
     gemm_simt_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(A), reinterpret_cast<const float*>(B), p);

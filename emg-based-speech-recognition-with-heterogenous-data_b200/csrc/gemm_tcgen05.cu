@@ -49,6 +49,8 @@ struct GemmKParams {
   int out_f32;
   int atomic_out;
   int remap_P, remap_T, remap_j0;
+  int out_seg_cols, out_grp_cols;       // segmented output columns (SstGemmDesc), 0 = plain
+  long out_seg_stride, out_grp_off[3];
 };
 
 // Debug timeline (-DSST_GEMM_TRACE, tools/gemm_trace.py): CTA 0 stamps %globaltimer at its pipeline events.
@@ -320,7 +322,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // Coalesced bf16 stores: the warp's (32 rows x 32 columns) chunk is transposed through shared memory so that one store
       // instruction writes 8 rows x 64 contiguous bytes (full sectors) instead of 32 rows x 16 bytes.  Lane l stores the
       // 16-byte piece (l & 3) of rows it*8 + (l >> 2); the row bookkeeping of those rows comes from their owner lanes.
-      const bool staged = !p.atomic_out && !p.out_f32 && !(p.epilogue & SST_EPI_ACCUM) && (p.ldc & 7) == 0;
+      const bool staged = !p.atomic_out && !p.out_f32 && !(p.epilogue & SST_EPI_ACCUM) && (p.ldc & 7) == 0 && p.out_seg_cols == 0;
       long st_row[4];
       bool st_ok[4];
 #pragma unroll
@@ -381,7 +383,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int i = 0; i < 32; ++i) v[i] = ((mb >> i) & 1u) ? v[i] * p.mask_scale : 0.f;
             }
           }
-          const long cb = out_row * p.ldc + nbase;
+          long cb = out_row * p.ldc + nbase;
+          if (p.out_seg_cols > 0) {             // the 32-column chunk never straddles a segment (segments are multiples of 32)
+            const int grp = nbase / p.out_grp_cols, nin = nbase - grp * p.out_grp_cols;
+            const int seg = nin / p.out_seg_cols;
+            cb = p.out_grp_off[grp] + (long)seg * p.out_seg_stride + out_row * p.ldc + (nin - seg * p.out_seg_cols);
+          }
           if (chunk_staged) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -627,6 +634,12 @@ int launch_gemm_tcgen05(const SstGemmDesc& d, const void* A, const void* B, void
   p.aux = aux; p.ldaux = d.ldaux; p.aux_f32 = d.aux_dtype == SST_F32;
   p.C = C; p.ldc = d.ldc; p.out_f32 = d.out_dtype == SST_F32;
   p.remap_P = d.remap_P; p.remap_T = d.remap_T; p.remap_j0 = d.remap_j0;
+  p.out_seg_cols = (int)d.out_seg_cols; p.out_grp_cols = (int)d.out_grp_cols; p.out_seg_stride = d.out_seg_stride;
+  for (int s = 0; s < 3; ++s) p.out_grp_off[s] = d.out_grp_off[s];
+  if (d.out_seg_cols > 0)
+    SST_REQUIRE(d.out_dtype == SST_F32 && d.out_seg_cols % 32 == 0 && d.out_grp_cols % d.out_seg_cols == 0 && d.N % 32 == 0 &&
+                cdiv(d.N, d.out_grp_cols) <= 3 && d.ldc % 4 == 0 && d.out_seg_stride % 4 == 0, SST_E_ARG,
+                "segmented output needs fp32 C, segments / groups of whole 32-column chunks and at most 3 groups");
   if (d.epilogue & SST_EPI_DROPOUT) SST_REQUIRE(d.N % 8 == 0, SST_E_ARG, "dropout epilogue needs N %% 8 == 0");
   // CTA pairs (256-row tiles) whenever there are at least two row blocks; SST_GEMM_CTAS=1 forces single-CTA tiles
   static const int ctas_env = [] { const char* e = getenv("SST_GEMM_CTAS"); return e ? atoi(e) : 2; }();

@@ -402,13 +402,19 @@ class Engine:
         return ds1
 
     def _qkv_wgrad(self, dproj, x, M, names, G):
-        """dW packed (len*H*dh, D) = dproj^T x, then accumulate into the per-head (H, D, dh) parameter gradients."""
+        """Weight gradients of the fused per-head projections, accumulated straight into the reference's (H, D, dh) layout of
+        w_q / w_k / w_v: C^T form  dW^T (D, len*H*dh) = x^T dproj  with segmented output columns (head h of tensor s lands at
+        G[names[s]] + h*D*dh, row pitch dh) -- no packed temporary, no permute launches."""
         D, H, dh = self.D, self.H, self.dh
         n = len(names)
-        dW = self.empty(n * D, D, dtype=torch.float32)
-        self.gemm(dproj, x, dW, n * D, D, M, dproj.stride(0), x.stride(0), D, layout=L.GEMM_NT_MN, a_cols=n * D, b_cols=D)
+        base = G[names[0]]
+        offs = [0, 0, 0]
         for s, name in enumerate(names):
-            L.permute3_cast(dW[s * D:], G[name], (H, D, dh), (dh * D, 1, D), (D * dh, dh, 1), accumulate=True)
+            g = G[name]
+            assert g.dtype == torch.float32 and g.is_contiguous() and (g.data_ptr() - base.data_ptr()) % 4 == 0
+            offs[s] = (g.data_ptr() - base.data_ptr()) // 4
+        self.gemm(x, dproj, base, D, n * D, M, x.stride(0), dproj.stride(0), dh, layout=L.GEMM_NT_MN, epilogue=L.EPI_ACCUM,
+                  a_cols=D, b_cols=n * D, out_seg=(dh, D * dh, H * dh, tuple(offs)))
 
     # ------------------------------------------------------------------------------------------------ decoder
     def _dec_layer_fwd(self, t, mem, B, S, Lm, tgt_lens, mem_lens, i, training, seeds, tgt_pad=None):

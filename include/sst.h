@@ -90,6 +90,13 @@ typedef struct SstGemmDesc {
   uint64_t seed;
   int32_t remap_P, remap_T, remap_j0;
   int32_t force_simt;  /* debugging / cross-check: run the CUDA-core kernel even for bf16 */
+  /* Segmented output columns (fp32 outputs; 0 = plain row-major C).  Column n of the result lands at
+   *   C + out_grp_off[n / out_grp_cols] + ((n % out_grp_cols) / out_seg_cols) * out_seg_stride + m * ldc + n % out_seg_cols
+   * (element offsets).  With out_seg_cols = dh, out_seg_stride = D*dh, ldc = dh, out_grp_cols = H*dh this writes the
+   * weight gradient of the fused per-head projections straight into the reference's (H, D, dh) parameter layout of
+   * w_q / w_k / w_v (transformer.py:146-149), one group per tensor -- no packed temporary, no permute.
+   * out_seg_cols and out_grp_cols must be multiples of 32, N a multiple of 32. */
+  int64_t out_seg_cols, out_seg_stride, out_grp_cols, out_grp_off[3];
 } SstGemmDesc;
 
 int sst_gemm(const SstGemmDesc* d, const void* A, const void* B, void* C, const void* bias /*fp32[N]*/,
