@@ -25,3 +25,28 @@ def test_reference_arm_prints_the_contract_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["unit"] == "frames/s" and cb["value"] == d["value"] and cb["sample"]
     e = d["e2e"]
     assert e["value"] == d["value"] and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_gpu_arm_prints_the_contract_line():
+    """The measured arm on one B200: device-resident value, end-to-end value from host buffers, launch count, clocks, the
+    dominant kernel's roofline entry.  Two timed steps after three warm-ups; the CPU baseline leg is skipped here."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "3", "--no-cpu-baseline"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["metric"].startswith("train EMG frames/s") and d["unit"] == "frames/s" and d["n_gpus"] == 1
+    assert d["steps"] == 2 and d["warmup"] == 3 and d["scaling"] == "weak" and d["dtype"] == "bf16" and d["vs_baseline"] is None
+    assert d["value"] > 5e5 and abs(d["value"] - 64000 / (d["ms_per_step"] / 1e3)) < 1e-3 * d["value"]
+    e = d["e2e"]
+    assert e["value"] > 5e5 and e["h2d_bytes_per_step"] > 1e7 and e["d2h_bytes_per_step"] == 12
+    assert d["gpu_launches"] > 100
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    r = d["roofline"]
+    assert r["bound"] in ("tensor", "hbm") and 0.0 < r["frac"] <= 1.0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
+    assert "workload" in d["config"] and "cfg2" in d["config"]["workload"]
