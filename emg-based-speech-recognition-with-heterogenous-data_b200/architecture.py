@@ -189,9 +189,8 @@ class Model(nn.Module):
         Fd = _flag("feed_forward_layer_size", 3072)
         R = _flag("relative_distance", 300)
         self.cfg = dict(d_model=D, d_ff=Fd, n_enc=_flag("num_layers_encoder", 6), n_dec=_flag("num_layers_decoder", 6),
-                        n_heads=_flag("n_heads_encoder", 8), rel_dist=R, dropout=_flag("dropout_model", .2),
-                        dropout_pos=_flag("dropout_pos_emb", .2))
-        assert _flag("n_heads_decoder", 8) == self.cfg["n_heads"], "the B200 path uses one head count for encoder and decoder"
+                        n_heads=_flag("n_heads_encoder", 8), n_heads_dec=_flag("n_heads_decoder", 8), rel_dist=R,
+                        dropout=_flag("dropout_model", .2), dropout_pos=_flag("dropout_pos_emb", .2))
         self.pad = _flag("pad", PAD)
         self.conv_blocks = nn.Sequential(ResBlock(8, D, 2), ResBlock(D, D, 2), ResBlock(D, D, 2))
         self.w_raw_in = nn.Linear(D, D)
@@ -199,7 +198,7 @@ class Model(nn.Module):
         self.embedding_tgt = nn.Embedding(num_outs_dec, D, padding_idx=self.pad)
         self.pos_decoder = PositionalEncoding(D)
         encoder_layer = TransformerEncoderLayer(D, self.cfg["n_heads"], Fd, R)
-        decoder_layer = TransformerDecoderLayer(D, self.cfg["n_heads"], Fd, R)
+        decoder_layer = TransformerDecoderLayer(D, self.cfg["n_heads_dec"], Fd, R)
         self.transformerEncoder = _LayerStack(encoder_layer, self.cfg["n_enc"])
         self.transformerDecoder = _LayerStack(decoder_layer, self.cfg["n_dec"])
         self.w_aux = nn.Linear(D, num_outs_enc)
@@ -218,12 +217,16 @@ class Model(nn.Module):
         self._seed_ctr = 0
         self._mem_lens = None
         self._mem_shape = None
+        self._weights_hooks = []           # called by weights_changed() (sst_b200.train.Trainer: refresh its bf16 shadow)
 
     # ---------------------------------------------------------------------------------------------- engine plumbing
     def weights_changed(self):
-        """Call after modifying parameters outside sst_b200.train (optimizer.step(), load_state_dict) so that the packed
-        GEMM operands are rebuilt.  `load_state_dict` and the drop-in forward call it automatically."""
+        """Force a rebuild of the packed GEMM operands at the next forward.  Not needed for the usual ways of changing
+        weights: in-place updates (torch optimizers, load_state_dict, p.data.copy_) are seen through the tensors' version
+        counters, sst_b200.train.Trainer repacks itself; only writes through raw pointers need this call."""
         self._weights_version += 1
+        for hook in self._weights_hooks:
+            hook()
 
     def load_state_dict(self, *a, **k):
         r = super().load_state_dict(*a, **k)
@@ -242,6 +245,7 @@ class Model(nn.Module):
                 if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
                     raise L.SstError("sst_b200.Model must live on a CUDA device in fp32 (parameter %s); call .to('cuda')" % n)
             self._param_names = list(params)
+            self._param_list = list(params.values())
             self._trainable = {n: not ("relative_positional" in n or n.startswith("emg_projection")) for n in params}
             self._engine = Engine({n: p.data for n, p in params.items()}, bufs, self.cfg, dtype=self.compute_dtype)
         return self._engine
@@ -251,9 +255,12 @@ class Model(nn.Module):
         self._engine = None                                      # parameter storage moved: rebuild views lazily
         return r
 
-    def _packed_engine(self, always=False):
+    def _packed_engine(self):
+        """The engine with GEMM operands that match the CURRENT parameter values.  A torch optimizer step, load_state_dict
+        or any other in-place write bumps the parameter tensors' version counters; the reference loop calls nothing between
+        optim.step() and the next forward (recognition_model.py:115-118, :126), so neither may this path."""
         eng = self.engine()
-        eng.pack(None if always else self._weights_version)
+        eng.pack((self._weights_version, tuple(p._version for p in self._param_list)))
         return eng
 
     def _unpad_logits(self, logits, B, Lx, C):
@@ -302,14 +309,14 @@ class Model(nn.Module):
     def forward_training(self, length_raw_signal, device, x_raw=None, y=None):
         self._check_input(x_raw)
         self._shift(x_raw)
-        self._packed_engine(always=torch.is_grad_enabled() and self.training)
+        self._packed_engine()
         lengths = [int(v) for v in length_raw_signal]
         self.tgt_key_padding_mask = self.create_tgt_padding_mask(y)
         params = [p for _, p in self.named_parameters()]
         return _StepFn.apply(self, x_raw, y.contiguous(), lengths, False, *params)
 
     def forward_search(self, part, length_raw_signal, device, x_raw=None, y=None, memory=None):
-        eng = self._packed_engine(always=torch.is_grad_enabled() and self.training)
+        eng = self._packed_engine()
         if part == 'encoder':
             self._check_input(x_raw)
             self._shift(x_raw)
@@ -324,15 +331,22 @@ class Model(nn.Module):
         if part == 'decoder':
             if self._mem_lens is None:
                 raise L.SstError("part='decoder' needs a preceding part='encoder' call (cached src_key_padding_mask)")
-            B, Lm = self._mem_shape
-            mem = memory.reshape(B * Lm, eng.D)
-            if mem.dtype != eng.dtype:
-                raise L.SstError("memory must be the tensor returned by the part='encoder' call")
+            B0, Lm = self._mem_shape
+            if memory.dim() != 3 or memory.shape[1] != Lm or memory.shape[2] != eng.D or memory.shape[0] % B0 != 0 \
+                    or memory.dtype != eng.dtype:
+                raise L.SstError("memory must be the tensor returned by the part='encoder' call (or memory.repeat(k, 1, 1) of it)")
+            # BeamSearch.py:111-114 decodes all hypotheses of an utterance as one batch of memory.repeat(n_hyp, 1, 1); the cached
+            # src_key_padding_mask (architecture.py:176) broadcasts over them, i.e. the memory lengths repeat the same way
+            B = memory.shape[0]
+            mem_lens = self._mem_lens if B == B0 else self._mem_lens.repeat(B // B0)
+            if y.shape[0] != B:
+                raise L.SstError("y has batch %d, memory has batch %d" % (y.shape[0], B))
+            mem = memory.contiguous().reshape(B * Lm, eng.D)
             y = y.contiguous()
             self.tgt_key_padding_mask = self.create_tgt_padding_mask(y)
             # search-time prefixes are generated, not padded: a PAD id may sit anywhere, so mask per position (:174,:178-183)
             tgt_pad = self.tgt_key_padding_mask.to(torch.uint8).contiguous()
             seeds = Engine._Seeds(self._next_seed())
-            x_dec = eng.decode(y, None, mem, self._mem_lens, B, Lm, self.training, seeds, tgt_pad=tgt_pad)
+            x_dec = eng.decode(y, None, mem, mem_lens, B, Lm, self.training, seeds, tgt_pad=tgt_pad)
             logits = eng.dec_head(x_dec, B * y.shape[1])
             return self._unpad_logits(logits, B, y.shape[1], eng.n_out_dec)

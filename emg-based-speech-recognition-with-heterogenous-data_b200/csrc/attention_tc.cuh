@@ -91,8 +91,9 @@ __device__ __forceinline__ void key_tile_range_valid(const AttnTcParams& p, int 
   const bool rows_unmasked = !p.mask_q_rows || (p.q_pad == nullptr && (p.q_lens == nullptr || i0 + BM <= p.q_lens[b]));
   if (p.k_lens != nullptr && rows_unmasked) {
     const int klen = p.k_lens[b];
-    const int t_valid = (max(klen, 1) - 1) / BN;          // last tile that holds a real key
-    t_hi = max(t_lo, min(t_hi, t_valid));
+    // klen == 0 (an empty memory): EVERY key is masked and the reference's softmax is uniform over all Lk of them -- no
+    // tile may be skipped then
+    if (klen > 0) t_hi = max(t_lo, min(t_hi, (klen - 1) / BN));      // (klen - 1) / BN: last tile that holds a real key
   }
 }
 // query tiles [q_lo, q_hi] (of BM rows) a key tile starting at j0 receives contributions from

@@ -42,6 +42,8 @@ class Engine:
         self.F = cfg["d_ff"]
         self.H = cfg["n_heads"]
         self.dh = self.D // self.H
+        self.Hd = cfg.get("n_heads_dec", self.H)          # FLAGS.n_heads_decoder (architecture.py:17); head dims other than 96
+        self.dhd = self.D // self.Hd                      # run on the CUDA-core attention kernels
         self.R = cfg["rel_dist"]
         self.n_enc = cfg["n_enc"]
         self.n_dec = cfg["n_dec"]
@@ -54,7 +56,7 @@ class Engine:
         self._packed_version = None
         self._bn_scratch = torch.empty(3 * self.D, dtype=torch.float64, device=self.dev)
         self._side = None                  # side stream for work that can run under the decoder (CTC)
-        assert self.D % 64 == 0 and self.dh % 8 == 0
+        assert self.D % 64 == 0 and self.dh % 8 == 0 and self.dhd % 8 == 0 and self.dhd * self.Hd == self.D
 
     # ------------------------------------------------------------------------------------------------ utils
     def empty(self, *shape, dtype=None):
@@ -241,9 +243,10 @@ class Engine:
                         G[prefix + ".weight"], G[prefix + ".bias"])
         return ds, (dr if p > 0 else ds)
 
-    def _attn_desc(self, B, Lq, Lk, ldq, ldk, ldv, causal, mask_q_rows, R, p, seed, q_pad=None, k_pad=None):
-        return L.attn_desc(self.dt, B, self.H, Lq, Lk, self.dh, ldq, ldk, ldv, self.D, causal, mask_q_rows, R,
-                           1.0 / math.sqrt(self.dh), p, seed, self.force_simt, q_pad=q_pad, k_pad=k_pad)
+    def _attn_desc(self, B, Lq, Lk, ldq, ldk, ldv, causal, mask_q_rows, R, p, seed, q_pad=None, k_pad=None, dec=False):
+        H, dh = (self.Hd, self.dhd) if dec else (self.H, self.dh)
+        return L.attn_desc(self.dt, B, H, Lq, Lk, dh, ldq, ldk, ldv, self.D, causal, mask_q_rows, R,
+                           1.0 / math.sqrt(dh), p, seed, self.force_simt, q_pad=q_pad, k_pad=k_pad)
 
     # ------------------------------------------------------------------------------------------------ conv front-end
     def _bn_stats(self, x, rows, ld, prefix, training):
@@ -401,11 +404,12 @@ class Engine:
         self.gemm(dqkv, self.pk[a + ".qkv.T"], ds1, M, D, 3 * D, 3 * D, 3 * D, D, epilogue=L.EPI_ACCUM)
         return ds1
 
-    def _qkv_wgrad(self, dproj, x, M, names, G):
+    def _qkv_wgrad(self, dproj, x, M, names, G, dec=False):
         """Weight gradients of the fused per-head projections, accumulated straight into the reference's (H, D, dh) layout of
         w_q / w_k / w_v: C^T form  dW^T (D, len*H*dh) = x^T dproj  with segmented output columns (head h of tensor s lands at
         G[names[s]] + h*D*dh, row pitch dh) -- no packed temporary, no permute launches."""
-        D, H, dh = self.D, self.H, self.dh
+        D = self.D
+        H, dh = (self.Hd, self.dhd) if dec else (self.H, self.dh)
         n = len(names)
         base = G[names[0]]
         offs = [0, 0, 0]
@@ -424,16 +428,16 @@ class Engine:
         a, m = pfx + ".self_attn", pfx + ".multihead_attn"
         qkv = self._linear_fwd(t, M, a + ".qkv")
         o1 = self.empty(M, D)
-        lse1 = self.empty(2 * B * self.H * S, dtype=torch.float32)
-        ad1 = self._attn_desc(B, S, S, 3 * D, 3 * D, 3 * D, True, True, 0, p, seeds(), q_pad=tgt_pad, k_pad=tgt_pad)
+        lse1 = self.empty(2 * B * self.Hd * S, dtype=torch.float32)
+        ad1 = self._attn_desc(B, S, S, 3 * D, 3 * D, 3 * D, True, True, 0, p, seeds(), q_pad=tgt_pad, k_pad=tgt_pad, dec=True)
         L.attn_fwd(ad1, qkv, qkv[:, D:], qkv[:, 2 * D:], None, tgt_lens, tgt_lens, o1, lse1)
         y = self._linear_fwd(o1, M, a + ".o.T")
         t1, ln1 = self._ln_fwd(t, y, M, pfx + ".norm1", p, seeds())
         q = self._linear_fwd(t1, M, m + ".q")
         kv = self._linear_fwd(mem, Mm, m + ".kv")
         o2 = self.empty(M, D)
-        lse2 = self.empty(2 * B * self.H * S, dtype=torch.float32)
-        ad2 = self._attn_desc(B, S, Lm, D, 2 * D, 2 * D, False, False, 0, p, seeds())
+        lse2 = self.empty(2 * B * self.Hd * S, dtype=torch.float32)
+        ad2 = self._attn_desc(B, S, Lm, D, 2 * D, 2 * D, False, False, 0, p, seeds(), dec=True)
         L.attn_fwd(ad2, q, kv, kv[:, D:], None, None, mem_lens, o2, lse2)
         y2 = self._linear_fwd(o2, M, m + ".o.T")
         t2, ln2 = self._ln_fwd(t1, y2, M, pfx + ".norm2", p, seeds())
@@ -460,11 +464,11 @@ class Engine:
         self.gemm(dy2, self.pk[m + ".o"], dO2, M, D, D, D, D, D)
         dq = self.empty(M, D)
         dkv = self.empty(Mm, 2 * D)
-        delta = self.empty(B * self.H * S, dtype=torch.float32)
+        delta = self.empty(B * self.Hd * S, dtype=torch.float32)
         L.attn_bwd(c.ad2, c.q, c.kv, c.kv[:, D:], None, None, mem_lens, c.o2, c.lse2, dO2, dq, dkv, dkv[:, D:], delta)
-        self._qkv_wgrad(dq, c.t1, M, [m + ".w_q"], G)
+        self._qkv_wgrad(dq, c.t1, M, [m + ".w_q"], G, dec=True)
         self.gemm(dq, self.pk[m + ".q.T"], ds2, M, D, D, D, D, D, epilogue=L.EPI_ACCUM)
-        self._qkv_wgrad(dkv, mem, Mm, [m + ".w_k", m + ".w_v"], G)
+        self._qkv_wgrad(dkv, mem, Mm, [m + ".w_k", m + ".w_v"], G, dec=True)
         self.gemm(dkv, self.pk[m + ".kv.T"], dmem, Mm, D, 2 * D, 2 * D, 2 * D, D, epilogue=L.EPI_ACCUM)
         ds1, dy1 = self._ln_bwd(ds2, c.ln1, M, pfx + ".norm1", G)
         # self attention
@@ -474,7 +478,7 @@ class Engine:
         dqkv = self.empty(M, 3 * D)
         L.attn_bwd(c.ad1, c.qkv, c.qkv[:, D:], c.qkv[:, 2 * D:], None, tgt_lens, tgt_lens, c.o1, c.lse1, dO1,
                    dqkv, dqkv[:, D:], dqkv[:, 2 * D:], delta)
-        self._qkv_wgrad(dqkv, c.t, M, [a + ".w_q", a + ".w_k", a + ".w_v"], G)
+        self._qkv_wgrad(dqkv, c.t, M, [a + ".w_q", a + ".w_k", a + ".w_v"], G, dec=True)
         self.gemm(dqkv, self.pk[a + ".qkv.T"], ds1, M, D, 3 * D, 3 * D, 3 * D, D, epilogue=L.EPI_ACCUM)
         return ds1
 
@@ -547,7 +551,7 @@ class Engine:
         is generated (a PAD position is masked as a key AND as a query row there, which makes earlier rows depend on the
         prefix length) -- the caller checks and falls back.  Arg-max, append and the stop test stay on the device; the host
         looks at the `done` flags every `check_every` steps.  Returns the (B, n) int64 device tensor of prefixes."""
-        D, H = self.D, self.H
+        D, H = self.D, self.Hd
         Tmax = max_seq_length - 1                                   # decoder input positions
         tokens = torch.full((B, max_seq_length), PAD, dtype=torch.int64, device=self.dev)
         tokens[:, 0] = start_tok
@@ -573,13 +577,13 @@ class Engine:
                 L.permute3_cast(qkv[:, D:], kv_s, (1, B, 2 * D), (0, 3 * D, 1), (0, Tmax * 2 * D, 1))
                 o1 = self.empty(B, D)
                 lse = self.empty(2 * B * H, dtype=torch.float32)
-                ad1 = self._attn_desc(B, 1, Tmax, 3 * D, 2 * D, 2 * D, False, False, 0, 0.0, 0)
+                ad1 = self._attn_desc(B, 1, Tmax, 3 * D, 2 * D, 2 * D, False, False, 0, 0.0, 0, dec=True)
                 L.attn_fwd(ad1, qkv, cache[i], cache[i][:, D:], None, None, klen, o1, lse)
                 y1 = self._linear_fwd(o1, B, a + ".o.T")
                 t1, _ = self._ln_fwd(t, y1, B, pfx + ".norm1", 0.0, 0)
                 q = self._linear_fwd(t1, B, m + ".q")
                 o2 = self.empty(B, D)
-                ad2 = self._attn_desc(B, 1, Lm, D, 2 * D, 2 * D, False, False, 0, 0.0, 0)
+                ad2 = self._attn_desc(B, 1, Lm, D, 2 * D, 2 * D, False, False, 0, 0.0, 0, dec=True)
                 L.attn_fwd(ad2, q, cross[i], cross[i][:, D:], None, None, mem_lens, o2, lse)
                 y2 = self._linear_fwd(o2, B, m + ".o.T")
                 t2, _ = self._ln_fwd(t1, y2, B, pfx + ".norm2", 0.0, 0)

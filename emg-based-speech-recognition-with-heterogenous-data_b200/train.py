@@ -121,6 +121,42 @@ class FlatState:
         self.g.zero_()
 
 
+class AccumulationGate:
+    """When to step (recognition_model.py:81,115-118: accumulate micro-batch gradients until the number of 1600-sample chunks
+    seen reaches batch_size_grad) -- decided IDENTICALLY on every rank.  Ranks hold different utterances, so their local
+    chunk counts differ; a rank deciding from its own count would enter the gradient all-reduce while another keeps
+    accumulating (hang, diverged weights).  The count that is thresholded is therefore the sum over ranks -- what
+    `len(X)` was for the whole batch under the reference's nn.DataParallel -- exchanged through a host-side (gloo) group so
+    that no device synchronisation enters the step.  `global_chunks` short-circuits the exchange when the caller already
+    knows every rank's batch (a shared DynamicBatchSampler)."""
+
+    def __init__(self, batch_size_grad, distributed=False):
+        self.batch_size_grad = batch_size_grad
+        self.sum_batch_size = 0
+        self.group = None
+        self.dist = None
+        if distributed:
+            import torch.distributed as dist
+            self.dist = dist
+            if dist.is_initialized() and dist.get_world_size() > 1:
+                self.group = dist.group.WORLD if dist.get_backend() == "gloo" else dist.new_group(backend="gloo")
+
+    def add(self, local_chunks, global_chunks=None):
+        """Account one micro-batch; True when the optimizer must step after it (and the count restarts)."""
+        if global_chunks is None:
+            if self.group is not None:
+                t = torch.tensor([int(local_chunks)], dtype=torch.int64)
+                self.dist.all_reduce(t, group=self.group)
+                global_chunks = int(t[0])
+            else:
+                global_chunks = int(local_chunks)
+        self.sum_batch_size += global_chunks
+        if self.sum_batch_size >= self.batch_size_grad:
+            self.sum_batch_size = 0
+            return True
+        return False
+
+
 class GradSync:
     def __init__(self, flat, n_enc, n_dec, bucket_bytes=25 << 20, group=None):
         import torch.distributed as dist
@@ -146,6 +182,15 @@ class GradSync:
         self.stream = torch.cuda.Stream() if self.cuda else None
         self._next = 0
         self._pending = []
+
+    def broadcast_state(self, tensors):
+        """Every rank starts from rank 0's parameters / optimizer moments (nn.DataParallel replicated module 0 on every
+        forward, recognition_model.py:284); without this ranks agree only if the caller seeded them identically."""
+        if self.world == 1:
+            return
+        for t in tensors:
+            if t is not None:
+                self.dist.broadcast(t, src=0, group=self.group)
 
     def begin(self):
         self._next = 0
@@ -193,16 +238,23 @@ class Trainer:
         self.lr_target, self.warmup = learning_rate, learning_rate_warmup
         self.lr = learning_rate
         self.alpha, self.eps_ls = alpha_loss, eps_ls
-        self.batch_size_grad = batch_size_grad
         self.wd = weight_decay
         model.engine()
         self.flat = FlatState(model)
         self.eng = model.engine()
         self.eng.shadow = self.flat.shadow
         self.eng.pack()
+        # Model.load_state_dict / weights_changed() write the fp32 masters only: refresh the bf16 shadow the GEMM operands
+        # are views of before the next repack
+        model._weights_hooks.append(self._refresh_shadow)
         self.sync = GradSync(self.flat, self.eng.n_enc, self.eng.n_dec, bucket_bytes) if distributed else None
+        if self.sync is not None:
+            self.sync.broadcast_state([self.flat.p, self.flat.m, self.flat.v, self.flat.pb] +
+                                      [p.data for n, p in model.named_parameters() if not model._trainable[n]] +
+                                      [b for b in model.buffers() if b.is_floating_point()])
+            self.eng.pack()
+        self.gate = AccumulationGate(batch_size_grad, distributed)
         self.batch_idx = 0
-        self.sum_batch_size = 0
         self.seed = seed
         self.dev = self.flat.p.device
         self._host_loss = torch.zeros(3, dtype=torch.float32).pin_memory() if self.dev.type == "cuda" else torch.zeros(3)
@@ -218,7 +270,7 @@ class Trainer:
         model_sd = {pre + k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()}
         return {"model": model_sd,
                 "optim": {"names": list(self.flat.names), "m": self.flat.m.cpu().clone(), "v": self.flat.v.cpu().clone(),
-                          "step_count": self.flat.step_count, "batch_idx": self.batch_idx, "sum_batch_size": self.sum_batch_size,
+                          "step_count": self.flat.step_count, "batch_idx": self.batch_idx, "sum_batch_size": self.gate.sum_batch_size,
                           "g": self.flat.g.cpu().clone(), "lr": self.lr}}
 
     def load_state_dict(self, sd):
@@ -229,12 +281,23 @@ class Trainer:
             if list(o["names"]) != list(self.flat.names):
                 raise L.SstError("optimizer state belongs to a different model configuration")
             self.flat.m.copy_(o["m"]); self.flat.v.copy_(o["v"]); self.flat.g.copy_(o["g"])
-            self.flat.step_count, self.batch_idx, self.sum_batch_size = o["step_count"], o["batch_idx"], o["sum_batch_size"]
+            self.flat.step_count, self.batch_idx, self.gate.sum_batch_size = o["step_count"], o["batch_idx"], o["sum_batch_size"]
             self.lr = o["lr"]
         if self.flat.pb is not None:
             self.flat.pb.copy_(self.flat.p)                      # refresh the bf16 shadow of the GEMM operands
         self.eng.pack()
         self.model._weights_version += 1
+
+    def _refresh_shadow(self):
+        if self.flat.pb is not None:
+            self.flat.pb.copy_(self.flat.p)
+        self.eng._packed_version = None
+
+    def start_epoch(self):
+        """The reference zeroes the gradients and the accumulated chunk count at the top of every epoch
+        (recognition_model.py:67-68), dropping a partial accumulation; call this where the reference enters training_loop()."""
+        self.flat.zero_grad()
+        self.gate.sum_batch_size = 0
 
     def schedule_lr(self, iteration):
         """recognition_model.py:57-64."""
@@ -256,15 +319,28 @@ class Trainer:
         return d
 
     # ---- one micro-batch (recognition_model.py:69-118) -----------------------------------------------------------------
-    def step_device(self, dev_batch, shift_r=None):
+    @property
+    def batch_size_grad(self):
+        return self.gate.batch_size_grad
+
+    @batch_size_grad.setter
+    def batch_size_grad(self, v):
+        self.gate.batch_size_grad = v
+
+    @property
+    def sum_batch_size(self):
+        return self.gate.sum_batch_size
+
+    def step_device(self, dev_batch, shift_r=None, global_chunks=None):
         """forward + loss + backward (+ optimizer when the accumulation threshold is reached) on device-resident inputs.
-        Returns the float32[3] device tensor (loss, loss_dec, loss_enc)."""
+        Returns the float32[3] device tensor (loss, loss_dec, loss_enc).  `global_chunks`: chunks of this micro-step summed
+        over all ranks when the caller knows it (AccumulationGate)."""
         import random
         model, eng, flat = self.model, self.eng, self.flat
         model.train()
         self.schedule_lr(self.batch_idx)
         X = dev_batch['X']
-        self.sum_batch_size += X.shape[0]
+        will_step = self.gate.add(X.shape[0], global_chunks)          # the same decision on every rank
         r = random.randrange(8) if shift_r is None else shift_r       # architecture.py:105
         if r > 0:
             L.shift_left(X, X.shape[0], X.shape[1], X.shape[2], r)
@@ -275,7 +351,6 @@ class Trainer:
                                 ctc=(dev_batch['ctc_tgt'], dev_batch['ctc_lens'], self.alpha if has_dec else 1.0))
         losses = eng.losses(ctx, dev_batch['ctc_tgt'], dev_batch['ctc_lens'], dev_batch['tgt_out'] if has_dec else None,
                             dev_batch['n_valid'], self.alpha, self.eps_ls)
-        will_step = self.sum_batch_size >= self.batch_size_grad
         if self.sync is not None and will_step:
             self.sync.begin()
             eng.backward(ctx, flat.G_all, on_stage=self.sync.on_stage)
@@ -286,7 +361,6 @@ class Trainer:
             flat.step_count += 1
             L.adamw(flat.p, flat.g, flat.m, flat.v, flat.numel, self.lr, 0.9, 0.999, 1e-8, self.wd, flat.step_count, flat.pb)
             flat.zero_grad()
-            self.sum_batch_size = 0
             eng.pack()
             model._weights_version += 1
         self.batch_idx += 1

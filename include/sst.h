@@ -187,7 +187,8 @@ int sst_attn_bwd(const SstAttnDesc* d, const void* q, const void* k, const void*
  *      states spread over the lanes, the utterance's log-probs staged in shared memory); the gradient is written
  *      directly w.r.t. the raw logits (softmax - occupancy), scaled by gcoef, zero for t >= in_lens[b].
  *      Workspaces: lp_ws float[B*L*C], alpha_ws float[2*B*L*(2*Smax+1)] (alpha then beta lattice), nll float[B].
- *      targets: int64 (B, Smax).
+ *      targets: int64 (B, Smax), Smax <= 255 (the lattice of 2*Smax+1 states is spread over one warp's registers; the
+ *      reference accepts any length, its corpus has <= ~120 phones per utterance): longer targets return SST_E_ARG.
  *  sst_ce_sumexp_loss : LabelSmoothingLoss.py:13-15 -- (1-eps)*CE(ignore_index, mean over kept) + eps/S*sum(exp(logits)),
  *      the sum running over every row including ignored ones; S = target length; gradient scaled by gcoef.
  *      row_ws float[2*rows].

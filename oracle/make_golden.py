@@ -33,6 +33,13 @@ CASES = {
     # L < R branch of the rel-pos module (start_pos > 0, no -1e8 edges) and L not multiple of anything
     "short_hybrid": dict(cfg=O.make_cfg(n_enc=1, n_dec=1, rel_dist=100, alpha=0.2), wseed=2,
                          batch=dict(seed=99, ragged=[70, 100, 30], tgt_lens=[9, 14, 5]), mode="hybrid"),
+    # the benchmarked shape (BASELINE.json configs[1]): utterances of 1000 frames -- banded attention over 8 query tiles with
+    # skipped key tiles, R = 100 -- with one ragged utterance (padded query rows / keys), 2 + 1 layers
+    "full_2p1": dict(cfg=O.make_cfg(n_enc=2, n_dec=1, rel_dist=100, alpha=0.2), wseed=3,
+                     batch=dict(seed=77, ragged=[1000, 777, 1000], tgt_lens=[60, 45, 52]), mode="hybrid"),
+    # the benchmarked MODEL (6 + 6 layers, d768 h8 ffn3072 R100) at the benchmarked utterance length, batch 2
+    "full_6p6": dict(cfg=O.make_cfg(n_enc=6, n_dec=6, rel_dist=100, alpha=0.2), wseed=4,
+                     batch=dict(n_utt=2, frames=1000, tgt_len=100, seed=78), mode="hybrid"),
 }
 
 
@@ -119,6 +126,35 @@ def run_case(name, case):
     out["out_enc_truth"] = r64["out_enc"].numpy().astype(np.float32)
     out["loss_truth"] = np.float64(r64["loss"].item())
     none_grad = [n for n, p in model.named_parameters() if p.grad is None]
+    # The same UNMODIFIED reference step under torch.autocast(bfloat16) -- PyTorch's own bf16 mode of the reference code
+    # (matmul / conv / linear operands rounded to bf16, normalisations and losses in fp32).  Its distance from the fp32
+    # reference is the noise floor of ANY bf16 evaluation of this network: a pre-activation within bf16 rounding of zero flips
+    # its ReLU mask bit and moves the gradient by a whole term.  The bf16-mode parity test uses it as the yardstick for the
+    # tensors behind ReLU / BatchNorm kinks (tests/helpers.check_grads_l2).
+    model_bf = ref_harness.build_model(ref_cfg, sd)
+    model_bf.train()
+    arch.random.randrange = lambda n: 0
+    Xb = du.combine_fixed_length(batch["raw_emg"], 1600).clone()
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        if case["mode"] == "encoder":
+            _, oe_bf = model_bf(batch["lengths"], "cpu", x_raw=Xb, mode="greedy_search", part="encoder")
+            od_bf = None
+        else:
+            oe_bf, od_bf = model_bf(batch["lengths"], "cpu", x_raw=Xb, y=tgt_in)
+    oe_bf = oe_bf.float()
+    l_bf = F.ctc_loss(F.log_softmax(oe_bf, 2).transpose(1, 0), ctc_tgt, batch["lengths"], ctc_lens, blank=43)
+    out["loss_enc_bf16"] = np.float64(l_bf.item())
+    if od_bf is not None:
+        ld_bf = LS.LabelSmoothingLoss(epsilon=cfg["eps_ls"], num_classes=43)(od_bf.float().permute(0, 2, 1), tgt_out)
+        out["loss_dec_bf16"] = np.float64(ld_bf.item())
+        l_bf = (1 - cfg["alpha"]) * ld_bf + cfg["alpha"] * l_bf
+    l_bf.backward()
+    arch.random.randrange = real_randrange
+    bfp = dict(model_bf.named_parameters())
+    for pname in names:
+        out["gbf16/" + pname] = bfp[pname].grad.detach().float().reshape(-1).numpy()[out["gidx/" + pname]].astype(np.float32)
+    out["out_enc_bf16_err"] = np.float64(float((oe_bf.detach() - out_enc.detach()).abs().max() / out_enc.detach().abs().max()))
+    del model_bf, bfp
     msd = model.state_dict()
     for k in msd:
         if k.endswith("running_mean") or k.endswith("running_var"):

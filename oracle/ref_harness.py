@@ -68,7 +68,7 @@ def cfg_to_argv(cfg):
             "--num_layers_encoder=%d" % cfg["n_enc"],
             "--num_layers_decoder=%d" % cfg["n_dec"],
             "--n_heads_encoder=%d" % cfg["n_heads"],
-            "--n_heads_decoder=%d" % cfg["n_heads"],
+            "--n_heads_decoder=%d" % cfg.get("n_heads_dec", cfg["n_heads"]),
             "--relative_distance=%d" % cfg["rel_dist"],
             "--dropout_model=%g" % cfg.get("dropout", 0.0),
             "--dropout_pos_emb=%g" % cfg.get("dropout_pos", 0.0)]

@@ -81,6 +81,8 @@ def state_dict_spec(cfg, num_features=112, n_out_enc=44, n_out_dec=43):
                  ("pos_decoder.pe", (5000, 1, D), "pe")])
 
     def mha(prefix, relpos):
+        H = cfg["n_heads"] if relpos else cfg.get("n_heads_dec", cfg["n_heads"])      # architecture.py:16-17
+        dh = D // H
         for w in ("w_q", "w_k", "w_v"):
             spec.append((prefix + "." + w, (H, D, dh), "xavier"))
         spec.append((prefix + ".w_o", (H, dh, D), "xavier"))
@@ -217,16 +219,29 @@ def batch_norm(x, sd, prefix, training, stats_out=None, momentum=0.1, eps=1e-5):
     return y
 
 
+RELU_MASKS = None
+"""Test hook (tests/test_engine_gpu.py::test_bf16_gradients_with_aligned_relu_masks): when set to a dict
+{site: bool tensor}, the ReLU at `site` multiplies by that mask instead of by (x > 0).  Sites and layouts:
+'conv_blocks.i.relu1' / '.relu2' (n, C, T); 'transformerEncoder.layers.i.relu' (L, B, F);
+'transformerDecoder.layers.i.relu' (S, B, F).  None (the default) = the reference's F.relu."""
+
+
+def _relu(x, site):
+    if RELU_MASKS is None:
+        return F.relu(x)
+    return x * RELU_MASKS[site].to(x.dtype)
+
+
 def res_block(x, sd, prefix, stride, training, stats_out=None):
     """ResBlock.forward, architecture.py:37-48."""
     inp = x
     x = F.conv1d(x, sd[prefix + ".conv1.weight"], sd[prefix + ".conv1.bias"], stride=stride, padding=1)
-    x = F.relu(batch_norm(x, sd, prefix + ".bn1", training, stats_out))
+    x = _relu(batch_norm(x, sd, prefix + ".bn1", training, stats_out), prefix + ".relu1")
     x = F.conv1d(x, sd[prefix + ".conv2.weight"], sd[prefix + ".conv2.bias"], stride=1, padding=1)
     x = batch_norm(x, sd, prefix + ".bn2", training, stats_out)
     res = F.conv1d(inp, sd[prefix + ".residual_path.weight"], sd[prefix + ".residual_path.bias"], stride=stride)
     res = batch_norm(res, sd, prefix + ".res_norm", training, stats_out)
-    return F.relu(x + res)
+    return _relu(x + res, prefix + ".relu2")
 
 
 def conv_frontend(x_raw, sd, training, stats_out=None):
@@ -326,7 +341,7 @@ def encoder_layer(src, sd, prefix, cfg, training, kpm, as_written=True):
     src2 = multi_head_attention(src, src, src, sd, prefix + ".self_attn", cfg, training, True,
                                 src_key_padding_mask=kpm, as_written=as_written)
     src = layer_norm(src + F.dropout(src2, p, training), sd, prefix + ".norm1")
-    h = F.dropout(F.relu(F.linear(src, sd[prefix + ".linear1.weight"], sd[prefix + ".linear1.bias"])), p, training)
+    h = F.dropout(_relu(F.linear(src, sd[prefix + ".linear1.weight"], sd[prefix + ".linear1.bias"]), prefix + ".relu"), p, training)
     src2 = F.linear(h, sd[prefix + ".linear2.weight"], sd[prefix + ".linear2.bias"])
     return layer_norm(src + F.dropout(src2, p, training), sd, prefix + ".norm2")
 
@@ -340,7 +355,7 @@ def decoder_layer(tgt, memory, sd, prefix, cfg, training, tgt_mask, tgt_kpm, mem
     t2 = multi_head_attention(tgt, memory, memory, sd, prefix + ".multihead_attn", cfg, training, False,
                               memory_key_padding_mask=mem_kpm)
     tgt = layer_norm(tgt + F.dropout(t2, p, training), sd, prefix + ".norm2")
-    h = F.dropout(F.relu(F.linear(tgt, sd[prefix + ".linear1.weight"], sd[prefix + ".linear1.bias"])), p, training)
+    h = F.dropout(_relu(F.linear(tgt, sd[prefix + ".linear1.weight"], sd[prefix + ".linear1.bias"]), prefix + ".relu"), p, training)
     t2 = F.linear(h, sd[prefix + ".linear2.weight"], sd[prefix + ".linear2.bias"])
     return layer_norm(tgt + F.dropout(t2, p, training), sd, prefix + ".norm3")
 

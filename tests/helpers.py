@@ -31,48 +31,76 @@ def rel_err(a, b, floor=0.0):
     return float((a - b).abs().max()) / denom
 
 
-KINK_SENSITIVE = ("conv_blocks.", ".linear1.")
+GOLDEN_CASES = ["short_hybrid", "ragged_hybrid", "cfg1_enc_ctc", "full_2p1", "full_6p6"]
+F64_SLACK = 3.0        # a tensor may sit this many times further from float64 arithmetic than the reference's own fp32 does
+BF16_SLACK = 2.5       # ... / from the fp32 reference than the reference's own torch.autocast(bfloat16) evaluation does (mask flips are a
+                       # random draw per evaluation: two bf16 evaluations of one tensor differ by up to ~2x in this distance)
 
 
-def kink_sensitive(name):
-    """Tensors whose gradient passes through a ReLU mask and/or training-mode BatchNorm statistics.  A pre-activation
-    within rounding distance of 0 flips its mask bit and changes the gradient by a whole term, and BN-backward subtracts
-    two nearly equal sums, so ANY two valid evaluations (reference fp32 vs float64, tensor-core vs CUDA-core bf16)
-    differ on them by far more than their rounding unit -- see DESIGN.md "Parity bars"."""
-    return any(k in name for k in KINK_SENSITIVE)
+def _l2(a):
+    return float(np.sqrt((np.asarray(a, dtype=np.float64) ** 2).sum()))
 
 
-def check_grads_against_golden(z, meta, grads, tol, label="", slack=3.0, report=None, kink_tol=None):
-    """grads: dict name -> tensor.  Per tensor, with e(a,b) = max|a-b| / max(max|b|, 1e-4 * global grad max):
-         pass  iff  e(mine, reference) <= tol
-               or   e(mine, truth64)   <= slack * e(reference, truth64) + tol
-               or   kink_sensitive(name) and e(mine, reference) <= kink_tol
-    The second clause covers tensors whose gradient the reference's own fp32 arithmetic only resolves to worse than
-    `tol` (BatchNorm/LayerNorm-backward cancellation; true gradient of conv biases in front of BN is exactly zero,
-    SURVEY.md Q7): there the yardstick is the reference's own distance from exact (float64) arithmetic."""
-    gmax = max(float(z["gstat/" + n][0]) for n in meta["grad_names"])
-    floor = 1e-4 * gmax
-    worst = (0.0, None)
-    for n in meta["grad_names"]:
+def l2_rows(names, mine, ref, truth, bf16, gmax):
+    """[(name, e_ref, e_truth, e_ref_truth, e_bf16)] with e(a, b) = ||a - b||_2 / max(||ref||_2, 1e-4 * gmax * sqrt(#entries));
+    `mine/ref/truth/bf16` map a name to a 1-D float64 numpy array (truth / bf16 may be None)."""
+    rows = []
+    for n in names:
+        r = ref[n]
+        den = max(_l2(r), 1e-4 * gmax * np.sqrt(r.size))
+        rows.append((n, _l2(mine[n] - r) / den,
+                     _l2(mine[n] - truth[n]) / den if truth is not None else float("inf"),
+                     _l2(r - truth[n]) / den if truth is not None else 0.0,
+                     _l2(bf16[n] - r) / den if bf16 is not None else 0.0))
+    return rows
+
+
+def l2_verdict(row, tol, bf16_mode):
+    """'ref' (within tol of the reference), 'f64' / 'bf16' (one of the two yardstick clauses) or None (fail)."""
+    n, e_ref, e_truth, e_rt, e_bf = row
+    if e_ref <= tol:
+        return "ref"
+    if e_truth <= F64_SLACK * e_rt + tol:
+        return "f64"
+    if bf16_mode and e_ref <= BF16_SLACK * e_bf + tol:
+        return "bf16"
+    return None
+
+
+def grad_l2_table(z, meta, grads):
+    """l2_rows() of an engine gradient dict against a golden fixture, over the fixture's sampled entries (the whole tensor
+    when it has <= 4096 elements)."""
+    names = meta["grad_names"]
+    gmax = max(float(z["gstat/" + n][0]) for n in names)
+    mine = {}
+    for n in names:
         assert n in grads, "missing gradient for %s" % n
-        g = grads[n].detach().double().cpu().reshape(-1).numpy()
-        idx = z["gidx/" + n]
-        ref = z["gval/" + n].astype(np.float64)
-        truth = z["gtruth/" + n].astype(np.float64)
-        denom = max(float(z["gstat/" + n][0]), floor)
-        e_ref = float(np.abs(g[idx] - ref).max()) / denom
-        e_truth = float(np.abs(g[idx] - truth).max()) / denom
-        e_ref_truth = float(np.abs(ref - truth).max()) / denom
-        if report is not None:
-            report.append((n, e_ref, e_truth, e_ref_truth))
-        ok = e_ref <= tol or e_truth <= slack * e_ref_truth + tol
-        if not ok and kink_tol is not None and kink_sensitive(n):
-            ok = e_ref <= kink_tol
-        score = min(e_ref / tol, e_truth / (slack * e_ref_truth + tol))
-        if score > worst[0]:
-            worst = (score, n)
-        assert ok, ("%s grad %s: vs reference %.3e, vs float64 truth %.3e (reference itself %.3e), tol %.1e"
-                    % (label, n, e_ref, e_truth, e_ref_truth, tol))
+        mine[n] = grads[n].detach().double().cpu().reshape(-1).numpy()[z["gidx/" + n]]
+    f = lambda pre: {n: z[pre + n].astype(np.float64) for n in names}      # noqa: E731
+    return l2_rows(names, mine, f("gval/"), f("gtruth/"), f("gbf16/") if ("gbf16/" + names[0]) in z.files else None, gmax)
+
+
+def assert_l2_rows(rows, tol, bf16_mode, label=""):
+    bad = [r for r in rows if l2_verdict(r, tol, bf16_mode) is None]
+    assert not bad, "%s: %d tensors outside %.0e relative L2: %s" % (
+        label, len(bad), tol, "; ".join("%s vs ref %.2e, vs f64 %.2e (ref itself %.2e), autocast-bf16 ref %.2e" % b for b in bad[:6]))
+    return max(rows, key=lambda r: r[1])
+
+
+def check_grads_l2(z, meta, grads, tol, bf16_mode, label=""):
+    """EVERY trainable tensor (conv_blocks.* and linear1 included) in per-tensor relative L2 at north_star's tolerance
+    (1e-4 fp32 mode, 2e-2 bf16 mode) against the UNMODIFIED reference's gradient.  A tensor passes iff
+        ||mine - reference|| <= tol * den                                                          or
+        ||mine - float64||   <= 3 * ||reference - float64|| + tol * den                             or, in bf16 mode only,
+        ||mine - reference|| <= 2.5 * ||reference under torch.autocast(bfloat16) - reference|| + tol * den.
+    Second clause: tensors the reference's own fp32 arithmetic only resolves to worse than tol (BatchNorm / LayerNorm
+    backward cancellation; the true gradient of a conv bias in front of BatchNorm is exactly zero).
+    Third clause: the tensors behind ReLU / BatchNorm kinks.  A pre-activation within bf16 rounding (2^-9 relative) of zero
+    flips its mask bit and moves the gradient by a whole term, so ANY bf16 evaluation -- PyTorch's own autocast mode of the
+    unmodified reference included, whose gradients the fixtures carry -- sits 5-18 % (relative L2) from the fp32 gradient of
+    conv_blocks.* / linear1; the yardstick is that measured distance, not a constant."""
+    rows = grad_l2_table(z, meta, grads)
+    worst = assert_l2_rows(rows, tol, bf16_mode, label)
     for n in meta["none_grad"]:
         assert n not in grads or grads[n] is None or float(grads[n].abs().max()) == 0.0, \
             "%s must not receive a gradient (Q2/Q14)" % n

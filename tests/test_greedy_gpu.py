@@ -32,30 +32,29 @@ def _setup(n_enc, n_dec, wseed, scale_out=30.0):
     return cfg, sd, model
 
 
-def test_run_greedy_matches_oracle_bit_exact():
+@pytest.mark.parametrize("wseed", [16, 13, 11])
+def test_run_greedy_matches_oracle_bit_exact(wseed):
+    """Every sample, over the WHOLE generated sequence: the seeds are chosen (oracle-side search, CPU) so that every arg-max
+    along the way is decided by a top-2 margin > 1e-2, two orders above the fp32 parity tolerance, so the decode is a
+    function of the inputs and must be bit-exact.  wseed 16: 11 distinct phones, no </S> before the length limit;
+    wseed 13: every sample produces </S> at step 5 (the stop rule); wseed 11: the round-1 case."""
     from sst_b200.greedy_search import run_greedy, phoneme_inventory
-    cfg, sd, model = _setup(1, 2, wseed=11)
+    cfg, sd, model = _setup(1, 2, wseed=wseed)
     batch = O.synthetic_batch(seed=5, ragged=[120, 200, 80], tgt_lens=[12, 12, 12])
     X = O.combine_fixed_length(batch["raw_emg"])
     max_len = 14
     margins = []
     seqs, out = O.greedy_decode(sd, cfg, X.clone(), batch["lengths"], max_len, margins)
-    tgt = torch.zeros(3, max_len - 1, dtype=torch.int64)
-    phones, ids = run_greedy(model, batch["lengths"], X.to(DEV), tgt, 43, DEV, cached=False)
     m = torch.stack(margins, 1)                             # (B, steps)
     print("min top-2 logit margin along the oracle's path: %.3e" % float(m.min()))
-    ids = ids.cpu()
-    assert ids.shape == out.shape and ids.dtype == torch.int32
-    for b in range(3):
-        # compare up to the first step whose arg-max margin is below the fp32 parity tolerance (1e-4 of the logit scale):
-        # beyond it the two valid fp32 evaluations may legitimately pick different tokens
-        amb = (m[b] < 1e-3).nonzero()
-        upto = int(amb[0]) + 1 if len(amb) else max_len
-        assert upto >= 4, "seed produces an ambiguous arg-max too early to test anything"
-        assert ids[b, :upto].tolist() == out[b, :upto].tolist(), "sample %d" % b
-        if upto == max_len:
-            assert phones[b] == " ".join(phoneme_inventory[t] for t in seqs[b])
-    assert sum(int((m[b] >= 1e-3).all()) for b in range(3)) >= 2, "at least two samples must be compared in full"
+    assert float(m.min()) > 1e-2, "seed no longer gives an unambiguous decode"
+    tgt = torch.zeros(3, max_len - 1, dtype=torch.int64)
+    for cached in (False, True):
+        phones, ids = run_greedy(model, batch["lengths"], X.to(DEV), tgt, 43, DEV, cached=cached)
+        ids = ids.cpu()
+        assert ids.shape == out.shape and ids.dtype == torch.int32
+        assert torch.equal(ids, out), "cached=%s" % cached
+        assert phones == [" ".join(phoneme_inventory[t] for t in s) for s in seqs]
 
 
 def test_kv_cached_search_equals_prefix_rerun():

@@ -172,3 +172,53 @@ def test_gradsync_world2_gloo_averages_every_bucket_once():
     for rank, err, launched, nb in res:
         assert err < 1e-6, "rank %d: reduced gradient differs from the mean over ranks" % rank
         assert launched == sorted(launched) and launched[-1] == nb   # buckets fire in order, all of them by the last stage
+
+
+def _gate_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    counts = [[3, 4, 5, 5, 1, 6, 2, 9], [1, 1, 7, 2, 2, 2, 8, 1]][rank]       # chunks per micro-batch: different on every rank
+    gate = T.AccumulationGate(batch_size_grad=10, distributed=True)
+    decisions = [gate.add(c) for c in counts]
+    q.put((rank, decisions, gate.sum_batch_size))
+    dist.destroy_process_group()
+
+
+def test_accumulation_gate_world2_gloo_decides_identically_on_every_rank():
+    """with batch_size_grad > 1 and unequal per-rank chunk counts, a rank that thresholds its LOCAL count
+    enters the all-reduce alone.  The gate thresholds the sum over ranks: same decision everywhere, and equal to the
+    single-process reference rule (recognition_model.py:81,115-118) applied to the global batch."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29850 + os.getpid() % 100
+    procs = [ctx.Process(target=_gate_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    glob = [a + b for a, b in zip([3, 4, 5, 5, 1, 6, 2, 9], [1, 1, 7, 2, 2, 2, 8, 1])]
+    want, acc = [], 0
+    for g in glob:
+        acc += g
+        want.append(acc >= 10)
+        if acc >= 10:
+            acc = 0
+    assert res[0][1] == want and res[1][1] == want
+    assert res[0][2] == res[1][2] == acc
+    # a local-count rule would have disagreed on this input: rank 0 alone reaches 10 after its third micro-batch
+    local0 = [sum([3, 4, 5, 5, 1, 6, 2, 9][:k + 1]) >= 10 for k in range(3)]
+    local1 = [sum([1, 1, 7, 2, 2, 2, 8, 1][:k + 1]) >= 10 for k in range(3)]
+    assert local0 != local1
+
+
+def test_accumulation_gate_single_process_matches_the_reference_rule():
+    gate = T.AccumulationGate(batch_size_grad=100)
+    out = [gate.add(c) for c in [40, 40, 40, 10, 95, 5, 100]]
+    assert out == [False, False, True, False, True, False, True]
+    assert [T.AccumulationGate(1).add(c) for c in (1, 320)] == [True, True]
+    g = T.AccumulationGate(10)
+    assert g.add(3, global_chunks=12) is True          # the caller supplied the sum over ranks

@@ -117,7 +117,7 @@ def test_batchnorm_two_branch_fwd_bwd(L, dtype):
     L.bn_bwd(L.dt(xa), n, T, C, dout, C, out, lead, trail, True,
              xa, C, res["a"][0], res["a"][1], ga, dxa, C, 1, 1, dga, dba,
              xb, 2 * C, res["b"][0], res["b"][1], gb, dxb_wide[:, :, C:], 2 * C, 0, 1, dgb, dbb, red)
-    tolg = 1e-4 if dtype == torch.float32 else 3e-2
+    tolg = 1e-4 if dtype == torch.float32 else 2e-2
     assert torch.all(dxa[:, 0] == 0) and torch.all(dxa[:, -1] == 0)
     assert rel(dxa[:, 1:T + 1].float().reshape(n * T, C), xa_l.grad) < tolg
     assert torch.all(dxb_wide[:, T, C:] == 0)
@@ -155,7 +155,7 @@ def ref_attention(q, k, v, E, R, scale, causal, q_lens, k_lens, mask_q_rows):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("case", ["enc_band", "enc_short", "dec_self", "dec_cross"])
+@pytest.mark.parametrize("case", ["enc_band", "enc_short", "enc_full_1000", "dec_self", "dec_cross", "dec_cross_1000", "dec_cross_empty_memory"])
 def test_attention_fwd_bwd(L, dtype, case):
     g = torch.Generator(device=DEV).manual_seed(3)
     H, dh = 4, 96
@@ -163,6 +163,15 @@ def test_attention_fwd_bwd(L, dtype, case):
     if case == "enc_band":
         B, Lq, Lk, R, causal, mqr = 2, 150, 150, 40, False, True
         q_lens = torch.tensor([150, 101], device=DEV, dtype=torch.int32); k_lens = q_lens
+    elif case == "enc_full_1000":         # the benchmarked shape: 8 query tiles, band of 199 keys, skipped key tiles, one ragged utterance
+        B, Lq, Lk, R, causal, mqr = 2, 1000, 1000, 100, False, True
+        q_lens = torch.tensor([1000, 777], device=DEV, dtype=torch.int32); k_lens = q_lens
+    elif case == "dec_cross_1000":        # decoder cross-attention over a full-length ragged memory
+        B, Lq, Lk, R, causal, mqr = 2, 121, 1000, 0, False, False
+        q_lens = None; k_lens = torch.tensor([1000, 640], device=DEV, dtype=torch.int32)
+    elif case == "dec_cross_empty_memory":   # k_lens[b] == 0: every key masked -> the reference's uniform softmax over all Lk keys
+        B, Lq, Lk, R, causal, mqr = 2, 21, 150, 0, False, False
+        q_lens = None; k_lens = torch.tensor([150, 0], device=DEV, dtype=torch.int32)
     elif case == "enc_short":
         B, Lq, Lk, R, causal, mqr = 2, 30, 30, 40, False, True
         q_lens = torch.tensor([30, 17], device=DEV, dtype=torch.int32); k_lens = q_lens
@@ -172,7 +181,7 @@ def test_attention_fwd_bwd(L, dtype, case):
     else:
         B, Lq, Lk, R, causal, mqr = 3, 21, 77, 0, False, False
         q_lens = None; k_lens = torch.tensor([77, 40, 59], device=DEV, dtype=torch.int32)
-    self_attn = case != "dec_cross"
+    self_attn = not case.startswith("dec_cross")
     qkv = (torch.randn(B * Lq, 3 * D, device=DEV, generator=g) * 0.7).to(dtype)
     kv = (torch.randn(B * Lk, 2 * D, device=DEV, generator=g) * 0.7).to(dtype)
     E = (torch.randn(H, 2 * max(R, 1) - 1, dh, device=DEV, generator=g) * dh ** -0.5).to(dtype)
@@ -206,7 +215,7 @@ def test_attention_fwd_bwd(L, dtype, case):
 
     def tok(t, Lx):
         return t.permute(0, 2, 1, 3).reshape(B * Lx, D)
-    tol = 1e-4 if dtype == torch.float32 else 3e-2
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
     assert rel(dq_t.float(), tok(qh.grad, Lq)) < tol
     assert rel(dk_t.float(), tok(kh.grad, Lk)) < tol
     assert rel(dv_t.float(), tok(vh.grad, Lk)) < tol

@@ -5,12 +5,12 @@ import pytest
 import torch
 
 import sst_oracle as O
-from helpers import load_golden, golden_inputs, rel_err, check_grads_against_golden
+from helpers import load_golden, golden_inputs, rel_err, check_grads_l2
 
 CASES = ["cfg1_enc_ctc", "ragged_hybrid", "short_hybrid"]
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + ["full_2p1", "full_6p6"])
 def test_forward_backward_matches_reference(name):
     z, meta = load_golden(name)
     cfg, sd, batch = golden_inputs(meta)
@@ -22,7 +22,7 @@ def test_forward_backward_matches_reference(name):
         assert abs(float(res["loss_dec"]) - float(z["loss_dec"])) < 1e-5 * abs(float(z["loss_dec"]))
     assert abs(float(res["loss"]) - float(z["loss"])) < 1e-5 * abs(float(z["loss"]))
     assert sorted(grads) == sorted(meta["grad_names"])
-    check_grads_against_golden(z, meta, grads, 2e-4, "oracle")
+    check_grads_l2(z, meta, grads, 1e-4, False, "oracle")
     for k, v in stats.items():
         if k.endswith("num_batches_tracked"):
             assert int(v) == 1
