@@ -688,7 +688,7 @@ class Engine:
 
     def backward(self, ctx, G, d_enc_logits=None, d_dec_logits=None, on_stage=None):
         """Accumulates every parameter gradient into G[name] (fp32, reference layout).  `on_stage(label)` is invoked when all
-        gradients of a stage are final ("decoder", "enc<i>", "w_raw_in", "conv") so that the caller can start reducing them."""
+        gradients of a stage are final ("heads", "dec<i>", "embed", "enc<i>", "w_raw_in", "conv") so that the caller can start reducing them."""
         on_stage = on_stage or (lambda label: None)
         B, Lx, D = ctx.B, ctx.Lmax, self.D
         M = B * Lx
@@ -700,10 +700,12 @@ class Engine:
             S = ctx.S
             Md = B * S
             dt_ = self._linear_bwd(d_dec_logits, ctx.x_dec, Md, "w_out", G, "w_out.weight", "w_out.bias")
+            on_stage("heads")
             for i in reversed(range(self.n_dec)):
                 dt_ = self._dec_layer_bwd(ctx.dec_layers[i], dt_, ctx.x_enc, dx, B, S, Lx, ctx.tgt_lens, ctx.lens, i, G)
+                on_stage("dec%d" % i)
             L.embed_bwd(self.dt, ctx.y, dt_, G["embedding_tgt.weight"], B, S, D, PAD, ctx.p_pos, ctx.s_emb)
-        on_stage("decoder")
+        on_stage("embed")
         for i in reversed(range(self.n_enc)):
             dx = self._enc_layer_bwd(ctx.layers[i], dx, B, Lx, ctx.lens, i, G)
             on_stage("enc%d" % i)

@@ -43,8 +43,12 @@ def backward_order(names, n_enc, n_dec):
 
 def stage_of(name, n_enc, n_dec):
     """Backward stage label after which `name`'s gradient is final (matches Engine.backward's on_stage calls)."""
-    if name.startswith("w_aux") or name.startswith("w_out") or name.startswith("transformerDecoder") or name.startswith("embedding_tgt"):
-        return "decoder"
+    if name.startswith("w_aux") or name.startswith("w_out"):
+        return "heads"
+    if name.startswith("transformerDecoder.layers."):
+        return "dec%d" % int(name.split(".")[2])
+    if name.startswith("embedding_tgt"):
+        return "embed"
     if name.startswith("transformerEncoder.layers."):
         return "enc%d" % int(name.split(".")[2])
     if name.startswith("w_raw_in"):
@@ -177,11 +181,14 @@ class GradSync:
                 start = off
             cur_stage = st
         self.buckets.append((start, flat.numel, cur_stage))
-        self.stage_order = ["decoder"] + ["enc%d" % i for i in reversed(range(n_enc))] + ["w_raw_in", "conv"]
+        self.stage_order = (["heads"] + ["dec%d" % i for i in reversed(range(n_dec))] + ["embed"] +
+                            ["enc%d" % i for i in reversed(range(n_enc))] + ["w_raw_in", "conv"])
         self.cuda = flat.g.is_cuda
         self.stream = torch.cuda.Stream() if self.cuda else None
         self._next = 0
         self._pending = []
+        self.trace = False            # record a CUDA-event timeline of the next step (tools/ddp_timeline.py)
+        self.timeline = None
 
     def broadcast_state(self, tensors):
         """Every rank starts from rank 0's parameters / optimizer moments (nn.DataParallel replicated module 0 on every
@@ -195,12 +202,24 @@ class GradSync:
     def begin(self):
         self._next = 0
         self._pending = []
+        if self.trace and self.cuda:
+            self.timeline = {"t0": self._event(torch.cuda.current_stream()), "stages": [], "buckets": []}
+        else:
+            self.timeline = None
+
+    @staticmethod
+    def _event(stream):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream)
+        return ev
 
     def on_stage(self, stage):
         """Called by Engine.backward when every gradient up to and including `stage` is final."""
         if self.world == 1:
             return
         done = self.stage_order.index(stage)
+        if self.timeline is not None:
+            self.timeline["stages"].append((stage, self._event(torch.cuda.current_stream())))
         while self._next < len(self.buckets) and self.stage_order.index(self.buckets[self._next][2]) <= done:
             s, e, _ = self.buckets[self._next]
             self._launch(self.flat.g[s:e])
@@ -213,11 +232,14 @@ class GradSync:
             ev.record(torch.cuda.current_stream())
             self.stream.wait_event(ev)
             with torch.cuda.stream(self.stream):
+                e0 = self._event(self.stream) if self.timeline is not None else None
                 if self.backend == "nccl":
                     dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
                 else:
                     dist.all_reduce(t, group=self.group)
                     t.div_(self.world)
+                if e0 is not None:
+                    self.timeline["buckets"].append((t.numel() * 4, ev, e0, self._event(self.stream)))
         else:
             dist.all_reduce(t, group=self.group)
             t.div_(self.world)
@@ -228,7 +250,27 @@ class GradSync:
             return
         self.on_stage("conv")
         if self.cuda:
+            if self.timeline is not None:
+                self.timeline["bwd_end"] = self._event(torch.cuda.current_stream())
             torch.cuda.current_stream().wait_stream(self.stream)
+            if self.timeline is not None:
+                self.timeline["sync_end"] = self._event(torch.cuda.current_stream())
+
+    def timeline_ms(self):
+        """The recorded step as plain numbers (ms since the start of backward): when each stage's gradients were final, when each
+        bucket became ready / started / finished its all-reduce, and how long the compute stream then had to wait for the last
+        bucket (`exposed_ms`: the only communication time that is not hidden behind backward)."""
+        tl = self.timeline
+        if tl is None:
+            return None
+        torch.cuda.synchronize()
+        t0 = tl["t0"]
+        ms = lambda e: round(t0.elapsed_time(e), 3)      # noqa: E731
+        buckets = [dict(mbytes=round(nb / 1e6, 1), ready=ms(r), start=ms(a), end=ms(b)) for nb, r, a, b in tl["buckets"]]
+        busy = sum(b["end"] - b["start"] for b in buckets)
+        return dict(stages=[(n, ms(e)) for n, e in tl["stages"]], buckets=buckets, backward_ms=ms(tl["bwd_end"]),
+                    exposed_ms=round(tl["bwd_end"].elapsed_time(tl["sync_end"]), 3), allreduce_busy_ms=round(busy, 3),
+                    mbytes=round(sum(b["mbytes"] for b in buckets), 1))
 
 
 class Trainer:
@@ -372,7 +414,7 @@ class Trainer:
         losses = self.step_device(dev_batch)
         return self.fetch_losses(losses)
 
-    def run(self, host_batches):
+    def run(self, host_batches, global_chunks=None):
         """Pipelined public entry for a stream of prepared (pinned) host batches, the way a training loop would drive it:
         the H2D copy of batch i+1 is issued on a copy stream while batch i computes, and the loss of step i is read back
         (async D2H + event) while step i+1 is already enqueued -- every step still uploads its inputs and downloads its
@@ -408,7 +450,7 @@ class Trainer:
             for v in d.values():
                 if torch.is_tensor(v):
                     v.record_stream(main)
-            losses = self.step_device(d)
+            losses = self.step_device(d, global_chunks=global_chunks)
             cur = upload(nxt) if nxt is not None else None
             slot = k & 1
             pinned[slot].copy_(losses, non_blocking=True)

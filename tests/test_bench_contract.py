@@ -50,3 +50,9 @@ def test_gpu_arm_prints_the_contract_line():
     r = d["roofline"]
     assert r["bound"] in ("tensor", "hbm") and 0.0 < r["frac"] <= 1.0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
     assert "workload" in d["config"] and "cfg2" in d["config"]["workload"]
+    # the other BASELINE.json configurations ride along in `also`, measured after the headline
+    also = d["also"]
+    for k in ("cfg3_hybrid", "cfg4_accumulation", "cfg5_inference", "greedy_search_latency"):
+        assert k in also and "error" not in also[k], (k, also.get(k))
+    assert also["cfg3_hybrid"]["frames_per_s"] > 3e5 and also["cfg4_accumulation"]["optimizer_steps"] == 3
+    assert also["cfg5_inference"]["utterances"] == 1000 and also["cfg5_inference"]["utterances_per_s"] > 100
