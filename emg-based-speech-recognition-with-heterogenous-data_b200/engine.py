@@ -688,7 +688,7 @@ class Engine:
 
     def backward(self, ctx, G, d_enc_logits=None, d_dec_logits=None, on_stage=None):
         """Accumulates every parameter gradient into G[name] (fp32, reference layout).  `on_stage(label)` is invoked when all
-        gradients of a stage are final ("heads", "dec<i>", "embed", "enc<i>", "w_raw_in", "conv") so that the caller can start reducing them."""
+        gradients of a stage are final ("heads", "dec<i>", "embed", "enc<i>", "w_raw_in", "conv<i>") so that the caller can start reducing them."""
         on_stage = on_stage or (lambda label: None)
         B, Lx, D = ctx.B, ctx.Lmax, self.D
         M = B * Lx
@@ -718,4 +718,4 @@ class Engine:
         on_stage("w_raw_in")
         for c in reversed(ctx.blocks):
             da = self._resblock_bwd(c, da, G)
-        on_stage("conv")
+            on_stage("conv%d" % c.i)

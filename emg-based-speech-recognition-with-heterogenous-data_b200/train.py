@@ -53,7 +53,9 @@ def stage_of(name, n_enc, n_dec):
         return "enc%d" % int(name.split(".")[2])
     if name.startswith("w_raw_in"):
         return "w_raw_in"
-    return "conv"
+    if name.startswith("conv_blocks."):
+        return "conv%d" % int(name.split(".")[1])
+    return "conv0"
 
 
 def prepare_batch(example):
@@ -182,7 +184,7 @@ class GradSync:
             cur_stage = st
         self.buckets.append((start, flat.numel, cur_stage))
         self.stage_order = (["heads"] + ["dec%d" % i for i in reversed(range(n_dec))] + ["embed"] +
-                            ["enc%d" % i for i in reversed(range(n_enc))] + ["w_raw_in", "conv"])
+                            ["enc%d" % i for i in reversed(range(n_enc))] + ["w_raw_in", "conv2", "conv1", "conv0"])
         self.cuda = flat.g.is_cuda
         self.stream = torch.cuda.Stream() if self.cuda else None
         self._next = 0
@@ -228,7 +230,7 @@ class GradSync:
     def _launch(self, t):
         dist = self.dist
         if self.cuda:
-            ev = torch.cuda.Event()
+            ev = torch.cuda.Event(enable_timing=self.timeline is not None)
             ev.record(torch.cuda.current_stream())
             self.stream.wait_event(ev)
             with torch.cuda.stream(self.stream):
@@ -248,7 +250,7 @@ class GradSync:
         """All buckets reduced and visible to the compute stream."""
         if self.world == 1:
             return
-        self.on_stage("conv")
+        self.on_stage("conv0")
         if self.cuda:
             if self.timeline is not None:
                 self.timeline["bwd_end"] = self._event(torch.cuda.current_stream())

@@ -106,7 +106,7 @@ def test_backward_order_follows_gradient_completion():
     order = T.backward_order(names, 2, 2)
     assert sorted(order) == sorted(names)
     stages = [T.stage_of(n, 2, 2) for n in order]
-    seq = ["heads", "dec1", "dec0", "embed", "enc1", "enc0", "w_raw_in", "conv"]
+    seq = ["heads", "dec1", "dec0", "embed", "enc1", "enc0", "w_raw_in", "conv2", "conv1", "conv0"]
     idx = [seq.index(s) for s in stages]
     assert idx == sorted(idx), "flat buffer must be laid out in backward-completion order"
     assert order[0].startswith("w_aux") and order[-1].startswith("conv_blocks.0")

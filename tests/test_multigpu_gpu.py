@@ -83,3 +83,41 @@ def test_allreduced_gradient_is_the_mean_of_the_per_rank_gradients():
     scale = float(want.abs().max())
     assert float((got - want).abs().max()) < 2e-5 * scale                                           # fp32, different summation order only
     assert float((gs[0] - gs[1]).abs().max()) > 1e-2 * scale                                        # the two shards really differ
+
+
+def _worker_accum(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    cfg = O.make_cfg(n_enc=1, n_dec=1, rel_dist=100, alpha=0.2)
+    sd0 = O.synthetic_state_dict(cfg, 7 + rank)                # DIFFERENT initial weights per rank: the Trainer must broadcast rank 0's
+    tr = _make_trainer(cfg, sd0, dev, True)
+    tr.batch_size_grad = 6                                     # chunks, summed over ranks
+    steps = []
+    for i in range(3):
+        # rank 0: 1 chunk per micro-batch, rank 1: 3 chunks -- a rank-local threshold would let rank 1 step (and all-reduce) alone
+        b = O.synthetic_batch(seed=70 + 10 * rank + i, ragged=[[70, 100, 30], [200, 150, 100]][rank], tgt_lens=[[9, 14, 5], [12, 6, 8]][rank])
+        tr.step_device(tr.to_device(tr.prepare(b)), shift_r=0)
+        steps.append(tr.flat.step_count)
+    torch.cuda.synchronize()
+    torch.save({"p": tr.flat.p.cpu(), "steps": steps, "acc": tr.sum_batch_size}, os.path.join(out_dir, "acc%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_accumulation_with_unequal_chunk_counts_steps_on_the_same_micro_batch_everywhere():
+    """ADVICE r1 (high / medium): batch_size_grad > 1 with different chunk counts per rank, and ranks that were NOT seeded
+    identically.  Global chunk counts per micro-step are 4, 4, 4 against a threshold of 6: every rank steps after the second
+    micro-batch (not rank 1 alone after its own second one), no collective hangs, and the replicas hold identical parameters
+    although they were constructed from different weights."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    out_dir = tempfile.mkdtemp()
+    mp.spawn(_worker_accum, args=(2, _free_port(), out_dir), nprocs=2, join=True)
+    res = [torch.load(os.path.join(out_dir, "acc%d.pt" % r)) for r in range(2)]
+    assert res[0]["steps"] == res[1]["steps"] == [0, 1, 1]
+    assert res[0]["acc"] == res[1]["acc"] == 4
+    assert torch.equal(res[0]["p"], res[1]["p"])
