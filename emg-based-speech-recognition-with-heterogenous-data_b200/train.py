@@ -164,7 +164,7 @@ class AccumulationGate:
 
 
 class GradSync:
-    def __init__(self, flat, n_enc, n_dec, bucket_bytes=25 << 20, group=None):
+    def __init__(self, flat, n_enc, n_dec, bucket_bytes=128 << 20, group=None):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -277,7 +277,7 @@ class GradSync:
 
 class Trainer:
     def __init__(self, model, learning_rate=3e-4, learning_rate_warmup=1500, alpha_loss=0.2, batch_size_grad=100,
-                 eps_ls=0.1, weight_decay=0.01, seed=0, distributed=False, bucket_bytes=25 << 20):
+                 eps_ls=0.1, weight_decay=0.01, seed=0, distributed=False, bucket_bytes=128 << 20):
         self.model = model
         self.lr_target, self.warmup = learning_rate, learning_rate_warmup
         self.lr = learning_rate

@@ -14,7 +14,7 @@ from sst_b200.train import Trainer
 import bench
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--bucket-mb", type=int, default=25)
+ap.add_argument("--bucket-mb", type=int, default=128)
 ap.add_argument("--workload", default="cfg2")
 ap.add_argument("--steps", type=int, default=10)
 args = ap.parse_args()
