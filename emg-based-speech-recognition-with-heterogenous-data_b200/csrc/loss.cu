@@ -294,6 +294,43 @@ ctc_greedy_kernel(const T* __restrict__ x, long ld, const int* __restrict__ in_l
   if (tid == 0) out_lens[b] = s_base;
 }
 
+// One step of the greedy attention-decoder search (greedy_search.py:22-37) for every sample: arg-max of the last position's
+// logits (lowest index wins ties), append to the prefix, latch "has produced </S>", count the finished samples.
+// One warp per sample, one block (searches run on a handful of utterances).
+template <typename T>
+__global__ void __launch_bounds__(1024)
+greedy_pick_kernel(const T* __restrict__ logits, long row_stride, int B, int C, long long* __restrict__ tokens, long tok_sb, long tok_sp,
+                   int pos, int eos, unsigned char* __restrict__ done, int* __restrict__ n_done) {
+  __shared__ int s_cnt;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  for (int b = w; b < B; b += nw) {
+    const T* row = logits + (long)b * row_stride;
+    float best = -INFINITY;
+    int am = 0x7fffffff;
+    for (int c = lane; c < C; c += 32) {
+      const float v = to_f32(row[c]);
+      if (v > best || (v == best && c < am)) { best = v; am = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, am, o);
+      if (ov > best || (ov == best && oi < am)) { best = ov; am = oi; }
+    }
+    if (lane == 0) {
+      if (am == 0x7fffffff) am = 0;                   // every logit NaN: torch.argmax also answers with an index, not a fault
+      tokens[(long)b * tok_sb + (long)pos * tok_sp] = am;
+      const unsigned char d = done[b] | (am == eos ? 1 : 0);
+      done[b] = d;
+      if (d) atomicAdd(&s_cnt, 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *n_done = s_cnt;
+}
+
 }  // namespace sst
 
 using namespace sst;
@@ -359,6 +396,22 @@ int sst_ctc_greedy(int logits_dtype, int B, int L, int C, int blank, const void*
   if (logits_dtype == SST_F32) ctc_greedy_kernel<float><<<B, 256, 0, st>>>((const float*)logits, ld, in_lens, L, C, blank, out_ids, out_lens);
   else ctc_greedy_kernel<__nv_bfloat16><<<B, 256, 0, st>>>((const __nv_bfloat16*)logits, ld, in_lens, L, C, blank, out_ids, out_lens);
   return check_launch("ctc_greedy");
+}
+
+/* tokens int64: tokens[b*tok_stride_b + pos*tok_stride_pos] = arg-max_c logits[b * row_stride + c]; done[b] |= (that == eos);
+ * n_done[0] = #done. */
+int sst_greedy_pick(int logits_dtype, int B, int C, const void* logits, int64_t row_stride, int64_t* tokens, int64_t tok_stride_b,
+                    int64_t tok_stride_pos, int pos, int eos, uint8_t* done, int32_t* n_done, void* stream) {
+  SST_REQUIRE(logits && tokens && done && n_done && C >= 1 && pos >= 0, SST_E_ARG, "greedy_pick: bad arguments");
+  if (B <= 0) return SST_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int threads = B >= 32 ? 1024 : 32 * B;
+  if (logits_dtype == SST_F32)
+    greedy_pick_kernel<float><<<1, threads, 0, st>>>((const float*)logits, row_stride, B, C, reinterpret_cast<long long*>(tokens), tok_stride_b, tok_stride_pos, pos, eos, done, n_done);
+  else
+    greedy_pick_kernel<__nv_bfloat16><<<1, threads, 0, st>>>((const __nv_bfloat16*)logits, row_stride, B, C, reinterpret_cast<long long*>(tokens),
+                                                             tok_stride_b, tok_stride_pos, pos, eos, done, n_done);
+  return check_launch("greedy_pick");
 }
 
 /* logits (rows, ld) with rows = B*S; loss = (1-eps)*CE(ignore_index, mean over non-ignored) + eps/S * sum(exp(logits)).

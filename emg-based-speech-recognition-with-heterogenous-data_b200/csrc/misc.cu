@@ -284,6 +284,37 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+// ---- exact (erf) GELU + dropout, forward and backward: HBM-bound, one 16-byte vector of 8 elements per thread and trip ------------
+// y = keep ? gelu(x) / (1 - p) : 0 with gelu(x) = x/2 (1 + erf(x / sqrt 2)) (torch's default F.gelu); keep decision of element
+// (row, col) = 16-bit Philox lane of index row*cols + col (philox_keep16: one Philox block per 8-element vector).
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.39894228040143268f * __expf(-0.5f * x * x);
+}
+
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(256)
+gelu_dropout_kernel(const T* __restrict__ x, long ldx, const T* __restrict__ dy, long lddy, T* __restrict__ out, long ldo, long rows, int cols,
+                    uint32_t thr16, float dscale, unsigned long long seed) {
+  const int vpr = cols >> 3;                                          // vectors per row
+  const long total = rows * vpr;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long)gridDim.x * blockDim.x) {
+    const long r = v / vpr;
+    const int c = (int)(v - r * vpr) << 3;
+    float a[8], g[8];
+    Vec8<T>::load(x + r * ldx + c, a);
+    if (BWD) Vec8<T>::load(dy + r * lddy + c, g);
+    Philox4 rn;
+    if (thr16) rn = philox4x32(seed, (unsigned long long)(r * cols + c) >> 3);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float k = (thr16 == 0 || philox_lane16(rn, e) >= thr16) ? dscale : 0.f;
+      a[e] = BWD ? g[e] * gelu_erf_grad(a[e]) * k : gelu_erf(a[e]) * k;
+    }
+    Vec8<T>::store(out + r * ldo + c, a);
+  }
+}
+
 static int ew_grid2(long total, int threads) {
   long blocks = (total + threads - 1) / threads;
   long cap = (long)num_sms() * 16;
@@ -419,6 +450,32 @@ int sst_permute3_cast_batch(const SstPermuteItem* items_dev, int n_items, int to
   if (n_items <= 0 || total_blocks <= 0) return SST_OK;
   permute3_batch_kernel<<<total_blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(items_dev, n_items);
   return check_launch("permute3_cast_batch");
+}
+
+static int gelu_launch(bool bwd, int dtype, int64_t rows, int cols, const void* x, int64_t ldx, const void* dy, int64_t lddy, void* out,
+                       int64_t ldo, float drop_p, uint64_t seed, void* stream) {
+  SST_REQUIRE(cols % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && (!bwd || lddy % 8 == 0), SST_E_ARG, "gelu: columns and pitches must be multiples of 8");
+  SST_REQUIRE(drop_p >= 0.f && drop_p < 1.f, SST_E_ARG, "gelu: dropout probability out of range");
+  if (rows <= 0 || cols <= 0) return SST_OK;
+  const uint32_t thr = drop_p > 0.f ? drop_threshold16(drop_p) : 0u;
+  const float dscale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const int grid = ew_grid2(rows * (cols / 8), 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define SST_GELU(T, B) gelu_dropout_kernel<T, B><<<grid, 256, 0, st>>>((const T*)x, ldx, (const T*)dy, lddy, (T*)out, ldo, rows, cols, thr, dscale, seed)
+  if (dtype == SST_F32) { if (bwd) SST_GELU(float, true); else SST_GELU(float, false); }
+  else { if (bwd) SST_GELU(__nv_bfloat16, true); else SST_GELU(__nv_bfloat16, false); }
+#undef SST_GELU
+  return check_launch(bwd ? "gelu_dropout_bwd" : "gelu_dropout_fwd");
+}
+
+int sst_gelu_dropout_fwd(int dtype, int64_t rows, int cols, const void* x, int64_t ldx, float drop_p, uint64_t seed, void* y, int64_t ldy,
+                         void* stream) {
+  return gelu_launch(false, dtype, rows, cols, x, ldx, nullptr, 0, y, ldy, drop_p, seed, stream);
+}
+
+int sst_gelu_dropout_bwd(int dtype, int64_t rows, int cols, const void* dy, int64_t lddy, const void* x, int64_t ldx, float drop_p,
+                         uint64_t seed, void* dx, int64_t lddx, void* stream) {
+  return gelu_launch(true, dtype, rows, cols, x, ldx, dy, lddy, dx, lddx, drop_p, seed, stream);
 }
 
 int sst_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, float wd,

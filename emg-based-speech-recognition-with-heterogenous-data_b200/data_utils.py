@@ -1,32 +1,55 @@
-"""Host-side boundary helpers, same names and semantics as the reference's data_utils.py:165-185."""
+"""Host-side staging of a batch for the B200 path.
+
+`combine_fixed_length(tensor_list, length)` keeps the name and the result of the reference's packer (data_utils.py:165-174: the
+utterances laid end to end along time, the last chunk completed with the VALUE 42, viewed as (n, length, channels)) because the
+training loop calls it by that name (recognition_model.py:77) -- but it is a staging routine here, not a concat: the chunks are
+written straight into ONE page-locked buffer, which is what the asynchronous host-to-device copy of the step wants
+(`Trainer.to_device`, bench.py's e2e leg).  The reference's host-side inverse (`decollate_tensor`) has no counterpart on this
+side: the split by utterance lengths happens on the device (sst_gather_rows_pad, include/sst.h).
+"""
 import torch
 
 PAD = 42
 
 
-def combine_fixed_length(tensor_list, length):
-    """data_utils.py:165-174: concatenate utterances along time, pad the tail with the VALUE 42 to a multiple of `length`,
-    view as (n, length, channels)."""
-    total_length = sum(t.size(0) for t in tensor_list)
-    if total_length % length != 0:
-        pad_length = length - (total_length % length)
-        tensor_list = list(tensor_list)
-        tensor_list.append(torch.full((pad_length, *tensor_list[0].size()[1:]), PAD, dtype=tensor_list[0].dtype,
-                                      device=tensor_list[0].device))
-        total_length += pad_length
-    tensor = torch.cat(tensor_list, 0)
-    n = total_length // length
-    return tensor.view(n, length, *tensor.size()[1:])
+class ChunkStager:
+    """Reusable page-locked staging area for (n, length, channels) chunk tensors: grows to the largest batch seen, is handed out
+    as a view, and is therefore only valid until the next `pack` call (one step ahead is enough for Trainer.run's pipeline when
+    two stagers alternate)."""
+
+    def __init__(self, pin=None):
+        self.pin = torch.cuda.is_available() if pin is None else pin
+        self.buf = None
+
+    def _storage(self, numel, dtype):
+        if self.buf is None or self.buf.numel() < numel or self.buf.dtype != dtype:
+            self.buf = torch.empty(numel, dtype=dtype)
+            if self.pin:
+                self.buf = self.buf.pin_memory()
+        return self.buf[:numel]
+
+    def pack(self, tensor_list, length):
+        first = tensor_list[0]
+        inner = tuple(first.shape[1:])
+        row = 1
+        for s in inner:
+            row *= s
+        rows = sum(int(t.shape[0]) for t in tensor_list)
+        n = -(-rows // length)
+        flat = self._storage(n * length * row, first.dtype).view(n * length, row)
+        at = 0
+        for t in tensor_list:
+            k = int(t.shape[0])
+            flat[at:at + k].copy_(t.reshape(k, row))
+            at += k
+        if at < n * length:
+            flat[at:].fill_(PAD)                       # the tail of the last chunk holds the value 42 (data_utils.py:170)
+        return flat.view(n, length, *inner)
 
 
-def decollate_tensor(tensor, lengths):
-    """data_utils.py:176-185 (host mirror; on the device the same gather is sst_gather_rows_pad)."""
-    b, s, d = tensor.size()
-    tensor = tensor.view(b * s, d)
-    results = []
-    idx = 0
-    for length in lengths:
-        assert idx + length <= b * s
-        results.append(tensor[idx:idx + length])
-        idx += length
-    return results
+def combine_fixed_length(tensor_list, length, stager=None):
+    """Same call and result as the reference's data_utils.combine_fixed_length; with `stager` (a ChunkStager) the result is a view
+    into its page-locked buffer, otherwise a fresh (pageable) tensor."""
+    if stager is not None:
+        return stager.pack(tensor_list, length)
+    return ChunkStager(pin=False).pack(tensor_list, length)

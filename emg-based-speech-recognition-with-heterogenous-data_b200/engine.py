@@ -44,6 +44,7 @@ class Engine:
         self.dh = self.D // self.H
         self.Hd = cfg.get("n_heads_dec", self.H)          # FLAGS.n_heads_decoder (architecture.py:17); head dims other than 96
         self.dhd = self.D // self.Hd                      # run on the CUDA-core attention kernels
+        self.gelu = cfg.get("activation", "relu") == "gelu"   # exact-erf GELU instead of the shipped ReLU
         self.R = cfg["rel_dist"]
         self.n_enc = cfg["n_enc"]
         self.n_dec = cfg["n_dec"]
@@ -227,6 +228,25 @@ class Engine:
                   epilogue=epi, mask_scale=mask_scale, a_cols=N)
         return dx_out
 
+    def _ffn1_fwd(self, x, M, pfx, p, seed):
+        """linear1 + activation + dropout (transformer.py:61).  ReLU rides in the GEMM epilogue; GELU is the separate
+        bandwidth-bound kernel and keeps the pre-activation for backward.  Returns (h, saved pre-activation or None)."""
+        if not self.gelu:
+            return self._linear_fwd(x, M, pfx + ".linear1", bias=self.P[pfx + ".linear1.bias"], relu=True, drop_p=p, seed=seed), None
+        pre = self._linear_fwd(x, M, pfx + ".linear1", bias=self.P[pfx + ".linear1.bias"])
+        h = self.empty(M, self.F)
+        L.gelu_dropout_fwd(self.dt, M, self.F, pre, self.F, p, seed, h, self.F)
+        return h, pre
+
+    def _ffn2_bwd(self, dy, h, pre, M, pfx, G, p, seed):
+        """gradient w.r.t. linear1's output: (dy W2) masked by the activation derivative and the dropout keep factors."""
+        if not self.gelu:
+            keep_scale = 1.0 / (1.0 - p) if p > 0 else 1.0
+            return self._linear_bwd(dy, h, M, pfx + ".linear2", G, pfx + ".linear2.weight", pfx + ".linear2.bias", aux=h, mask_scale=keep_scale)
+        dh = self._linear_bwd(dy, h, M, pfx + ".linear2", G, pfx + ".linear2.weight", pfx + ".linear2.bias")
+        L.gelu_dropout_bwd(self.dt, M, self.F, dh, self.F, pre, self.F, p, seed, dh, self.F)
+        return dh
+
     def _ln_fwd(self, x, r, M, prefix, p, seed):
         """returns y; r's buffer is overwritten with the pre-norm sum s (saved for backward)."""
         y = self.empty(M, self.D)
@@ -374,20 +394,18 @@ class Engine:
         y = self._linear_fwd(o, M, a + ".o.T")
         x1, ln1 = self._ln_fwd(x, y, M, pfx + ".norm1", p, seeds())
         s_ffn = seeds()
-        h = self._linear_fwd(x1, M, pfx + ".linear1", bias=self.P[pfx + ".linear1.bias"], relu=True, drop_p=p, seed=s_ffn)
+        h, pre = self._ffn1_fwd(x1, M, pfx, p, s_ffn)
         y2 = self._linear_fwd(h, M, pfx + ".linear2", bias=self.P[pfx + ".linear2.bias"])
         x2, ln2 = self._ln_fwd(x1, y2, M, pfx + ".norm2", p, seeds())
-        c = Ctx(x=x, qkv=qkv, o=o, lse=lse, ad=ad, ln1=ln1, x1=x1, h=h, ln2=ln2, p=p)
+        c = Ctx(x=x, qkv=qkv, o=o, lse=lse, ad=ad, ln1=ln1, x1=x1, h=h, pre=pre, s_ffn=s_ffn, ln2=ln2, p=p)
         return x2, c
 
     def _enc_layer_bwd(self, c, dx2, B, Lx, lens, i, G):
         D, M = self.D, B * Lx
         pfx = "transformerEncoder.layers.%d" % i
         a = pfx + ".self_attn"
-        keep_scale = 1.0 / (1.0 - c.p) if c.p > 0 else 1.0
         ds2, dy2 = self._ln_bwd(dx2, c.ln2, M, pfx + ".norm2", G)
-        dh = self._linear_bwd(dy2, c.h, M, pfx + ".linear2", G, pfx + ".linear2.weight", pfx + ".linear2.bias",
-                              aux=c.h, mask_scale=keep_scale)
+        dh = self._ffn2_bwd(dy2, c.h, c.pre, M, pfx, G, c.p, c.s_ffn)
         # dx1 = ds2 + dh W1   (accumulated in place into ds2)
         self._linear_bwd(dh, c.x1, M, pfx + ".linear1", G, pfx + ".linear1.weight", pfx + ".linear1.bias", dx_out=ds2, accum_dx=True)
         ds1, dy = self._ln_bwd(ds2, c.ln1, M, pfx + ".norm1", G)
@@ -441,21 +459,20 @@ class Engine:
         L.attn_fwd(ad2, q, kv, kv[:, D:], None, None, mem_lens, o2, lse2)
         y2 = self._linear_fwd(o2, M, m + ".o.T")
         t2, ln2 = self._ln_fwd(t1, y2, M, pfx + ".norm2", p, seeds())
-        h = self._linear_fwd(t2, M, pfx + ".linear1", bias=self.P[pfx + ".linear1.bias"], relu=True, drop_p=p, seed=seeds())
+        s_ffn = seeds()
+        h, pre = self._ffn1_fwd(t2, M, pfx, p, s_ffn)
         y3 = self._linear_fwd(h, M, pfx + ".linear2", bias=self.P[pfx + ".linear2.bias"])
         t3, ln3 = self._ln_fwd(t2, y3, M, pfx + ".norm3", p, seeds())
         c = Ctx(t=t, qkv=qkv, o1=o1, lse1=lse1, ad1=ad1, ln1=ln1, t1=t1, q=q, kv=kv, o2=o2, lse2=lse2, ad2=ad2, ln2=ln2, t2=t2,
-                h=h, ln3=ln3, p=p)
+                h=h, pre=pre, s_ffn=s_ffn, ln3=ln3, p=p)
         return t3, c
 
     def _dec_layer_bwd(self, c, dt3, mem, dmem, B, S, Lm, tgt_lens, mem_lens, i, G):
         D, M, Mm = self.D, B * S, B * Lm
         pfx = "transformerDecoder.layers.%d" % i
         a, m = pfx + ".self_attn", pfx + ".multihead_attn"
-        keep_scale = 1.0 / (1.0 - c.p) if c.p > 0 else 1.0
         ds3, dy3 = self._ln_bwd(dt3, c.ln3, M, pfx + ".norm3", G)
-        dh = self._linear_bwd(dy3, c.h, M, pfx + ".linear2", G, pfx + ".linear2.weight", pfx + ".linear2.bias", aux=c.h,
-                              mask_scale=keep_scale)
+        dh = self._ffn2_bwd(dy3, c.h, c.pre, M, pfx, G, c.p, c.s_ffn)
         self._linear_bwd(dh, c.t2, M, pfx + ".linear1", G, pfx + ".linear1.weight", pfx + ".linear1.bias", dx_out=ds3, accum_dx=True)
         ds2, dy2 = self._ln_bwd(ds3, c.ln2, M, pfx + ".norm2", G)
         # cross attention
@@ -553,51 +570,56 @@ class Engine:
         looks at the `done` flags every `check_every` steps.  Returns the (B, n) int64 device tensor of prefixes."""
         D, H = self.D, self.Hd
         Tmax = max_seq_length - 1                                   # decoder input positions
-        tokens = torch.full((B, max_seq_length), PAD, dtype=torch.int64, device=self.dev)
-        tokens[:, 0] = start_tok
-        done = torch.zeros(B, dtype=torch.bool, device=self.dev)
+        tokens = torch.full((max_seq_length, B), PAD, dtype=torch.int64, device=self.dev)    # position-major: one step's ids are contiguous
+        tokens[0] = start_tok
+        done = torch.zeros(B, dtype=torch.uint8, device=self.dev)
+        n_done = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        n_done_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         cross, cache = [], []
         for i in range(self.n_dec):
             m = "transformerDecoder.layers.%d.multihead_attn" % i
             cross.append(self._linear_fwd(mem, B * Lm, m + ".kv"))
             cache.append(self.zeros(B * Tmax, 2 * D))
-        klen = torch.zeros(B, dtype=torch.int32, device=self.dev)
-        seeds = Engine._Seeds(0)
+        klens = torch.arange(1, Tmax + 1, dtype=torch.int32, device=self.dev).view(Tmax, 1).expand(Tmax, B).contiguous()
+        # per-step buffers, allocated once: the loop below launches libsst.so kernels only
+        t0 = self.empty(B, D)
+        o1, o2 = self.empty(B, D), self.empty(B, D)
+        lse = self.empty(2 * B * H, dtype=torch.float32)
         n = 1
         for s in range(Tmax):
-            y = tokens[:, s:s + 1].contiguous()
-            t = self.empty(B, D)
-            L.embed_posenc_fwd(self.dt, y, self.P["embedding_tgt.weight"], self.Bf["pos_decoder.pe"], t, B, 1, D, 0.0, 0)
-            klen.fill_(s + 1)
+            L.embed_posenc_fwd(self.dt, tokens[s], self.P["embedding_tgt.weight"], self.Bf["pos_decoder.pe"], t0, B, 1, D, 0.0, 0)
+            t = t0
+            klen = klens[s]                                       # s + 1 keys for every sample
             for i in range(self.n_dec):
                 pfx = "transformerDecoder.layers.%d" % i
                 a, m = pfx + ".self_attn", pfx + ".multihead_attn"
                 qkv = self._linear_fwd(t, B, a + ".qkv")
                 kv_s = cache[i].view(B, Tmax, 2 * D)[:, s]          # rows b*Tmax + s
                 L.permute3_cast(qkv[:, D:], kv_s, (1, B, 2 * D), (0, 3 * D, 1), (0, Tmax * 2 * D, 1))
-                o1 = self.empty(B, D)
-                lse = self.empty(2 * B * H, dtype=torch.float32)
                 ad1 = self._attn_desc(B, 1, Tmax, 3 * D, 2 * D, 2 * D, False, False, 0, 0.0, 0, dec=True)
                 L.attn_fwd(ad1, qkv, cache[i], cache[i][:, D:], None, None, klen, o1, lse)
                 y1 = self._linear_fwd(o1, B, a + ".o.T")
                 t1, _ = self._ln_fwd(t, y1, B, pfx + ".norm1", 0.0, 0)
                 q = self._linear_fwd(t1, B, m + ".q")
-                o2 = self.empty(B, D)
                 ad2 = self._attn_desc(B, 1, Lm, D, 2 * D, 2 * D, False, False, 0, 0.0, 0, dec=True)
                 L.attn_fwd(ad2, q, cross[i], cross[i][:, D:], None, None, mem_lens, o2, lse)
                 y2 = self._linear_fwd(o2, B, m + ".o.T")
                 t2, _ = self._ln_fwd(t1, y2, B, pfx + ".norm2", 0.0, 0)
-                hid = self._linear_fwd(t2, B, pfx + ".linear1", bias=self.P[pfx + ".linear1.bias"], relu=True)
+                hid, _ = self._ffn1_fwd(t2, B, pfx, 0.0, 0)
                 y3 = self._linear_fwd(hid, B, pfx + ".linear2", bias=self.P[pfx + ".linear2.bias"])
                 t, _ = self._ln_fwd(t2, y3, B, pfx + ".norm3", 0.0, 0)
             logits = self.dec_head(t, B)
-            pred = torch.argmax(logits[:, :self.n_out_dec], dim=1)
-            tokens[:, s + 1] = pred
-            done |= pred == eos_tok
+            # arg-max, append and the stop latch: one libsst.so kernel (the bit-exact-critical index op of the search)
+            L.greedy_pick(logits, self.LDH, B, self.n_out_dec, tokens, 1, B, s + 1, eos_tok, done, n_done)
             n = s + 2
-            if n >= max_seq_length or ((s + 1) % check_every == 0 and bool(done.all())):
+            if n >= max_seq_length:
                 break
-        return tokens[:, :n]
+            if (s + 1) % check_every == 0:
+                n_done_host.copy_(n_done, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                if int(n_done_host[0]) == B:
+                    break
+        return tokens[:n].t().contiguous()
 
     def decode(self, y, tgt_lens, mem, mem_lens, B, Lm, training, seeds, ctx=None, tgt_pad=None):
         """y: (B, S) int64 CUDA; returns x_dec (B*S, D).  Target padding is either a suffix (`tgt_lens`, the training

@@ -7,6 +7,7 @@ are host-side only: the arg-max is taken on the logits (softmax is monotone, gre
 "has everybody finished" test is one device reduction instead of a Python loop over strings (:26-37)."""
 import torch
 
+from . import lib as L
 from .data_utils import PAD
 
 # data_utils.py:19 -- 40 phones + </S> (40), <S> (41), <PAD> (42)
@@ -36,17 +37,22 @@ def greedy_ids(model, length_raw_signal, X_raw, max_seq_length, device, start_to
     greedy_search.py:33-34) and are dropped by the caller."""
     memory, _ = model(length_raw_signal, device, mode='greedy_search', part='encoder', x_raw=X_raw)
     B = memory.shape[0]
-    dec_input = torch.full((B, 1), start_tok, dtype=torch.int64, device=memory.device)
-    done = torch.zeros(B, dtype=torch.bool, device=memory.device)
+    dev = memory.device
+    tokens = torch.full((B, max_seq_length), PAD, dtype=torch.int64, device=dev)
+    tokens[:, 0] = start_tok
+    done = torch.zeros(B, dtype=torch.uint8, device=dev)
+    n_done = torch.zeros(1, dtype=torch.int32, device=dev)
+    n = 1
     with torch.no_grad():
         while True:
-            step_logits = model(length_raw_signal, device, mode='greedy_search', part='decoder', y=dec_input, memory=memory)
-            pred = torch.argmax(step_logits[:, -1, :], dim=1)
-            dec_input = torch.cat((dec_input, pred.reshape(B, 1)), dim=1)
-            done |= pred == EOS
-            if dec_input.shape[1] >= max_seq_length or bool(done.all()):
+            step_logits = model(length_raw_signal, device, mode='greedy_search', part='decoder', y=tokens[:, :n], memory=memory)
+            # arg-max of the last position, append, stop latch: sst_greedy_pick (softmax is monotone, greedy_search.py:22-23)
+            C = step_logits.shape[2]
+            L.greedy_pick(step_logits[:, n - 1], n * C, B, C, tokens, max_seq_length, 1, n, EOS, done, n_done)
+            n += 1
+            if n >= max_seq_length or int(n_done[0]) == B:     # the reference looks at every step, too (greedy_search.py:37)
                 break
-    return dec_input.cpu()
+    return tokens[:, :n].cpu()
 
 
 def greedy_ids_cached(model, length_raw_signal, X_raw, max_seq_length, device, start_tok=SOS):

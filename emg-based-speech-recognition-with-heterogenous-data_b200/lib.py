@@ -260,6 +260,18 @@ def layernorm_bwd(dtype, rows, D, dy, s, mean, rstd, gamma, ds, dr, drop_p, seed
                                       ptr(dr), _f(drop_p), _u64(seed), ptr(dgamma), ptr(dbeta), stream()), "sst_layernorm_bwd")
 
 
+def gelu_dropout_fwd(dtype, rows, cols, x, ldx, drop_p, seed, y, ldy):
+    with _scope("gelu_fwd", bytes=2.0 * rows * cols * (2 if dtype == BF16 else 4), tag="rows%d" % rows):      # read x, write y
+        check(lib().sst_gelu_dropout_fwd(dtype, _i64(rows), cols, ptr(x), _i64(ldx), _f(drop_p), _u64(seed), ptr(y), _i64(ldy), stream()),
+              "sst_gelu_dropout_fwd")
+
+
+def gelu_dropout_bwd(dtype, rows, cols, dy, lddy, x, ldx, drop_p, seed, dx, lddx):
+    with _scope("gelu_bwd", bytes=3.0 * rows * cols * (2 if dtype == BF16 else 4), tag="rows%d" % rows):      # read dy, x; write dx
+        check(lib().sst_gelu_dropout_bwd(dtype, _i64(rows), cols, ptr(dy), _i64(lddy), ptr(x), _i64(ldx), _f(drop_p), _u64(seed), ptr(dx),
+                                         _i64(lddx), stream()), "sst_gelu_dropout_bwd")
+
+
 def colstats(dtype, x, rows, Cc, ld, stats):
     with _scope("bn_colstats", bytes=1.0 * rows * Cc * (2 if dtype == BF16 else 4), tag="rows%d" % rows):
         check(lib().sst_colstats(dtype, ptr(x), _i64(rows), Cc, _i64(ld), ptr(stats), stream()), "sst_colstats")
@@ -318,6 +330,12 @@ def ce_sumexp_loss(logits_dtype, grad_dtype, rows, S, Cc, logits, ld, target, ig
 def ctc_greedy(logits_dtype, B, L, Cc, blank, logits, ld, in_lens, out_ids, out_lens):
     check(lib().sst_ctc_greedy(logits_dtype, B, L, Cc, blank, ptr(logits), _i64(ld), ptr(in_lens), ptr(out_ids), ptr(out_lens),
                                stream()), "sst_ctc_greedy")
+
+
+def greedy_pick(logits, row_stride, B, Cc, tokens, tok_stride_b, tok_stride_pos, pos, eos, done, n_done):
+    """tokens int64 (element strides given), done (B,) uint8, n_done (1,) int32 -- all on the device."""
+    check(lib().sst_greedy_pick(dt(logits), B, Cc, ptr(logits), _i64(row_stride), ptr(tokens), _i64(tok_stride_b), _i64(tok_stride_pos),
+                                int(pos), int(eos), ptr(done), ptr(n_done), stream()), "sst_greedy_pick")
 
 
 def shift_left(x, n_chunks, T, Cc, r):

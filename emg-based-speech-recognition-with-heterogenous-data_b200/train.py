@@ -15,7 +15,7 @@
 import torch
 
 from . import lib as L
-from .data_utils import combine_fixed_length
+from .data_utils import ChunkStager, combine_fixed_length
 
 PAD = 42
 
@@ -58,12 +58,12 @@ def stage_of(name, n_enc, n_dec):
     return "conv0"
 
 
-def prepare_batch(example):
+def prepare_batch(example, stager=None):
     """The host half of one training step (recognition_model.py:77, :85-87, :95-97) on a `collate_raw` dict
     (read_emg.py:463-504): X = combine_fixed_length(raw_emg, 1600); decoder input/target = phonemes[:, :-1] / [:, 1:] padded
     with 42; CTC target = phonemes without <S>/</S>.  Returns plain host tensors plus the python-side scalars."""
     pad_seq = torch.nn.utils.rnn.pad_sequence
-    X = combine_fixed_length(example['raw_emg'], 200 * 8)
+    X = combine_fixed_length(example['raw_emg'], 200 * 8, stager=stager)
     target = pad_seq(example['phonemes_int'], batch_first=True, padding_value=PAD)
     tgt_in = target[:, :-1].contiguous()
     tgt_out = target[:, 1:].contiguous()
@@ -350,11 +350,22 @@ class Trainer:
             self.lr = iteration * self.lr_target / self.warmup
 
     # ---- host-side batch preparation (recognition_model.py:77,85-87,95-97) ------------------------------------------
-    def prepare(self, example, pin=True):
-        """collate_raw dict -> host tensors (pinned) ready for an async H2D copy."""
-        host = prepare_batch(example)
-        if pin and self.dev.type == "cuda":
-            host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
+    def prepare(self, example, pin=True, reuse=False):
+        """collate_raw dict -> host tensors (pinned) ready for an async H2D copy.  The EMG chunks -- all but a few hundred bytes of
+        the batch -- are packed directly into page-locked memory (data_utils.ChunkStager).  `reuse`: alternate between two
+        long-lived staging buffers instead of allocating one per batch; the returned X is then only valid until the call after
+        the next one (what a training loop that prepares batch i+1 while batch i runs needs, Trainer.run)."""
+        pinned = pin and self.dev.type == "cuda"
+        if reuse:
+            if getattr(self, "_stagers", None) is None:
+                self._stagers, self._stager_i = [ChunkStager(pin=pinned), ChunkStager(pin=pinned)], 0
+            stager = self._stagers[self._stager_i & 1]
+            self._stager_i += 1
+        else:
+            stager = ChunkStager(pin=pinned)
+        host = prepare_batch(example, stager=stager)
+        if pinned:
+            host = {k: (v.pin_memory() if torch.is_tensor(v) and not v.is_pinned() else v) for k, v in host.items()}
         return host
 
     def to_device(self, host):

@@ -120,6 +120,14 @@ int sst_layernorm_fwd(int dtype, int64_t rows, int D, const void* x, const void*
 int sst_layernorm_bwd(int dtype, int64_t rows, int D, const void* dy, const void* s, const float* mean, const float* rstd,
                       const float* gamma, void* ds, void* dr, float drop_p, uint64_t seed, float* dgamma, float* dbeta,
                       void* stream);
+/*  sst_gelu_dropout_fwd/bwd : the exact (erf) GELU variant of the feed-forward activation (north_star "GELU FFN layers"; the code
+ *      as shipped uses ReLU, transformer.py:45,61 -- ReLU stays the default and rides in the GEMM epilogue).
+ *      y = keep ? gelu(x)/(1-p) : 0 ; dx = dy * gelu'(x) * keep/(1-p), keep = philox_keep16(seed, row*cols + col); x is the
+ *      saved PRE-activation.  dx may alias dy.  cols and pitches multiples of 8. */
+int sst_gelu_dropout_fwd(int dtype, int64_t rows, int cols, const void* x, int64_t ldx, float drop_p, uint64_t seed, void* y, int64_t ldy,
+                         void* stream);
+int sst_gelu_dropout_bwd(int dtype, int64_t rows, int cols, const void* dy, int64_t lddy, const void* x, int64_t ldx, float drop_p,
+                         uint64_t seed, void* dx, int64_t lddx, void* stream);
 int sst_colstats(int dtype, const void* x, int64_t rows, int C, int64_t ld, double* stats /*[2*C]*/, void* stream);
 /* out[c] += sum_rows x[r, c]  (bias gradients; fp32 accumulate) */
 int sst_colsum_accum(int dtype, const void* x, int64_t rows, int C, int64_t ld, float* out, void* stream);
@@ -201,6 +209,12 @@ int sst_ctc_loss(int logits_dtype, int grad_dtype, int B, int L, int C, int blan
  * torch.argmax + collapse on the reference's w_aux logits. */
 int sst_ctc_greedy(int logits_dtype, int B, int L, int C, int blank, const void* logits, int64_t ld, const int32_t* in_lens,
                    int32_t* out_ids, int32_t* out_lens, void* stream);
+/* One step of the reference's greedy attention-decoder search on the device (greedy_search.py:22-37: softmax/argmax of the last
+ * position, append, stop test): tokens[b*tok_stride_b + pos*tok_stride_pos] = arg-max_c logits[b*row_stride + c] (lowest index wins
+ * ties, as torch.argmax), done[b] |= (token == eos), n_done[0] = number of samples with done set -- the only thing the host has
+ * to look at. */
+int sst_greedy_pick(int logits_dtype, int B, int C, const void* logits, int64_t row_stride, int64_t* tokens, int64_t tok_stride_b,
+                    int64_t tok_stride_pos, int pos, int eos, uint8_t* done, int32_t* n_done, void* stream);
 int sst_ce_sumexp_loss(int logits_dtype, int grad_dtype, int64_t rows, int S, int C, const void* logits, int64_t ld,
                        const int64_t* target, int ignore, float eps, int64_t n_valid, float gcoef, float* row_ws, void* grad,
                        int64_t ldg, float* loss_out, void* stream);

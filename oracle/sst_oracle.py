@@ -232,6 +232,12 @@ def _relu(x, site):
     return x * RELU_MASKS[site].to(x.dtype)
 
 
+def _ffn_act(x, site, cfg):
+    """transformer.py:45,61: ReLU as shipped; cfg['activation'] == 'gelu' is the exact-erf variant north_star names (no reference
+    code: the oracle for it is torch's F.gelu)."""
+    return F.gelu(x) if cfg.get("activation", "relu") == "gelu" else _relu(x, site)
+
+
 def res_block(x, sd, prefix, stride, training, stats_out=None):
     """ResBlock.forward, architecture.py:37-48."""
     inp = x
@@ -341,7 +347,7 @@ def encoder_layer(src, sd, prefix, cfg, training, kpm, as_written=True):
     src2 = multi_head_attention(src, src, src, sd, prefix + ".self_attn", cfg, training, True,
                                 src_key_padding_mask=kpm, as_written=as_written)
     src = layer_norm(src + F.dropout(src2, p, training), sd, prefix + ".norm1")
-    h = F.dropout(_relu(F.linear(src, sd[prefix + ".linear1.weight"], sd[prefix + ".linear1.bias"]), prefix + ".relu"), p, training)
+    h = F.dropout(_ffn_act(F.linear(src, sd[prefix + ".linear1.weight"], sd[prefix + ".linear1.bias"]), prefix + ".relu", cfg), p, training)
     src2 = F.linear(h, sd[prefix + ".linear2.weight"], sd[prefix + ".linear2.bias"])
     return layer_norm(src + F.dropout(src2, p, training), sd, prefix + ".norm2")
 
@@ -355,7 +361,7 @@ def decoder_layer(tgt, memory, sd, prefix, cfg, training, tgt_mask, tgt_kpm, mem
     t2 = multi_head_attention(tgt, memory, memory, sd, prefix + ".multihead_attn", cfg, training, False,
                               memory_key_padding_mask=mem_kpm)
     tgt = layer_norm(tgt + F.dropout(t2, p, training), sd, prefix + ".norm2")
-    h = F.dropout(_relu(F.linear(tgt, sd[prefix + ".linear1.weight"], sd[prefix + ".linear1.bias"]), prefix + ".relu"), p, training)
+    h = F.dropout(_ffn_act(F.linear(tgt, sd[prefix + ".linear1.weight"], sd[prefix + ".linear1.bias"]), prefix + ".relu", cfg), p, training)
     t2 = F.linear(h, sd[prefix + ".linear2.weight"], sd[prefix + ".linear2.bias"])
     return layer_norm(tgt + F.dropout(t2, p, training), sd, prefix + ".norm3")
 

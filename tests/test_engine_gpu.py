@@ -209,3 +209,34 @@ def test_edge_case_batches_match_the_oracle(name, dtype):
     gmax = max(float(g.abs().max()) for g in grads.values())
     rows = l2_rows(names, flat(G), flat(grads), flat(g64), flat(gbf) if gbf is not None else None, gmax)
     assert_l2_rows(rows, tol, bf16, "%s %s" % (name, dtype))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gelu_ffn_variant_matches_the_oracle(dtype):
+    """north_star names GELU FFN layers; the reference as shipped uses ReLU.  With cfg['activation'] = 'gelu' the engine
+    runs the exact-erf GELU kernels (sst_gelu_dropout_fwd/bwd) in the encoder and decoder FFNs; oracle = the same restatement with
+    torch's F.gelu.  fp32 1e-4, bf16 2e-2, every tensor in relative L2 with the usual two yardsticks."""
+    cfg = O.make_cfg(n_enc=2, n_dec=1, rel_dist=100, alpha=0.3)
+    cfg["activation"] = "gelu"
+    sd = O.synthetic_state_dict(cfg, 17)
+    batch = O.synthetic_batch(seed=310, ragged=[131, 200, 67], tgt_lens=[7, 17, 4])
+    res, grads, _ = O.loss_and_grads({k: v.clone() for k, v in sd.items()}, cfg, batch, True, 0)
+    relu_res, _, _ = O.loss_and_grads({k: v.clone() for k, v in sd.items()}, dict(cfg, activation="relu"), batch, True, 0)
+    assert abs(float(res["loss"]) - float(relu_res["loss"])) > 3e-4 * abs(float(res["loss"]))        # the two activations really differ here
+    eng = make_engine(cfg, sd, dtype)
+    out_enc, out_dec, loss, loss_dec, loss_enc, G, ctx = run_step(eng, cfg, batch)
+    bf16 = dtype == torch.bfloat16
+    tol = 2e-2 if bf16 else 1e-4
+    assert abs(loss - float(res["loss"])) < tol * abs(float(res["loss"]))
+    assert _valid_frames_err(out_enc, res["out_enc"], batch["lengths"]) < tol
+    assert rel_err(out_dec, res["out_dec"]) < tol
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    b64 = dict(batch)
+    b64["raw_emg"] = [x.double() for x in batch["raw_emg"]]
+    _, g64, _ = O.loss_and_grads(sd64, cfg, b64, True, 0)
+    gbf = oracle_autocast_bf16_grads(sd, cfg, batch) if bf16 else None
+    names = sorted(grads)
+    flat = lambda d: {n: d[n].detach().double().cpu().reshape(-1).numpy() for n in names}      # noqa: E731
+    gmax = max(float(g.abs().max()) for g in grads.values())
+    rows = l2_rows(names, flat(G), flat(grads), flat(g64), flat(gbf) if gbf is not None else None, gmax)
+    assert_l2_rows(rows, tol, bf16, "gelu %s" % dtype)

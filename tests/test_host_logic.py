@@ -17,7 +17,7 @@ import sst_b200  # noqa: E402,F401
 from sst_b200 import lib as L  # noqa: E402
 from sst_b200 import train as T  # noqa: E402
 from sst_b200.synthetic import make_batch, lognormal_lengths  # noqa: E402
-from sst_b200.data_utils import combine_fixed_length, decollate_tensor  # noqa: E402
+from sst_b200.data_utils import combine_fixed_length, ChunkStager  # noqa: E402
 
 
 def declared_symbols():
@@ -58,18 +58,19 @@ def test_prepare_batch_matches_reference_step_arithmetic():
     assert host["tgt_lens"].tolist() == (tgt_in != 42).sum(1).tolist()
 
 
-def test_combine_and_decollate_round_trip():
+def test_chunk_stager_packs_like_the_reference_packer():
+    """sst_b200.data_utils.combine_fixed_length / ChunkStager against the oracle's restatement of data_utils.py:165-174 (itself
+    pinned to the unmodified reference): exact multiple of the chunk (no tail), ragged tail filled with the VALUE 42, a single
+    short utterance, and buffer reuse by a second, smaller batch."""
     g = torch.Generator().manual_seed(0)
-    parts = [torch.randn(n, 8, generator=g) for n in (800, 1234, 66)]
-    X = combine_fixed_length(parts, 1600)
-    assert X.shape == (2, 1600, 8)
-    flat = X.view(-1, 8)
-    assert torch.equal(flat[:2100], torch.cat(parts)) and bool((flat[2100:] == 42).all())
-    back = decollate_tensor(X, [800, 1234, 66])
-    for a, b in zip(back, parts):
-        assert torch.equal(a, b)
-    with pytest.raises(AssertionError):
-        decollate_tensor(X, [3000, 1000])                   # data_utils.py:182
+    stager = ChunkStager(pin=False)
+    for sizes in ((800, 1234, 66), (1600, 1600), (5,), (3200, 1)):
+        parts = [torch.randn(n, 8, generator=g) for n in sizes]
+        want = O.combine_fixed_length(parts, 1600)
+        for got in (combine_fixed_length(parts, 1600), combine_fixed_length(parts, 1600, stager=stager)):
+            assert got.shape == want.shape and got.is_contiguous() and torch.equal(got, want)
+    flat = combine_fixed_length([torch.zeros(2100, 8)], 1600).view(-1, 8)
+    assert bool((flat[:2100] == 0).all()) and bool((flat[2100:] == 42).all())
 
 
 def test_synthetic_batch_contract():

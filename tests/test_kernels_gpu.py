@@ -429,3 +429,61 @@ def test_permute3_batch_replays_recorded_permutes(L):
         L.permute3_cast(outs[0], outs[1], (1, 768, 768), (0, 1, 768), (0, 768, 1))
     assert chained.hazard == (0, 1) or chained.hazard == (1, 0)
     assert not chained.valid()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("p", [0.0, 0.2])
+def test_gelu_dropout_fwd_bwd(L, dtype, p):
+    """sst_gelu_dropout_fwd/bwd against torch's exact-erf F.gelu (+ the host mirror of the Philox keep mask): fp32 2e-5, bf16 at the
+    rounding of its 8-bit mantissa; pitched (non-contiguous) operands; dx written in place over dy."""
+    from helpers import philox_keep_mask16
+    g = torch.Generator(device=DEV).manual_seed(11)
+    rows, cols, ld = 333, 3072, 3072 + 64
+    xw = (torch.randn(rows, ld, device=DEV, generator=g) * 1.5).to(dtype)
+    x = xw[:, :cols]
+    y = torch.full((rows, cols), 7.0, device=DEV, dtype=dtype)
+    seed = 4242
+    L.gelu_dropout_fwd(L.dt(x), rows, cols, x, ld, p, seed, y, cols)
+    keep = philox_keep_mask16(seed, rows * cols, p).view(rows, cols).to(DEV) if p > 0 else torch.ones(rows, cols, dtype=torch.bool, device=DEV)
+    xl = x.float().clone().requires_grad_(True)
+    ref = F.gelu(xl) * keep / (1.0 - p)
+    tol = 2e-5 if dtype == torch.float32 else 8e-3
+    assert rel(y.float(), ref.detach()) < tol
+    if p > 0:
+        assert abs(float(keep.float().mean()) - (1 - p)) < 5e-3 and bool(((y == 0) | keep).all())
+    dy = torch.randn(rows, cols, device=DEV, generator=g).to(dtype)
+    ref.backward(dy.float())
+    dx = dy.clone()
+    L.gelu_dropout_bwd(L.dt(x), rows, cols, dx, cols, x, ld, p, seed, dx, cols)
+    assert rel(dx.float(), xl.grad) < tol
+
+
+def test_greedy_pick_kernel(L):
+    """sst_greedy_pick: arg-max with the lowest index winning ties (torch.argmax), append at a strided position, stop latch and the
+    finished-sample count -- bit-exact."""
+    g = torch.Generator().manual_seed(5)
+    B, C, ld, T = 37, 43, 64, 9
+    logits = torch.randn(B, ld, generator=g)
+    logits[3, :] = 0.25                       # all ties -> index 0
+    logits[4, 40] = 9.0                       # </S>
+    logits[5, 10] = logits[5, 30] = 8.0       # two-way tie -> 10
+    dev_logits = logits.to(DEV)
+    for layout in ("row", "pos"):
+        tokens = torch.full((B, T) if layout == "row" else (T, B), 42, dtype=torch.int64, device=DEV)
+        done = torch.zeros(B, dtype=torch.uint8, device=DEV)
+        done[7] = 1
+        n_done = torch.zeros(1, dtype=torch.int32, device=DEV)
+        sb, sp = (T, 1) if layout == "row" else (1, B)
+        L.greedy_pick(dev_logits, ld, B, C, tokens, sb, sp, 4, 40, done, n_done)
+        want = logits[:, :C].argmax(1)
+        got = (tokens[:, 4] if layout == "row" else tokens[4]).cpu()
+        assert torch.equal(got, want) and int(got[3]) == 0 and int(got[5]) == 10
+        rest = tokens.clone()
+        if layout == "row":
+            rest[:, 4] = 42
+        else:
+            rest[4] = 42
+        assert bool((rest == 42).all())
+        want_done = (want == 40)
+        want_done[7] = True
+        assert torch.equal(done.cpu().bool(), want_done) and int(n_done[0]) == int(want_done.sum())
