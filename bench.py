@@ -290,16 +290,17 @@ def run_ours(args, w):
         roof = {"kernel": dk, "bound": "hbm", "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s",
                 "frac": round(ach / pk["hbm"], 4), "traffic": None, "launches_per_step": dd["launches"],
                 "avg_launch_ms": round(dd["ms"] / dd["launches"], 4), "peak_source": pk["source"]}
-    # DRAM traffic of the dominant kernel, per launch: taken from the committed ncu capture of the same workload
-    # (profiles/r01_kernel_traffic.json, written by tools/kernel_traffic.py from `ncu --metrics dram__bytes_read.sum,
-    # dram__bytes_write.sum` over one step); null when the capture does not cover this workload / kernel family
+    # DRAM traffic of the dominant kernel family, per launch: from the committed ncu capture of one step of the same workload
+    # (profiles/r02_kernel_traffic.json, tools/traffic_step.py + tools/kernel_traffic.py: dram__bytes_read.sum + dram__bytes_write.sum of
+    # every launch, grouped per family); null when the capture does not cover this workload / family
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_kernel_traffic.json")))
         ent = tr.get(w["name"], {}).get(dk)
-        if ent and ent["launches_per_step"] == dd["launches"]:
+        if ent:
             roof["traffic"] = ent["avg_bytes_per_launch"]
-            roof["traffic_note"] = "ncu dram bytes / launch, %s; algorithmic operand+result bytes / launch: %d" % (
-                tr["source"], int(dd["bytes"] / dd["launches"]))
+            roof["traffic_note"] = ("ncu dram bytes per launch, family average over the %d launches of one step (this run: %d); algorithmic "
+                                    "operand + result bytes per launch here: %d" % (ent["launches_per_step"], dd["launches"],
+                                                                                    int(dd["bytes"] / dd["launches"])))
     except (OSError, ValueError, KeyError):
         pass
     # whole-step tensor roofline: algorithmic flops of every GEMM/attention launch / step time

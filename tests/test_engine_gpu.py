@@ -240,3 +240,63 @@ def test_gelu_ffn_variant_matches_the_oracle(dtype):
     gmax = max(float(g.abs().max()) for g in grads.values())
     rows = l2_rows(names, flat(G), flat(grads), flat(g64), flat(gbf) if gbf is not None else None, gmax)
     assert_l2_rows(rows, tol, bf16, "gelu %s" % dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_no_kernel_writes_outside_its_buffers(dtype):
+    """compute-sanitizer is closed on this GPU pool (profiles/r02_sanitizer_note.txt), so the out-of-bounds check is done by hand:
+    every buffer the engine allocates during a training step (activations, saved statistics, workspaces, gradients) sits between
+    two 1 KiB canary bands; after forward + losses + backward every band must be intact.  Ragged batch whose lengths are no multiple
+    of any tile size, last chunk partly filled, both FFN activations."""
+    from sst_b200.engine import Engine
+    GUARD = 1024
+    arenas = []
+
+    def guarded(shape, tdtype, dev, fill):
+        numel = 1
+        for s_ in shape:
+            numel *= int(s_)
+        nbytes = numel * torch.empty((), dtype=tdtype).element_size()
+        pad = (-nbytes) % 16
+        raw = torch.full((GUARD + nbytes + pad + GUARD,), 0xA5, dtype=torch.uint8, device=dev)
+        body = raw[GUARD:GUARD + nbytes].view(tdtype).view(*shape)
+        if fill is not None:
+            body.fill_(fill)
+        arenas.append((raw, nbytes + pad))
+        return body
+
+    class GuardedEngine(Engine):
+        def empty(self, *shape, dtype=None):
+            return guarded(shape, dtype or self.dtype, self.dev, None)
+
+        def zeros(self, *shape, dtype=None):
+            return guarded(shape, dtype or self.dtype, self.dev, 0)
+
+    for act in ("relu", "gelu"):
+        cfg = O.make_cfg(n_enc=2, n_dec=1, rel_dist=100, alpha=0.2, dropout=0.2, dropout_pos=0.2)
+        cfg["activation"] = act
+        sd = O.synthetic_state_dict(cfg, 5)
+        batch = O.synthetic_batch(seed=77, ragged=[131, 8, 333, 67, 1], tgt_lens=[3, 1, 17, 2, 1])
+        params, buffers = {}, {}
+        for k, v in sd.items():
+            t = v.to(DEV).contiguous()
+            (buffers if (k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked") or k == "pos_decoder.pe")
+             else params)[k] = t
+        eng = GuardedEngine(params, buffers, cfg, dtype=dtype)
+        eng.pack()
+        X = O.combine_fixed_length(batch["raw_emg"]).to(DEV)
+        tgt_in, tgt_out, ctc_tgt, ctc_lens = O.make_targets(batch)
+        nmax = max(batch["phonemes_int_lengths"])
+        tgt_lens = torch.tensor([min(n, nmax - 1) for n in batch["phonemes_int_lengths"]], dtype=torch.int32, device=DEV)
+        _, _, ctx = eng.forward(X, batch["lengths"], tgt_in.to(DEV).contiguous(), tgt_lens, training=True, seed=3)
+        eng.losses(ctx, ctc_tgt.to(DEV).contiguous(), torch.tensor(ctc_lens, dtype=torch.int32, device=DEV),
+                   tgt_out.to(DEV).contiguous().view(-1), int((tgt_out != 42).sum()), cfg["alpha"], cfg["eps_ls"])
+        G = {n: guarded(p.shape, torch.float32, DEV, 0) for n, p in eng.P.items()}
+        eng.backward(ctx, G)
+        torch.cuda.synchronize()
+        assert all(bool(torch.isfinite(g).all()) for g in G.values())
+    assert len(arenas) > 200
+    bad = 0
+    for raw, nb in arenas:
+        bad += int((raw[:GUARD] != 0xA5).sum()) + int((raw[GUARD + nb:] != 0xA5).sum())
+    assert bad == 0, "%d canary bytes overwritten across %d buffers" % (bad, len(arenas))
