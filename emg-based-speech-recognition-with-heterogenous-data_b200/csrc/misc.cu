@@ -196,9 +196,60 @@ permute3_tiled_kernel(const TI* __restrict__ in, TO* __restrict__ out, long d1, 
 __device__ __forceinline__ float ld_any(const void* p, long i, int dtype) { return ld_as_f32(p, i, dtype); }
 __device__ __forceinline__ void st_any(void* p, long i, int dtype, float v) { st_from_f32(p, i, dtype, v); }
 
+// modes 3 / 4: 64 x 64 tiles, 16-byte global accesses on both sides, bf16 output (the big weight transposes of the repack: the
+// 32 x 32 scalar tiles above move 2 bytes per thread and instruction and pay the item lookup per 1024 elements).
+// c = the input's contiguous dimension (j in mode 3, k in mode 4), r = the other one, which is the output's contiguous dimension.
+// Shared tile: row r, 16-byte chunk (c / 8) XOR (r / 8 % 8) -- both the vector stores of the read phase and the 2-byte column
+// gathers of the write phase are bank-conflict free.
+constexpr int PT_TILES_PER_BLOCK = 4;
+template <typename TI>
+__device__ __forceinline__ void permute_tile64(const SstPermuteItem& it, bool in_j, long a, long j0, long k0, uint16_t (*tile)[64]) {
+  const TI* in = reinterpret_cast<const TI*>(it.in);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(it.out);
+  const long dC = in_j ? it.d1 : it.d2, dR = in_j ? it.d2 : it.d1;
+  const long c0 = in_j ? j0 : k0, r0 = in_j ? k0 : j0;
+  const long s_r = in_j ? it.s2 : it.s1, o_c = in_j ? it.o1 : it.o2;
+  const int t = threadIdx.x;
+  {
+    const int cv = t & 7;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int rl = (t >> 3) + 32 * h;
+      const long r = r0 + rl, c = c0 + 8 * cv;
+      uint4 w = make_uint4(0u, 0u, 0u, 0u);
+      if (r < dR && c < dC) {
+        float v[8];
+        Vec8<TI>::load(in + a * it.s0 + r * s_r + c, v);
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+      }
+      *reinterpret_cast<uint4*>(&tile[rl][((cv ^ (rl >> 3)) & 7) * 8]) = w;
+    }
+  }
+  __syncthreads();
+  {
+    const int rv = t & 7;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int cl = (t >> 3) + 32 * h;
+      const long c = c0 + cl, r = r0 + 8 * rv;
+      if (c < dC && r < dR) {
+        uint4 w;
+        uint16_t* hw = reinterpret_cast<uint16_t*>(&w);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) hw[e] = tile[8 * rv + e][(((cl >> 3) ^ rv) & 7) * 8 + (cl & 7)];
+        *reinterpret_cast<uint4*>(out + a * it.o0 + c * o_c + r) = w;
+      }
+    }
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(256)
 permute3_batch_kernel(const SstPermuteItem* __restrict__ items, int n_items) {
-  __shared__ float tile[32][33];
+  __shared__ __align__(16) float tile[32][33];
+  __shared__ __align__(16) uint16_t tile64[64][64];
   __shared__ int s_item;
   if (threadIdx.x == 0) {
     int lo = 0, hi = n_items - 1;
@@ -220,6 +271,17 @@ permute3_batch_kernel(const SstPermuteItem* __restrict__ items, int n_items) {
       float v = ld_any(it.in, a * it.s0 + j * it.s1 + k * it.s2, it.in_dtype);
       if (it.accumulate) v += ld_any(it.out, oi, it.out_dtype);
       st_any(it.out, oi, it.out_dtype, v);
+    }
+    return;
+  }
+  if (it.mode >= 3) {
+    const bool inj = it.mode == 3;
+    const long tk = (it.d2 + 63) / 64, tj = (it.d1 + 63) / 64, tiles = tk * tj * it.d0;
+    for (long tl = (long)lb * PT_TILES_PER_BLOCK; tl < tiles && tl < (long)(lb + 1) * PT_TILES_PER_BLOCK; ++tl) {
+      const long a = tl / (tk * tj), rem = tl - a * tk * tj;
+      const long j0 = (rem / tk) * 64, k0 = (rem % tk) * 64;
+      if (it.in_dtype == SST_F32) permute_tile64<float>(it, inj, a, j0, k0, tile64);
+      else permute_tile64<__nv_bfloat16>(it, inj, a, j0, k0, tile64);
     }
     return;
   }
@@ -431,7 +493,15 @@ int sst_permute3_plan(SstPermuteItem* items, int n_items, int* total_blocks) {
     SST_REQUIRE(total > 0, SST_E_ARG, "permute3_plan: item %d is empty", i);
     const bool in_j = (it.s1 == 1 && it.o2 == 1 && it.s2 != 1), in_k = (it.s2 == 1 && it.o1 == 1 && it.o2 != 1);
     it.first_block = (int)nb;
-    if ((in_j || in_k) && it.d1 >= 32 && it.d2 >= 32) {
+    const long s_r = in_j ? it.s2 : it.s1, o_c = in_j ? it.o1 : it.o2;
+    const bool vec_ok = (in_j || in_k) && it.out_dtype == SST_BF16 && !it.accumulate && it.d1 % 8 == 0 && it.d2 % 8 == 0 && it.d1 >= 16 &&
+                        it.d2 >= 16 && s_r % 8 == 0 && o_c % 8 == 0 && (it.d0 == 1 || (it.s0 % 8 == 0 && it.o0 % 8 == 0)) &&
+                        ((uintptr_t)it.in & 31) == 0 && ((uintptr_t)it.out & 15) == 0;
+    if (vec_ok) {
+      it.mode = in_j ? 3 : 4;
+      const long tiles = ((it.d2 + 63) / 64) * ((it.d1 + 63) / 64) * it.d0;
+      it.nblocks = (int)((tiles + PT_TILES_PER_BLOCK - 1) / PT_TILES_PER_BLOCK);
+    } else if ((in_j || in_k) && it.d1 >= 32 && it.d2 >= 32) {
       it.mode = in_j ? 1 : 2;
       it.nblocks = (int)(((it.d2 + 31) / 32) * ((it.d1 + 31) / 32) * it.d0);
     } else {

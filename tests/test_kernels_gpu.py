@@ -396,9 +396,14 @@ def test_permute3_batch_replays_recorded_permutes(L):
     a2 = torch.randn(300, 200, device=DEV, generator=g).to(torch.bfloat16)
     small = torch.randn(5, 7, 3, device=DEV, generator=g)
     acc_src = torch.randn(64, 96, device=DEV, generator=g)
+    wl = torch.randn(3072, 768, device=DEV, generator=g).to(torch.bfloat16)    # a linear weight: the vectorised 64 x 64 transposes
+    odd = torch.randn(3, 72, 104, device=DEV, generator=g).to(torch.bfloat16)  # partial 64 x 64 tiles, three planes
 
     def run(outs):
-        W, WT, A2T, S, ACC = outs
+        W, WT, A2T, S, ACC, WLT, WLT2, ODDT = outs
+        L.permute3_cast(wl, WLT, (1, 3072, 768), (0, 768, 1), (0, 1, 3072))                        # bf16 -> bf16, input contiguous along k
+        L.permute3_cast(wl, WLT2, (1, 768, 3072), (0, 1, 768), (0, 3072, 1))                       # the same transpose, contiguous along j
+        L.permute3_cast(odd, ODDT, (3, 72, 104), (72 * 104, 104, 1), (72 * 104, 1, 72))
         L.permute3_cast(w, W, (8, 96, 768), (768 * 96, 1, 96), (96 * 768, 768, 1))                # tiled, input contiguous along j
         L.permute3_cast(w, WT, (8, 768, 96), (768 * 96, 96, 1), (96, 768, 1))                     # per-head transpose, 96-element runs
         L.permute3_cast(a2, A2T, (1, 200, 300), (0, 1, 200), (0, 300, 1))                         # ragged tile edges, bf16 -> fp32
@@ -407,17 +412,19 @@ def test_permute3_batch_replays_recorded_permutes(L):
 
     def fresh():
         return (torch.empty(768, 768, device=DEV, dtype=torch.bfloat16), torch.empty(768, 768, device=DEV, dtype=torch.bfloat16),
-                torch.empty(200, 300, device=DEV), torch.empty(5, 3, 7, device=DEV), torch.full((96, 64), 2.0, device=DEV))
+                torch.empty(200, 300, device=DEV), torch.empty(5, 3, 7, device=DEV), torch.full((96, 64), 2.0, device=DEV),
+                torch.empty(768, 3072, device=DEV, dtype=torch.bfloat16), torch.empty(768, 3072, device=DEV, dtype=torch.bfloat16),
+                torch.empty(3, 104, 72, device=DEV, dtype=torch.bfloat16))
     ref = fresh()
     run(ref)
+    assert torch.equal(ref[5], wl.t()) and torch.equal(ref[6], wl.t()) and torch.equal(ref[7], odd.transpose(1, 2))
     outs = fresh()
     plan = L.PermutePlan()
     with plan.record():
         run(outs)
-    for o in outs[:4]:
-        o.fill_(7)
-    outs[4].fill_(2.0)
-    assert plan.valid() and plan.n == 5
+    for k, o in enumerate(outs):
+        o.fill_(2.0 if k == 4 else 7)
+    assert plan.valid() and plan.n == 8
     plan.replay()
     torch.cuda.synchronize()
     for o, r in zip(outs, ref):
