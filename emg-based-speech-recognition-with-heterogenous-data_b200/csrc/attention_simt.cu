@@ -14,7 +14,14 @@ struct AttnP {
   uint32_t thr; float dscale; unsigned long long seed;
   const int* q_lens; const int* k_lens;
   const uint8_t* q_pad; const uint8_t* k_pad;
+  const long long* q_off; const long long* k_off;     // packed layouts (include/sst.h): first row of entry b, or null
 };
+
+// first row of batch entry b in the query-side / key-side matrices, and the rows that exist for it
+__device__ __forceinline__ long q_base(const AttnP& p, int b) { return p.q_off ? (long)p.q_off[b] : (long)b * p.Lq; }
+__device__ __forceinline__ long k_base(const AttnP& p, int b) { return p.k_off ? (long)p.k_off[b] : (long)b * p.Lk; }
+__device__ __forceinline__ int q_rows(const AttnP& p, int b) { return p.q_off ? min(p.q_lens[b], p.Lq) : p.Lq; }
+__device__ __forceinline__ int k_rows(const AttnP& p, int b) { return p.k_off ? min(p.k_lens[b], p.Lk) : p.Lk; }
 
 template <typename T>
 __device__ __forceinline__ float dot_row(const float* __restrict__ a_smem, const T* __restrict__ row, int dh) {
@@ -40,9 +47,12 @@ __device__ __forceinline__ float make_logit(const AttnP& p, int b, int i, int j,
   return s;
 }
 
-__device__ __forceinline__ void key_range(const AttnP& p, int i, int& lo, int& hi) {
+// keys a query row visits.  Packed layouts: keys j >= k_rows(b) do not exist in memory (their probability is exactly 0 in the
+// padded layout as well, where they are masked with -1e8 next to at least one real key)
+__device__ __forceinline__ void key_range(const AttnP& p, int b, int i, int& lo, int& hi) {
   lo = 0; hi = p.Lk - 1;
   if (p.R > 0 && p.Lk > p.R) { lo = max(0, i - p.R + 1); hi = min(p.Lk - 1, i + p.R - 1); }
+  hi = min(hi, k_rows(p, b) - 1);
 }
 
 template <typename T>
@@ -59,16 +69,18 @@ attn_fwd_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __restr
   const int i = (int)(row_id % p.Lq);
   const int h = (int)((row_id / p.Lq) % p.H);
   const int b = (int)(row_id / ((long)p.Lq * p.H));
-  const T* qrow = q + ((long)b * p.Lq + i) * p.ldq + h * p.dh;
+  if (i >= q_rows(p, b)) return;                 // packed layout: the row does not exist
+  const long qb = q_base(p, b), kb = k_base(p, b);
+  const T* qrow = q + (qb + i) * p.ldq + h * p.dh;
   for (int a = lane; a < p.dh; a += 32) qs[a] = to_f32(qrow[a]);
   __syncwarp();
   int lo, hi;
-  key_range(p, i, lo, hi);
+  key_range(p, b, i, lo, hi);
   const int nk = hi - lo + 1;
   float mx = -INFINITY;
   for (int jj = lane; jj < nk; jj += 32) {
     const int j = lo + jj;
-    const float qk = dot_row(qs, k + ((long)b * p.Lk + j) * p.ldk + h * p.dh, p.dh);
+    const float qk = dot_row(qs, k + (kb + j) * p.ldk + h * p.dh, p.dh);
     float qe = 0.f;
     const int rel = j - i;
     if (p.R > 0 && rel > -p.R && rel < p.R) qe = dot_row(qs, E + ((long)h * (2 * p.R - 1) + rel + p.R - 1) * p.dh, p.dh);
@@ -92,9 +104,9 @@ attn_fwd_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __restr
   __syncwarp();
   for (int a = lane; a < p.dh; a += 32) {
     float acc = 0.f;
-    const T* vp = v + ((long)b * p.Lk + lo) * p.ldv + h * p.dh + a;
+    const T* vp = v + (kb + lo) * p.ldv + h * p.dh + a;
     for (int jj = 0; jj < nk; ++jj) acc = fmaf(sc[jj], to_f32(vp[(long)jj * p.ldv]), acc);
-    o[((long)b * p.Lq + i) * p.ldo + h * p.dh + a] = from_f32<T>(acc);
+    o[(qb + i) * p.ldo + h * p.dh + a] = from_f32<T>(acc);
   }
 }
 
@@ -115,7 +127,8 @@ attn_bwd_dq_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __re
   const int i = (int)(row_id % p.Lq);
   const int h = (int)((row_id / p.Lq) % p.H);
   const int b = (int)(row_id / ((long)p.Lq * p.H));
-  const long tok = (long)b * p.Lq + i;
+  if (i >= q_rows(p, b)) return;
+  const long tok = q_base(p, b) + i, kb = k_base(p, b);
   float dl = 0.f;
   for (int a = lane; a < p.dh; a += 32) {
     qs[a] = to_f32(q[tok * p.ldq + h * p.dh + a]);
@@ -128,11 +141,11 @@ attn_bwd_dq_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __re
   __syncwarp();
   const float Lm = lse[row_id], Ll = lse[(long)p.B * p.H * p.Lq + row_id];
   int lo, hi;
-  key_range(p, i, lo, hi);
+  key_range(p, b, i, lo, hi);
   const int nk = hi - lo + 1;
   for (int jj = lane; jj < nk; jj += 32) {
     const int j = lo + jj;
-    const float qk = dot_row(qs, k + ((long)b * p.Lk + j) * p.ldk + h * p.dh, p.dh);
+    const float qk = dot_row(qs, k + (kb + j) * p.ldk + h * p.dh, p.dh);
     float qe = 0.f;
     const int rel = j - i;
     const bool inband = p.R > 0 && rel > -p.R && rel < p.R;
@@ -140,7 +153,7 @@ attn_bwd_dq_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     bool masked;
     const float s = make_logit(p, b, i, j, qk, qe, masked);
     const float pr = __expf((s - Lm) - Ll);
-    float dp = dot_row(dos, v + ((long)b * p.Lk + j) * p.ldv + h * p.dh, p.dh);
+    float dp = dot_row(dos, v + (kb + j) * p.ldv + h * p.dh, p.dh);
     if (p.thr) dp = philox_keep16(p.seed, (unsigned long long)row_id * p.Lkp + j, p.thr) ? dp * p.dscale : 0.f;
     const float ds = pr * (dp - dl);
     dsq[jj] = masked ? 0.f : ds * p.scale;
@@ -149,7 +162,7 @@ attn_bwd_dq_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __re
   __syncwarp();
   for (int a = lane; a < p.dh; a += 32) {
     float acc = 0.f;
-    const T* kp = k + ((long)b * p.Lk + lo) * p.ldk + h * p.dh + a;
+    const T* kp = k + (kb + lo) * p.ldk + h * p.dh + a;
     for (int jj = 0; jj < nk; ++jj) acc = fmaf(dsq[jj], to_f32(kp[(long)jj * p.ldk]), acc);
     if (p.R > 0) {
       for (int jj = 0; jj < nk; ++jj) {
@@ -178,7 +191,8 @@ attn_bwd_dkv_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __r
   const int j = (int)(row_id % p.Lk);
   const int h = (int)((row_id / p.Lk) % p.H);
   const int b = (int)(row_id / ((long)p.Lk * p.H));
-  const long tokk = (long)b * p.Lk + j;
+  if (j >= k_rows(p, b)) return;                 // packed layout: the key does not exist
+  const long tokk = k_base(p, b) + j, qb = q_base(p, b);
   for (int a = lane; a < p.dh; a += 32) {
     ks[a] = to_f32(k[tokk * p.ldk + h * p.dh + a]);
     vs[a] = to_f32(v[tokk * p.ldv + h * p.dh + a]);
@@ -186,10 +200,11 @@ attn_bwd_dkv_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __r
   __syncwarp();
   int lo = 0, hi = p.Lq - 1;
   if (p.R > 0 && p.Lk > p.R) { lo = max(0, j - p.R + 1); hi = min(p.Lq - 1, j + p.R - 1); }
-  const int nq = hi - lo + 1;
+  hi = min(hi, q_rows(p, b) - 1);
+  const int nq = max(hi - lo + 1, 0);
   for (int ii = lane; ii < nq; ii += 32) {
     const int i = lo + ii;
-    const long tokq = (long)b * p.Lq + i;
+    const long tokq = qb + i;
     const long rid = ((long)b * p.H + h) * p.Lq + i;
     const T* qrow = q + tokq * p.ldq + h * p.dh;
     const float qk = dot_row(ks, qrow, p.dh);
@@ -213,8 +228,8 @@ attn_bwd_dkv_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __r
   __syncwarp();
   for (int a = lane; a < p.dh; a += 32) {
     float accv = 0.f, acck = 0.f;
-    const T* dop = dO + ((long)b * p.Lq + lo) * p.ldo + h * p.dh + a;
-    const T* qp = q + ((long)b * p.Lq + lo) * p.ldq + h * p.dh + a;
+    const T* dop = dO + (qb + lo) * p.ldo + h * p.dh + a;
+    const T* qp = q + (qb + lo) * p.ldq + h * p.dh + a;
     for (int ii = 0; ii < nq; ++ii) {
       accv = fmaf(pw[ii], to_f32(dop[(long)ii * p.ldo]), accv);
       acck = fmaf(dsw[ii], to_f32(qp[(long)ii * p.ldq]), acck);
@@ -235,6 +250,7 @@ static AttnP make_params(const SstAttnDesc& d, const int* q_lens, const int* k_l
   p.seed = d.seed;
   p.q_lens = q_lens; p.k_lens = k_lens;
   p.q_pad = d.q_pad; p.k_pad = d.k_pad;
+  p.q_off = reinterpret_cast<const long long*>(d.q_off); p.k_off = reinterpret_cast<const long long*>(d.k_off);
   return p;
 }
 
@@ -311,11 +327,20 @@ static int attn_check(const SstAttnDesc* d, const void* q, const void* k, const 
               "attention: relative-position bias needs E and unmasked self-attention (Lq == Lk)");
   return SST_OK;
 }
+// packed layouts need the lengths that say which rows exist
+static int attn_check_packed(const SstAttnDesc* d, const int32_t* q_lens, const int32_t* k_lens) {
+  SST_REQUIRE((d->q_off == nullptr || q_lens != nullptr) && (d->k_off == nullptr || k_lens != nullptr), SST_E_ARG,
+              "attention: q_off / k_off need q_lens / k_lens");
+  SST_REQUIRE((d->q_off == nullptr || d->q_pad == nullptr) && (d->k_off == nullptr || d->k_pad == nullptr), SST_E_ARG,
+              "attention: per-position padding masks are indexed b*L + t and do not combine with a packed layout");
+  return SST_OK;
+}
 
 int sst_attn_fwd(const SstAttnDesc* d, const void* q, const void* k, const void* v, const void* E, const int32_t* q_lens,
                  const int32_t* k_lens, void* o, float* lse, void* stream) {
   int rc = attn_check(d, q, k, v, E);
   if (rc) return rc;
+  if ((rc = attn_check_packed(d, q_lens, k_lens))) return rc;
   if (d->B * d->H * d->Lq == 0) return SST_OK;
   if (use_tc(*d)) return attn_fwd_tc_launch(*d, q, k, v, E, q_lens, k_lens, o, lse, reinterpret_cast<cudaStream_t>(stream));
   return attn_fwd_simt_launch(*d, q, k, v, E, q_lens, k_lens, o, lse, reinterpret_cast<cudaStream_t>(stream));
@@ -331,6 +356,7 @@ int sst_attn_bwd(const SstAttnDesc* d, const void* q, const void* k, const void*
                  float* delta, void* ws, size_t ws_bytes, void* stream) {
   int rc = attn_check(d, q, k, v, E);
   if (rc) return rc;
+  if ((rc = attn_check_packed(d, q_lens, k_lens))) return rc;
   if (d->B * d->H * d->Lq == 0) return SST_OK;
   if (use_tc(*d))
     return attn_bwd_tc_launch(*d, q, k, v, E, q_lens, k_lens, o, lse, dO, dq, dk, dv, delta, ws, ws_bytes,

@@ -57,6 +57,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nQT = (p.Lq + BM - 1) / BM;
   const int n_items = nQT * p.H * p.B;                       // item = (b * H + h) * nQT + query tile
+  // items this CTA works on: blockIdx.x, + gridDim.x, ... minus the query tiles a packed layout does not have (both roles walk
+  // the same sequence, so the running tile / item counters stay in step)
+  auto item_exists = [&](int it) {
+    if (p.q_off == nullptr) return true;
+    const int bh = it / nQT;
+    return q_tile_exists(p, bh / p.H, (it - bh * nQT) * BM);
+  };
+  auto next_item = [&](int it) {
+    it += (int)gridDim.x;
+    while (it < n_items && !item_exists(it)) it += (int)gridDim.x;
+    return it;
+  };
+  int first_item = blockIdx.x;
+  if (first_item < n_items && !item_exists(first_item)) first_item = next_item(first_item);
 
   if (w == 0) {
     if (lane == 0) {
@@ -82,13 +96,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (lane == 0) {
       const uint32_t ke_bytes = NATOM * K_ATOM + (p.R > 0 ? NATOM * E_ATOM : 0);
       uint32_t g = 0, n_done = 0;                 // tiles / items this CTA has issued so far: every phase derives from them
-      int i0 = 0, h = 0, b = 0;
+      int i0 = 0, h = 0, b = 0, qb = 0, kb = 0;     // qb / kb: first row of the entry in the query- / key-side matrices
       auto load_ke = [&](int t, uint32_t gt) {    // gt = running index of tile t
         const int st = gt & 1;
         ptx::mbar_arrive_expect_tx(&bar_ke[st], ke_bytes);
 #pragma unroll
         for (int a = 0; a < NATOM; ++a)
-          ptx::tma_load_2d(sK + (st * NATOM + a) * K_ATOM, &tmK, &bar_ke[st], h * DH + a * 64, b * p.Lk + t * BN);
+          ptx::tma_load_2d(sK + (st * NATOM + a) * K_ATOM, &tmK, &bar_ke[st], h * DH + a * 64, kb + t * BN);
         if (p.R > 0) {
           const int e0 = (t * BN - i0) - (BM - 1) + (p.R - 1);
 #pragma unroll
@@ -101,7 +115,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         ptx::mbar_arrive_expect_tx(&bar_v[st], NATOM * V_GRP);
 #pragma unroll
         for (int a = 0; a < NATOM; ++a)
-          ptx::tma_load_2d(sV + (st * NATOM + a) * V_GRP, &tmV, &bar_v[st], h * DH + a * 64, b * p.Lk + t * BN);
+          ptx::tma_load_2d(sV + (st * NATOM + a) * V_GRP, &tmV, &bar_v[st], h * DH + a * 64, kb + t * BN);
       };
       auto issue_s = [&](int st) {   // S = Q K^T and PB = Q E_win^T from stage `st`
         const uint32_t qb = ptx::smem_u32(sQ), kb = ptx::smem_u32(sK + st * NATOM * K_ATOM), eb = ptx::smem_u32(sE + st * NATOM * E_ATOM);
@@ -129,21 +143,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       auto decode = [&](int item, int& t_lo, int& t_hi) {
         const int bh = item / nQT;
         i0 = (item - bh * nQT) * BM; b = bh / p.H; h = bh - b * p.H;
+        qb = q_base(p, b); kb = k_base(p, b);
         key_tile_range_valid(p, i0, b, t_lo, t_hi);
       };
       auto head_loads = [&](int t_lo, int t_hi, uint32_t gh) {
         ptx::mbar_arrive_expect_tx(bar_q, NATOM * Q_ATOM);
 #pragma unroll
-        for (int a = 0; a < NATOM; ++a) ptx::tma_load_2d(sQ + a * Q_ATOM, &tmQ, bar_q, h * DH + a * 64, b * p.Lq + i0);
+        for (int a = 0; a < NATOM; ++a) ptx::tma_load_2d(sQ + a * Q_ATOM, &tmQ, bar_q, h * DH + a * 64, qb + i0);
         load_ke(t_lo, gh);
         load_v(t_lo, gh);
         if (t_lo < t_hi) load_ke(t_lo + 1, gh + 1);
       };
-      int item = blockIdx.x, t_lo = 0, t_hi = -1;
+      int item = first_item, t_lo = 0, t_hi = -1;
       if (item < n_items) { decode(item, t_lo, t_hi); head_loads(t_lo, t_hi, 0); }
       bool sfree_seen = true;                     // bar_sfree(g - 1) already waited for (nothing to wait for at g = 0)
       while (item < n_items) {
-        const int next = item + (int)gridDim.x;
+        const int next = next_item(item);
         ptx::mbar_wait(bar_q, n_done & 1u);
         ptx::mbar_wait(&bar_ke[g & 1], (g >> 1) & 1u);
         if (!sfree_seen) ptx::mbar_wait(bar_sfree, (g - 1) & 1u);   // the previous item's last S / PB are in registers
@@ -197,7 +212,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     bool o_pending = false, o_valid = false;
     float o_scale = 0.f;
     __nv_bfloat16* o_dst = nullptr;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = first_item; item < n_items; item = next_item(item)) {
     const int bh = item / nQT;
     const int i0 = (item - bh * nQT) * BM, b = bh / p.H, h = bh - b * p.H;
     int t_lo, t_hi;
@@ -286,9 +301,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
     for (int g = 0; g < NSPLIT; ++g) l_tot += red[g * 128 + li];
 
-    const bool valid = i < p.Lq;
+    const bool valid = i < q_rows(p, b);
     o_pending = true; o_valid = valid; o_scale = 1.f / l_tot;
-    o_dst = p.o + ((long)b * p.Lq + i) * p.ldo + h * DH + hf * OC;
+    o_dst = p.o + ((long)q_base(p, b) + i) * p.ldo + h * DH + hf * OC;
     if (valid && hf == 0) {
       const long nrows = (long)p.B * p.H * p.Lq;
       p.lse[rc.row_id] = m_run;
@@ -320,9 +335,9 @@ static int attn_fwd_tc_launch_n(const SstAttnDesc& d, const void* q, const void*
   CUtensorMap tmQ, tmK, tmV, tmE;
   int rc;
   const long HD = (long)d.H * d.dh;
-  if ((rc = make_tmap_bf16_2d(&tmQ, q, HD, (long)d.B * d.Lq, d.ldq, 64, BM))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmK, k, HD, (long)d.B * d.Lk, d.ldk, 64, BN))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmV, v, HD, (long)d.B * d.Lk, d.ldv, 64, BN))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmQ, q, HD, attn_q_rows_total(d), d.ldq, 64, BM))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmK, k, HD, attn_k_rows_total(d), d.ldk, 64, BN))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmV, v, HD, attn_k_rows_total(d), d.ldv, 64, BN))) return rc;
   if (d.rel_dist > 0) {
     if ((rc = make_tmap_bf16_2d(&tmE, E, d.dh, (long)d.H * (2 * d.rel_dist - 1), d.dh, 64, PBW))) return rc;
   } else {

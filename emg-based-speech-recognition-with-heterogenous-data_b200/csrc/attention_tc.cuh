@@ -32,6 +32,7 @@ struct AttnTcParams {
   uint32_t thr; float dscale; unsigned long long seed;   // thr: 16-bit keep threshold (0 = no dropout)
   const int* q_lens; const int* k_lens;
   const uint8_t* q_pad; const uint8_t* k_pad;   // optional per-position padding masks (OR-ed with the length masks)
+  const long long* q_off; const long long* k_off;   // packed layouts (include/sst.h): first row of entry b, or null = b*Lq / b*Lk
   __nv_bfloat16* o; long ldo;
   float* lse;
   // backward only
@@ -68,8 +69,21 @@ inline AttnTcParams make_tc_params(const SstAttnDesc& d, const int* q_lens, cons
   p.seed = d.seed;
   p.q_lens = q_lens; p.k_lens = k_lens;
   p.q_pad = d.q_pad; p.k_pad = d.k_pad;
+  p.q_off = reinterpret_cast<const long long*>(d.q_off); p.k_off = reinterpret_cast<const long long*>(d.k_off);
   return p;
 }
+
+// rows of the token matrices the tensor maps may touch: the padded B*L, or what a packed layout says it holds
+inline long attn_q_rows_total(const SstAttnDesc& d) { return d.q_off ? d.q_rows_total : (long)d.B * d.Lq; }
+inline long attn_k_rows_total(const SstAttnDesc& d) { return d.k_off ? d.k_rows_total : (long)d.B * d.Lk; }
+
+// first row of batch entry b in the query-side (q, o, dO, dq) / key-side (k, v, dk, dv) matrices and the rows that exist for it
+__device__ __forceinline__ int q_base(const AttnTcParams& p, int b) { return p.q_off ? (int)p.q_off[b] : b * p.Lq; }
+__device__ __forceinline__ int k_base(const AttnTcParams& p, int b) { return p.k_off ? (int)p.k_off[b] : b * p.Lk; }
+__device__ __forceinline__ int q_rows(const AttnTcParams& p, int b) { return p.q_off ? min(p.q_lens[b], p.Lq) : p.Lq; }
+__device__ __forceinline__ int k_rows(const AttnTcParams& p, int b) { return p.k_off ? min(p.k_lens[b], p.Lk) : p.Lk; }
+// packed query side: a (batch, query tile) pair whose first row lies beyond the entry's length has no rows at all
+__device__ __forceinline__ bool q_tile_exists(const AttnTcParams& p, int b, int i0) { return p.q_off == nullptr || i0 < p.q_lens[b]; }
 
 // key tiles [t_lo, t_hi] a query tile starting at i0 has to visit
 __device__ __forceinline__ void key_tile_range(const AttnTcParams& p, int i0, int& t_lo, int& t_hi) {
@@ -88,7 +102,9 @@ __device__ __forceinline__ void key_tile_range(const AttnTcParams& p, int i0, in
 // reference (transformer.py:185-187), padding included, and stays bit-compatible with that here.
 __device__ __forceinline__ void key_tile_range_valid(const AttnTcParams& p, int i0, int b, int& t_lo, int& t_hi) {
   key_tile_range(p, i0, t_lo, t_hi);
-  const bool rows_unmasked = !p.mask_q_rows || (p.q_pad == nullptr && (p.q_lens == nullptr || i0 + BM <= p.q_lens[b]));
+  // (packed query side: rows beyond the length do not exist, so there is no masked row to keep compatible)
+  const bool rows_unmasked = p.q_off != nullptr || !p.mask_q_rows ||
+                             (p.q_pad == nullptr && (p.q_lens == nullptr || i0 + BM <= p.q_lens[b]));
   if (p.k_lens != nullptr && rows_unmasked) {
     const int klen = p.k_lens[b];
     // klen == 0 (an empty memory): EVERY key is masked and the reference's softmax is uniform over all Lk of them -- no

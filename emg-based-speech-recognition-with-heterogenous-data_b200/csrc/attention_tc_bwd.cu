@@ -134,11 +134,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
 
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
+  if (!q_tile_exists(p, b, i0)) return;           // packed layout: no such rows (the dK/dV kernel does not visit this tile either)
+  const int qb = q_base(p, b), kb = k_base(p, b), n_q = q_rows(p, b);
 
   // The Q / dO / O rows the compute warps park in TMEM below were written by the forward pass long ago: pull them towards
   // L2 now (no registers involved), so that their latency runs under the barrier / TMEM set-up and the first block barrier.
-  if (w < 12 && i0 + 32 * (w & 3) + lane < p.Lq) {
-    const long row = (long)b * p.Lq + i0 + 32 * (w & 3) + lane;
+  if (w < 12 && i0 + 32 * (w & 3) + lane < n_q) {
+    const long row = (long)qb + i0 + 32 * (w & 3) + lane;
     const int which = w >> 2;                       // 0: Q, 1: dO, 2: O
     const char* rp = reinterpret_cast<const char*>(which == 0 ? qg + row * p.ldq : (which == 1 ? p.dO : p.o) + row * p.ldo) + h * DH * 2;
     asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
@@ -173,7 +175,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
     ptx::mbar_arrive_expect_tx(&bar_ke[st], ke_bytes);
 #pragma unroll
     for (int a = 0; a < NATOM; ++a)
-      ptx::tma_load_2d(sK + (st * NATOM + a) * K_ATOM, &tmK, &bar_ke[st], h * DH + a * 64, b * p.Lk + t * BN);
+      ptx::tma_load_2d(sK + (st * NATOM + a) * K_ATOM, &tmK, &bar_ke[st], h * DH + a * 64, kb + t * BN);
     if (p.R > 0) {
       const int e0 = (t * BN - i0) - (BM - 1) + (p.R - 1);
 #pragma unroll
@@ -186,7 +188,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
     ptx::mbar_arrive_expect_tx(&bar_v[st], NATOM * K_ATOM);
 #pragma unroll
     for (int a = 0; a < NATOM; ++a)
-      ptx::tma_load_2d(sV + (st * NATOM + a) * K_ATOM, &tmV, &bar_v[st], h * DH + a * 64, b * p.Lk + t * BN);
+      ptx::tma_load_2d(sV + (st * NATOM + a) * K_ATOM, &tmV, &bar_v[st], h * DH + a * 64, kb + t * BN);
   };
   const bool issuer = (w == NW);
   if (issuer && lane == 0) {        // the first loads do not depend on anything the compute warps set up
@@ -199,7 +201,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
   const int q = w & 3, hf = w >> 2;
   const int li = 32 * q + lane;
   const int i = i0 + li;
-  const bool valid = !issuer && i < p.Lq;
+  const bool valid = !issuer && i < n_q;
   const uint32_t lane_base = (uint32_t)(q * 32) << 16;
   const RowCtx rc = make_row_ctx(p, b, h, issuer ? 0 : i);
   float Lm = 0.f, Ll = 3.0e38f, delta = 0.f;       // rows that do not exist: p = exp(-inf) = 0
@@ -212,8 +214,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
       Ll = p.lse[nrows + rc.row_id];
     }
     if (hf < 2) {                                   // column group 0 moves the Q row, group 1 the dO row (and forms delta)
-      const __nv_bfloat16* src = (hf == 0 ? qg + ((long)b * p.Lq + i) * p.ldq : p.dO + ((long)b * p.Lq + i) * p.ldo) + h * DH;
-      const __nv_bfloat16* orow = p.o + ((long)b * p.Lq + i) * p.ldo + h * DH;
+      const __nv_bfloat16* src = (hf == 0 ? qg + ((long)qb + i) * p.ldq : p.dO + ((long)qb + i) * p.ldo) + h * DH;
+      const __nv_bfloat16* orow = p.o + ((long)qb + i) * p.ldo + h * DH;
 #pragma unroll
       for (int c = 0; c < DH / 32; ++c) {           // 32 bf16 = 16 TMEM columns per store
         uint32_t r[16];
@@ -384,7 +386,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
     }
     ptx::mbar_wait(bar_dq, (uint32_t)((t_hi - t_lo) & 1));
     ptx::tc_fence_after();
-    tmem_row_to_global<OC>(tmem + TM_DQ + hf * OC + lane_base, p.dq + ((long)b * p.Lq + i) * p.ldq + h * DH + hf * OC, 1.f, valid);
+    tmem_row_to_global<OC>(tmem + TM_DQ + hf * OC + lane_base, p.dq + ((long)qb + i) * p.ldq + h * DH + hf * OC, 1.f, valid);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -443,6 +445,20 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  // Packed layouts: key tiles beyond an entry's keys are not items at all, query tiles beyond its queries are not visited
+  // (the dQ kernel wrote no hand-off tiles for them).  The issuer and the epilogue warps walk the same item sequence.
+  auto item_exists = [&](int item) {
+    if (p.k_off == nullptr) return true;
+    const int b = (item / n_kt) / p.H;
+    return (item % n_kt) * BN < p.k_lens[b] && (p.q_off == nullptr || p.q_lens[b] > 0);
+  };
+  auto next_item = [&](int item) {
+    item += (int)gridDim.x;
+    while (item < n_items && !item_exists(item)) item += (int)gridDim.x;
+    return item;
+  };
+  int first_item = blockIdx.x;
+  if (first_item < n_items && !item_exists(first_item)) first_item = next_item(first_item);
   auto open_item = [&](DkvCursor& c) -> bool {        // position the cursor on the first query tile of c.item
     if (c.item >= n_items) return false;
     c.kt = c.item % n_kt;
@@ -450,12 +466,13 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     c.h = bh % p.H; c.b = bh / p.H;
     int q_lo;
     query_tile_range(p, c.kt * BN, q_lo, c.q_hi);
+    if (p.q_off != nullptr) c.q_hi = min(c.q_hi, (p.q_lens[c.b] - 1) / BM);
     c.u = q_lo; c.first = true;
     return true;
   };
   auto advance = [&](DkvCursor& c) -> bool {
     if (c.u < c.q_hi) { ++c.u; c.first = false; return true; }
-    c.item += gridDim.x;
+    c.item = next_item(c.item);
     return open_item(c);
   };
 
@@ -470,14 +487,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         ptx::mbar_arrive_expect_tx(&bar_full[st], STAGE);
 #pragma unroll
         for (int a = 0; a < NATOM; ++a) {
-          ptx::tma_load_2d(sb + a * Q_ATOM, &tmQ, &bar_full[st], c.h * DH + a * 64, c.b * p.Lq + c.u * BM);
-          ptx::tma_load_2d(sb + (NATOM + a) * Q_ATOM, &tmDO, &bar_full[st], c.h * DH + a * 64, c.b * p.Lq + c.u * BM);
+          ptx::tma_load_2d(sb + a * Q_ATOM, &tmQ, &bar_full[st], c.h * DH + a * 64, q_base(p, c.b) + c.u * BM);
+          ptx::tma_load_2d(sb + (NATOM + a) * Q_ATOM, &tmDO, &bar_full[st], c.h * DH + a * 64, q_base(p, c.b) + c.u * BM);
         }
         ptx::tma_load_2d(sb + 2 * NATOM * Q_ATOM, &tmP, &bar_full[st], 0, (int)(tile * BM));
         ptx::tma_load_2d(sb + 2 * NATOM * Q_ATOM + BM * 128, &tmDS, &bar_full[st], 0, (int)(tile * BM));
       };
       DkvCursor cur, nxt;
-      cur.item = blockIdx.x;
+      cur.item = first_item;
       bool have = open_item(cur);
       nxt = cur;
       bool have_next = have && advance(nxt);
@@ -526,9 +543,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t lane_base = (uint32_t)(w * 32) << 16;
     const int dcol = w * 32 + lane, tid = threadIdx.x;
     int n_items_done = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_items_done) {
+    for (int item = first_item; item < n_items; item = next_item(item), ++n_items_done) {
       const int kt = item % n_kt, bh = item / n_kt, h = bh % p.H, b = bh / p.H;
       const int j0 = kt * BN, ab = n_items_done & 1;
+      const int n_k = k_rows(p, b);
+      const long kb = k_base(p, b);
       ptx::mbar_wait(&bar_acc[ab], (uint32_t)((n_items_done >> 1) & 1));
       ptx::tc_fence_after();
       __nv_bfloat16* so = reinterpret_cast<__nv_bfloat16*>(sOut);
@@ -552,11 +571,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int k = tid; k < 2 * BN * PIECES; k += 128) {
         const int which = k / (BN * PIECES), rem = k - which * BN * PIECES, jr = rem / PIECES, pc = rem - jr * PIECES;
         const int j = j0 + jr;
-        if (j < p.Lk) {
+        if (j < n_k) {
           const uint4 v = *reinterpret_cast<const uint4*>(so + (which * BN + jr) * DH + pc * 8);
           __nv_bfloat16* out = which == 0 ? p.dv : p.dk;
           const long ld = which == 0 ? p.ldv : p.ldk;
-          *reinterpret_cast<uint4*>(out + ((long)b * p.Lk + j) * ld + h * DH + pc * 8) = v;
+          *reinterpret_cast<uint4*>(out + (kb + j) * ld + h * DH + pc * 8) = v;
         }
       }
       ptx::named_bar_sync(1, 128);                            // sOut is rewritten by the next item
@@ -585,10 +604,10 @@ static int attn_bwd_tc_launch_n(const SstAttnDesc& d, const void* q, const void*
   CUtensorMap tmQ, tmK, tmV, tmE, tmDO;
   int rc;
   const long HD = (long)d.H * d.dh;
-  if ((rc = make_tmap_bf16_2d(&tmQ, q, HD, (long)d.B * d.Lq, d.ldq, 64, BM))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmDO, dO, HD, (long)d.B * d.Lq, d.ldo, 64, BM))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmK, k, HD, (long)d.B * d.Lk, d.ldk, 64, BN))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmV, v, HD, (long)d.B * d.Lk, d.ldv, 64, BN))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmQ, q, HD, attn_q_rows_total(d), d.ldq, 64, BM))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmDO, dO, HD, attn_q_rows_total(d), d.ldo, 64, BM))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmK, k, HD, attn_k_rows_total(d), d.ldk, 64, BN))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmV, v, HD, attn_k_rows_total(d), d.ldv, 64, BN))) return rc;
   if (d.rel_dist > 0) {
     if ((rc = make_tmap_bf16_2d(&tmE, E, d.dh, (long)d.H * (2 * d.rel_dist - 1), d.dh, 64, PBW))) return rc;
   } else {

@@ -169,7 +169,8 @@ class AttnDesc(C.Structure):
                 ("dh", C.c_int32), ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64), ("ldo", C.c_int64),
                 ("causal", C.c_int32), ("mask_q_rows", C.c_int32), ("rel_dist", C.c_int32), ("scale", C.c_float),
                 ("drop_p", C.c_float), ("seed", C.c_uint64), ("force_simt", C.c_int32),
-                ("q_pad", C.c_void_p), ("k_pad", C.c_void_p)]
+                ("q_pad", C.c_void_p), ("k_pad", C.c_void_p),
+                ("q_off", C.c_void_p), ("k_off", C.c_void_p), ("q_rows_total", C.c_int64), ("k_rows_total", C.c_int64)]
 
 
 def _i64(v):
@@ -185,7 +186,9 @@ def _u64(v):
 
 
 def attn_desc(dtype, B, H, Lq, Lk, dh, ldq, ldk, ldv, ldo, causal, mask_q_rows, rel_dist, scale, drop_p, seed,
-              force_simt=False, q_pad=None, k_pad=None):
+              force_simt=False, q_pad=None, k_pad=None, q_off=None, k_off=None, q_rows_total=0, k_rows_total=0):
+    """q_off / k_off: int64 (B,) device tensors of first rows for the packed layouts of include/sst.h (with the number of rows
+    the packed matrices hold); None = the padded layout."""
     d = AttnDesc()
     d.dtype, d.B, d.H, d.Lq, d.Lk, d.dh = dtype, B, H, Lq, Lk, dh
     d.ldq, d.ldk, d.ldv, d.ldo = ldq, ldk, ldv, ldo
@@ -193,7 +196,11 @@ def attn_desc(dtype, B, H, Lq, Lk, dh, ldq, ldk, ldv, ldo, causal, mask_q_rows, 
     d.scale, d.drop_p, d.seed, d.force_simt = scale, drop_p, seed & 0xFFFFFFFFFFFFFFFF, int(force_simt)
     d.q_pad = q_pad.data_ptr() if q_pad is not None else None
     d.k_pad = k_pad.data_ptr() if k_pad is not None else None
-    d._keep = (q_pad, k_pad)                      # the descriptor holds raw pointers: keep the mask tensors alive with it
+    d.q_off = q_off.data_ptr() if q_off is not None else None
+    d.k_off = k_off.data_ptr() if k_off is not None else None
+    d.q_rows_total, d.k_rows_total = int(q_rows_total), int(k_rows_total)
+    assert (q_off is None or (q_off.dtype == torch.int64 and q_rows_total > 0)) and (k_off is None or (k_off.dtype == torch.int64 and k_rows_total > 0))
+    d._keep = (q_pad, k_pad, q_off, k_off)        # the descriptor holds raw pointers: keep the tensors alive with it
     return d
 
 

@@ -150,7 +150,8 @@ int sst_bn_bwd(int dtype, int64_t n_chunks, int T, int C, const void* dout, int6
  * Attention.  Replaces MultiHeadAttention.forward between the projections (transformer.py:177-208) together
  * with LearnedRelativePositionalEmbedding (transformer.py:260-403): logits = mask(q.k * scale) + relpos(q),
  * softmax, dropout on the probabilities, probs.v -- without materialising (B,H,L,L).
- *   q/k/v/o are token matrices: row = b*L + t (pitch ld*), head h occupies columns [h*dh, (h+1)*dh).
+ *   q/k/v/o are token matrices: row = b*L + t (pitch ld*; or q_off[b] + t / k_off[b] + t, see the descriptor), head h
+ *   occupies columns [h*dh, (h+1)*dh).
  *   masks are SET to -1e8 exactly as masked_fill does: causal (j > i), keys j >= k_lens[b] (or k_pad), and, with
  *   mask_q_rows, whole rows i >= q_lens[b] (or q_pad); fully masked rows therefore give the reference's uniform softmax.
  *   rel_dist R > 0 adds bias[i][j] = q_i . E[h][j-i+R-1] for |j-i| < R and -1e8 otherwise; E is
@@ -175,6 +176,17 @@ typedef struct SstAttnDesc {
    * middle of a greedy prefix, greedy_search.py:21 + architecture.py:174) */
   const uint8_t* q_pad;
   const uint8_t* k_pad;
+  /* optional PACKED (variable-length) layouts, SURVEY.md 8(f) N2/N4 -- device int64[B], NULL = the padded layout b*Lq / b*Lk:
+   *   q_off[b] = row of batch entry b's first query in q / o / dO / dq; entry b owns rows [q_off[b], q_off[b] + q_lens[b])
+   *              (q_lens required, every length >= 1).  Rows i >= q_lens[b] do not exist: nothing is read for or written to
+   *              them (they are the next entry's rows), Lq is only the maximum length (tile grid, lse / delta index space).
+   *   k_off[b] = the same for k / v / dk / dv with k_lens (required).  Keys j >= k_lens[b] get probability exactly 0, as the
+   *              masked padding keys of the padded layout do for every row that has one real key.
+   *   Entries may share key rows in FORWARD calls (k_off[b] = 0 for all b: the hypotheses of a beam search attend to one
+   *   encoder memory, BeamSearch.py:111 without the memory.repeat); backward needs disjoint ranges. */
+  const int64_t* q_off;
+  const int64_t* k_off;
+  int64_t q_rows_total, k_rows_total;   /* rows the packed q-side / k-side matrices hold (bounds of the TMA descriptors) */
 } SstAttnDesc;
 
 int sst_attn_fwd(const SstAttnDesc* d, const void* q, const void* k, const void* v, const void* E, const int32_t* q_lens,
