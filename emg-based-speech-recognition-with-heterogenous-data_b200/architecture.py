@@ -157,7 +157,10 @@ class _StepFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, x_raw, y, lengths, want_memory, *params):
         eng = model.engine()
-        enc_logits, dec_logits, c = eng.forward(x_raw, lengths, y, None, training=model.training, seed=model._next_seed())
+        # the encoder memory handed back to a search loop keeps the reference's padded (B, Lmax, D) shape; a training step
+        # (nothing but the logits leaves) runs ragged batches packed
+        enc_logits, dec_logits, c = eng.forward(x_raw, lengths, y, None, training=model.training, seed=model._next_seed(),
+                                                packed=False if want_memory else None)
         ctx.model, ctx.c = model, c
         model._cache_memory(c)
         out_enc = model._unpad_logits(enc_logits, c.B, c.Lmax, eng.n_out_enc)

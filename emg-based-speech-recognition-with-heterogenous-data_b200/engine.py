@@ -263,10 +263,12 @@ class Engine:
                         G[prefix + ".weight"], G[prefix + ".bias"])
         return ds, (dr if p > 0 else ds)
 
-    def _attn_desc(self, B, Lq, Lk, ldq, ldk, ldv, causal, mask_q_rows, R, p, seed, q_pad=None, k_pad=None, dec=False):
+    def _attn_desc(self, B, Lq, Lk, ldq, ldk, ldv, causal, mask_q_rows, R, p, seed, q_pad=None, k_pad=None, dec=False,
+                   q_off=None, k_off=None, q_rows=0, k_rows=0):
         H, dh = (self.Hd, self.dhd) if dec else (self.H, self.dh)
         return L.attn_desc(self.dt, B, H, Lq, Lk, dh, ldq, ldk, ldv, self.D, causal, mask_q_rows, R,
-                           1.0 / math.sqrt(dh), p, seed, self.force_simt, q_pad=q_pad, k_pad=k_pad)
+                           1.0 / math.sqrt(dh), p, seed, self.force_simt, q_pad=q_pad, k_pad=k_pad,
+                           q_off=q_off, k_off=k_off, q_rows_total=q_rows, k_rows_total=k_rows)
 
     # ------------------------------------------------------------------------------------------------ conv front-end
     def _bn_stats(self, x, rows, ld, prefix, training):
@@ -381,15 +383,17 @@ class Engine:
         return dinp
 
     # ------------------------------------------------------------------------------------------------ encoder
-    def _enc_layer_fwd(self, x, B, Lx, lens, i, training, seeds):
-        D, M = self.D, B * Lx
+    def _enc_layer_fwd(self, x, B, Lx, lens, i, training, seeds, M=None, off=None):
+        """M / off: rows and per-utterance first rows of a PACKED batch (SstAttnDesc.q_off); default = the padded (B*Lx) layout."""
+        D = self.D
+        M = M if M is not None else B * Lx
         p = self.cfg["dropout"] if training else 0.0
         pfx = "transformerEncoder.layers.%d" % i
         a = pfx + ".self_attn"
         qkv = self._linear_fwd(x, M, a + ".qkv")
         o = self.empty(M, D)
         lse = self.empty(2 * B * self.H * Lx, dtype=torch.float32)
-        ad = self._attn_desc(B, Lx, Lx, 3 * D, 3 * D, 3 * D, False, True, self.R, p, seeds())
+        ad = self._attn_desc(B, Lx, Lx, 3 * D, 3 * D, 3 * D, False, True, self.R, p, seeds(), q_off=off, k_off=off, q_rows=M, k_rows=M)
         L.attn_fwd(ad, qkv, qkv[:, D:], qkv[:, 2 * D:], self.pk[a + ".E"], lens, lens, o, lse)
         y = self._linear_fwd(o, M, a + ".o.T")
         x1, ln1 = self._ln_fwd(x, y, M, pfx + ".norm1", p, seeds())
@@ -400,8 +404,9 @@ class Engine:
         c = Ctx(x=x, qkv=qkv, o=o, lse=lse, ad=ad, ln1=ln1, x1=x1, h=h, pre=pre, s_ffn=s_ffn, ln2=ln2, p=p)
         return x2, c
 
-    def _enc_layer_bwd(self, c, dx2, B, Lx, lens, i, G):
-        D, M = self.D, B * Lx
+    def _enc_layer_bwd(self, c, dx2, B, Lx, lens, i, G, M=None):
+        D = self.D
+        M = M if M is not None else B * Lx
         pfx = "transformerEncoder.layers.%d" % i
         a = pfx + ".self_attn"
         ds2, dy2 = self._ln_bwd(dx2, c.ln2, M, pfx + ".norm2", G)
@@ -439,8 +444,11 @@ class Engine:
                   a_cols=D, b_cols=n * D, out_seg=(dh, D * dh, H * dh, tuple(offs)))
 
     # ------------------------------------------------------------------------------------------------ decoder
-    def _dec_layer_fwd(self, t, mem, B, S, Lm, tgt_lens, mem_lens, i, training, seeds, tgt_pad=None):
-        D, M, Mm = self.D, B * S, B * Lm
+    def _dec_layer_fwd(self, t, mem, B, S, Lm, tgt_lens, mem_lens, i, training, seeds, tgt_pad=None, Mm=None, mem_off=None, cross_kv=None):
+        """Mm / mem_off: rows and per-utterance first rows of a PACKED encoder memory (SstAttnDesc.k_off); cross_kv: this layer's
+        already projected memory keys / values (Mm, 2D) (search loops project the memory once, not once per step)."""
+        D, M = self.D, B * S
+        Mm = Mm if Mm is not None else B * Lm
         p = self.cfg["dropout"] if training else 0.0
         pfx = "transformerDecoder.layers.%d" % i
         a, m = pfx + ".self_attn", pfx + ".multihead_attn"
@@ -452,10 +460,10 @@ class Engine:
         y = self._linear_fwd(o1, M, a + ".o.T")
         t1, ln1 = self._ln_fwd(t, y, M, pfx + ".norm1", p, seeds())
         q = self._linear_fwd(t1, M, m + ".q")
-        kv = self._linear_fwd(mem, Mm, m + ".kv")
+        kv = cross_kv if cross_kv is not None else self._linear_fwd(mem, Mm, m + ".kv")
         o2 = self.empty(M, D)
         lse2 = self.empty(2 * B * self.Hd * S, dtype=torch.float32)
-        ad2 = self._attn_desc(B, S, Lm, D, 2 * D, 2 * D, False, False, 0, p, seeds(), dec=True)
+        ad2 = self._attn_desc(B, S, Lm, D, 2 * D, 2 * D, False, False, 0, p, seeds(), dec=True, k_off=mem_off, k_rows=Mm)
         L.attn_fwd(ad2, q, kv, kv[:, D:], None, None, mem_lens, o2, lse2)
         y2 = self._linear_fwd(o2, M, m + ".o.T")
         t2, ln2 = self._ln_fwd(t1, y2, M, pfx + ".norm2", p, seeds())
@@ -467,8 +475,9 @@ class Engine:
                 h=h, pre=pre, s_ffn=s_ffn, ln3=ln3, p=p)
         return t3, c
 
-    def _dec_layer_bwd(self, c, dt3, mem, dmem, B, S, Lm, tgt_lens, mem_lens, i, G):
-        D, M, Mm = self.D, B * S, B * Lm
+    def _dec_layer_bwd(self, c, dt3, mem, dmem, B, S, Lm, tgt_lens, mem_lens, i, G, Mm=None):
+        D, M = self.D, B * S
+        Mm = Mm if Mm is not None else B * Lm
         pfx = "transformerDecoder.layers.%d" % i
         a, m = pfx + ".self_attn", pfx + ".multihead_attn"
         ds3, dy3 = self._ln_bwd(dt3, c.ln3, M, pfx + ".norm3", G)
@@ -508,9 +517,13 @@ class Engine:
             self.n += 1
             return (self.base * 1000003 + self.n * 7919) & 0xFFFFFFFFFFFFFFFF
 
-    def encode(self, x_raw, lengths, training, seed=0, save=True):
+    def encode(self, x_raw, lengths, training, seed=0, save=True, packed=False):
         """x_raw: (n, 1600, 8) fp32 CUDA (already shifted); lengths: list[int] frames per utterance.
-        Returns (x_enc (B*Lmax, D), ctx)."""
+        Returns (x_enc (B*Lmax, D), ctx).  packed=True: a ragged batch is NOT padded to (B, Lmax) -- the
+        transformer runs on the sum(lengths) rows decollate_tensor (data_utils.py:176-185) yields, utterance b at rows
+        [offs[b], offs[b] + lengths[b]), the attention kernels taking the offsets (SstAttnDesc.q_off / k_off); x_enc is then
+        (sum(lengths), D).  Every real position computes what it computes in the padded layout: padded keys have probability
+        exactly 0 there, and everything else in the transformer is row-local."""
         assert x_raw.dtype == torch.float32 and x_raw.is_cuda and x_raw.is_contiguous()
         n, T0, Cc = x_raw.shape
         assert Cc == 8 and T0 % 8 == 0
@@ -528,33 +541,45 @@ class Engine:
         assert total <= rows3, "lengths exceed the available frames (data_utils.py:182)"
         lens_dev = torch.tensor(lengths, dtype=torch.int32).to(self.dev, non_blocking=True)
         ragged = not (all(l == Lmax for l in lengths) and total == rows3)
+        packed = bool(packed and ragged and min(lengths) >= 1)
+        M, off = B * Lmax, None
         if ragged:
             offs = [0]
             for l in lengths[:-1]:
                 offs.append(offs[-1] + l)
             offs_dev = torch.tensor(offs, dtype=torch.int64).to(self.dev, non_blocking=True)
-            x = self.empty(B * Lmax, self.D)
-            L.gather_rows_pad(self.dt, xlin, x, offs_dev, lens_dev, B, Lmax, self.D, float(PAD))
             ctx.offs = offs_dev
+            if packed:
+                x, M, off = xlin[:total], total, offs_dev       # the decollated rows as they are
+            else:
+                x = self.empty(B * Lmax, self.D)
+                L.gather_rows_pad(self.dt, xlin, x, offs_dev, lens_dev, B, Lmax, self.D, float(PAD))
         else:
             x = xlin
-        ctx.update(a3=a3, rows3=rows3, B=B, Lmax=Lmax, lens=lens_dev, ragged=ragged, lengths=list(lengths))
+        ctx.update(a3=a3, rows3=rows3, B=B, Lmax=Lmax, lens=lens_dev, ragged=ragged, lengths=list(lengths), packed=packed, M=M, off=off)
         for i in range(self.n_enc):
-            x, c = self._enc_layer_fwd(x, B, Lmax, lens_dev, i, training, seeds)
+            x, c = self._enc_layer_fwd(x, B, Lmax, lens_dev, i, training, seeds, M=M, off=off)
             ctx.layers.append(c)
         ctx.x_enc = x
         ctx.seeds = seeds
         return x, ctx
 
-    def enc_head(self, x_enc, M):
-        """w_aux: fp32 logits in a pitch-64 matrix (columns >= 44 undefined)."""
-        return self._linear_fwd(x_enc, M, "w_aux", bias=self.P["w_aux.bias"], out_dtype=torch.float32, ldc=self.LDH)
+    def enc_head(self, x_enc, M, ctx=None):
+        """w_aux: fp32 logits in a pitch-64 matrix (columns >= 44 undefined), always in the padded (B*Lmax) row layout the
+        reference returns and the CTC kernels index: a packed batch (`ctx.packed`) is re-padded here, 64 columns only (padded
+        positions read 0; the reference leaves the network's response to the 42-filled rows there, which nothing consumes)."""
+        logits = self._linear_fwd(x_enc, M, "w_aux", bias=self.P["w_aux.bias"], out_dtype=torch.float32, ldc=self.LDH)
+        if ctx is not None and ctx.packed:
+            padded = self.empty(ctx.B * ctx.Lmax, self.LDH, dtype=torch.float32)
+            L.gather_rows_pad(L.F32, logits, padded, ctx.off, ctx.lens, ctx.B, ctx.Lmax, self.LDH, 0.0)
+            return padded
+        return logits
 
     def ctc_greedy(self, x_raw, lengths):
         """Inference (BASELINE.json config 5): encoder forward in eval mode + CTC best-path decode on the device.
         Returns (ids int32 (B, Lmax) padded with -1, lens int32 (B,)) -- still on the device, no host sync."""
-        x_enc, ctx = self.encode(x_raw, lengths, training=False)
-        logits = self.enc_head(x_enc, ctx.B * ctx.Lmax)
+        x_enc, ctx = self.encode(x_raw, lengths, training=False, packed=self.cfg.get("packed", True))
+        logits = self.enc_head(x_enc, ctx.M, ctx)
         ids = torch.empty(ctx.B, ctx.Lmax, dtype=torch.int32, device=self.dev)
         lens = torch.empty(ctx.B, dtype=torch.int32, device=self.dev)
         L.ctc_greedy(L.F32, ctx.B, ctx.Lmax, self.n_out_enc, self.n_out_enc - 1, logits, self.LDH, ctx.lens, ids, lens)
@@ -621,7 +646,7 @@ class Engine:
                     break
         return tokens[:n].t().contiguous()
 
-    def decode(self, y, tgt_lens, mem, mem_lens, B, Lm, training, seeds, ctx=None, tgt_pad=None):
+    def decode(self, y, tgt_lens, mem, mem_lens, B, Lm, training, seeds, ctx=None, tgt_pad=None, Mm=None, mem_off=None, cross=None):
         """y: (B, S) int64 CUDA; returns x_dec (B*S, D).  Target padding is either a suffix (`tgt_lens`, the training
         batches of pad_sequence) or an arbitrary per-position mask `tgt_pad` (uint8 (B, S); greedy prefixes, where a
         generated PAD id can sit anywhere: architecture.py:174 masks by `tgt == pad`)."""
@@ -632,22 +657,27 @@ class Engine:
         L.embed_posenc_fwd(self.dt, y, self.P["embedding_tgt.weight"], self.Bf["pos_decoder.pe"], t, B, S, self.D, p_pos, s_emb)
         layers = []
         for i in range(self.n_dec):
-            t, c = self._dec_layer_fwd(t, mem, B, S, Lm, tgt_lens, mem_lens, i, training, seeds, tgt_pad)
+            t, c = self._dec_layer_fwd(t, mem, B, S, Lm, tgt_lens, mem_lens, i, training, seeds, tgt_pad, Mm=Mm, mem_off=mem_off,
+                                       cross_kv=cross[i] if cross is not None else None)
             layers.append(c)
         if ctx is not None:
             ctx.update(y=y, S=S, tgt_lens=tgt_lens, dec_layers=layers, p_pos=p_pos, s_emb=s_emb, x_dec=t)
         return t
 
+    def project_memory(self, mem, Mm):
+        """Cross-attention keys / values of every decoder layer for an encoder memory of Mm rows: [(Mm, 2D)] * n_dec."""
+        return [self._linear_fwd(mem, Mm, "transformerDecoder.layers.%d.multihead_attn.kv" % i) for i in range(self.n_dec)]
+
     def dec_head(self, x_dec, M):
         return self._linear_fwd(x_dec, M, "w_out", bias=self.P["w_out.bias"], out_dtype=torch.float32, ldc=self.LDH)
 
-    def forward(self, x_raw, lengths, y=None, tgt_lens=None, training=True, seed=0, ctc=None):
+    def forward(self, x_raw, lengths, y=None, tgt_lens=None, training=True, seed=0, ctc=None, packed=None):
         """Model.forward_training (architecture.py:101-139).  Returns (enc_logits (B*L, 64) fp32, dec_logits (B*S, 64) fp32 | None, ctx).
         `ctc` = (targets (B, Smax) int64, target lengths int32, coefficient): start the CTC loss + gradient on the side stream as
         soon as the encoder logits exist, so that its serial alpha/beta recursion runs under the decoder forward."""
-        x_enc, ctx = self.encode(x_raw, lengths, training, seed)
+        x_enc, ctx = self.encode(x_raw, lengths, training, seed, packed=self.cfg.get("packed", True) if packed is None else packed)
         B, Lmax = ctx.B, ctx.Lmax
-        ctx.enc_logits = self.enc_head(x_enc, B * Lmax)
+        ctx.enc_logits = self.enc_head(x_enc, ctx.M, ctx)
         ctx.dec_logits = None
         ctx.loss_out = torch.zeros(3, dtype=torch.float32, device=self.dev)
         if ctc is not None:
@@ -655,7 +685,7 @@ class Engine:
         if y is not None and self.n_dec >= 0 and y.numel() > 0:
             if tgt_lens is None:
                 tgt_lens = (y != PAD).sum(1).to(torch.int32)
-            x_dec = self.decode(y, tgt_lens, x_enc, ctx.lens, B, Lmax, training, ctx.seeds, ctx)
+            x_dec = self.decode(y, tgt_lens, x_enc, ctx.lens, B, Lmax, training, ctx.seeds, ctx, Mm=ctx.M, mem_off=ctx.off)
             ctx.dec_logits = self.dec_head(x_dec, B * y.shape[1])
         return ctx.enc_logits, ctx.dec_logits, ctx
 
@@ -713,9 +743,13 @@ class Engine:
         gradients of a stage are final ("heads", "dec<i>", "embed", "enc<i>", "w_raw_in", "conv<i>") so that the caller can start reducing them."""
         on_stage = on_stage or (lambda label: None)
         B, Lx, D = ctx.B, ctx.Lmax, self.D
-        M = B * Lx
+        M = ctx.M                                       # B * Lx, or sum(lengths) for a packed batch
         d_enc_logits = d_enc_logits if d_enc_logits is not None else ctx.d_enc_logits
         d_dec_logits = d_dec_logits if d_dec_logits is not None else ctx.get("d_dec_logits")
+        if ctx.packed:                                  # the loss kernels index (b, t): bring their gradient to the packed rows
+            d_packed = self.empty(M, self.LDH)
+            L.scatter_rows(self.dt, d_enc_logits, d_packed, ctx.off, ctx.lens, B, Lx, self.LDH)
+            d_enc_logits = d_packed
         # CTC head
         dx = self._linear_bwd(d_enc_logits, ctx.x_enc, M, "w_aux", G, "w_aux.weight", "w_aux.bias")
         if ctx.dec_logits is not None and d_dec_logits is not None:
@@ -724,19 +758,25 @@ class Engine:
             dt_ = self._linear_bwd(d_dec_logits, ctx.x_dec, Md, "w_out", G, "w_out.weight", "w_out.bias")
             on_stage("heads")
             for i in reversed(range(self.n_dec)):
-                dt_ = self._dec_layer_bwd(ctx.dec_layers[i], dt_, ctx.x_enc, dx, B, S, Lx, ctx.tgt_lens, ctx.lens, i, G)
+                dt_ = self._dec_layer_bwd(ctx.dec_layers[i], dt_, ctx.x_enc, dx, B, S, Lx, ctx.tgt_lens, ctx.lens, i, G, Mm=M)
                 on_stage("dec%d" % i)
             L.embed_bwd(self.dt, ctx.y, dt_, G["embedding_tgt.weight"], B, S, D, PAD, ctx.p_pos, ctx.s_emb)
         on_stage("embed")
         for i in reversed(range(self.n_enc)):
-            dx = self._enc_layer_bwd(ctx.layers[i], dx, B, Lx, ctx.lens, i, G)
+            dx = self._enc_layer_bwd(ctx.layers[i], dx, B, Lx, ctx.lens, i, G, M=M)
             on_stage("enc%d" % i)
-        if ctx.ragged:
-            dxlin = self.zeros(ctx.rows3, D)
-            L.scatter_rows(self.dt, dx, dxlin, ctx.offs, ctx.lens, B, Lx, D)
+        if ctx.packed:
+            # dx already is the gradient of w_raw_in's first sum(lengths) output rows; the rest of the last chunk (the 42-filled
+            # tail) has gradient 0: run the layer's backward over the real rows only and leave zeros behind them
+            da = self.zeros(ctx.rows3, D)
+            self._linear_bwd(dx, ctx.a3, M, "w_raw_in", G, "w_raw_in.weight", "w_raw_in.bias", dx_out=da)
         else:
-            dxlin = dx
-        da = self._linear_bwd(dxlin, ctx.a3, ctx.rows3, "w_raw_in", G, "w_raw_in.weight", "w_raw_in.bias")
+            if ctx.ragged:
+                dxlin = self.zeros(ctx.rows3, D)
+                L.scatter_rows(self.dt, dx, dxlin, ctx.offs, ctx.lens, B, Lx, D)
+            else:
+                dxlin = dx
+            da = self._linear_bwd(dxlin, ctx.a3, ctx.rows3, "w_raw_in", G, "w_raw_in.weight", "w_raw_in.bias")
         on_stage("w_raw_in")
         for c in reversed(ctx.blocks):
             da = self._resblock_bwd(c, da, G)

@@ -131,6 +131,46 @@ def test_beam_search_call_pattern_memory_repeat():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_beam_decoder_shares_the_memory_across_hypotheses(dtype):
+    """sst_b200.beam_search.BeamDecoder projects the encoder memory once per utterance and lets every hypothesis
+    attend to the same key / value rows (SstAttnDesc.k_off = 0) instead of BeamSearch.py:111's memory.repeat -- the logits must be
+    the memory.repeat call's BIT FOR BIT (same arithmetic on the same values), step after step of a growing, re-ordered beam, and
+    (fp32) sit on the oracle at 1e-4.  Two utterances in the encoder batch: the search runs on the SHORTER one, whose memory is padded."""
+    from sst_b200.beam_search import BeamDecoder
+    cfg = O.make_cfg(n_enc=1, n_dec=2, rel_dist=100)
+    sd = O.synthetic_state_dict(cfg, 33)
+    A, model = _model(cfg, sd, dtype)
+    model.eval()
+    batch = O.synthetic_batch(seed=19, ragged=[200, 137], tgt_lens=[6, 6])
+    X = O.combine_fixed_length(batch["raw_emg"])
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        memory, _ = model(batch["lengths"], DEV, mode='beam_search', part='encoder', x_raw=X.to(DEV))
+        dec = BeamDecoder(model, memory, index=1)
+        mem1 = memory[1:2]
+        model._mem_lens_saved = model._mem_lens
+        hist = torch.tensor([[41]], dtype=torch.int64)
+        for step in range(6):
+            n = hist.shape[0]
+            got = dec(hist.to(DEV))
+            # the reference call pattern on the same utterance: its cached mask row repeated with the memory
+            model._mem_lens, model._mem_shape = model._mem_lens_saved[1:2], (1, memory.shape[1])
+            want = model(batch["lengths"], DEV, mode='beam_search', part='decoder', y=hist.to(DEV), memory=mem1.repeat(n, 1, 1))
+            model._mem_lens, model._mem_shape = model._mem_lens_saved, (2, memory.shape[1])
+            assert got.shape == want.shape == (n, step + 1, 43)
+            assert torch.equal(got, want), (step, float((got - want).abs().max()))
+            assert torch.equal(dec.step_logits(hist.to(DEV)), want[:, -1, :-2])
+            if dtype == torch.float32:
+                mem_ref, kpm = O.encode(sd, cfg, X.clone(), batch["lengths"], False)
+                ref = F.linear(O.decode(sd, cfg, hist, mem_ref[1:2].repeat(n, 1, 1), kpm[1:2].repeat(n, 1), False), sd["w_out.weight"], sd["w_out.bias"])
+                assert rel_err(got.cpu(), ref) < 1e-4
+            # grow and re-order the beam: top-3 continuations of every hypothesis, shuffled, at most 23 kept
+            top = torch.topk(torch.log_softmax(got[:, -1, :-2].float().cpu(), 1), 3, dim=1).indices
+            new = torch.cat([torch.cat([hist, top[:, k:k + 1]], 1) for k in range(3)], 0)
+            hist = new[torch.randperm(new.shape[0], generator=g)[:23]]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_decoder_head_count_differs_from_encoder(dtype):
     """FLAGS.n_heads_decoder != FLAGS.n_heads_encoder (architecture.py:16-17): 4 decoder heads of 192 dims next to 8 encoder
     heads of 96; one training step against the oracle."""

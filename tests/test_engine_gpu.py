@@ -132,7 +132,7 @@ def test_bf16_gradients_with_aligned_relu_masks(name):
     no yardstick clause, and the flipped bits are a sub-percent fraction sitting at |pre-activation| ~ 0."""
     z, meta = load_golden(name)
     cfg, sd, batch = golden_inputs(meta)
-    eng = make_engine(cfg, sd, torch.bfloat16)
+    eng = make_engine(dict(cfg, packed=False), sd, torch.bfloat16)      # padded layout: the masks map 1:1 onto the oracle's (L, B, F) tensors
     G, ctx = run_step(eng, cfg, batch)[5:7]
     masks = engine_relu_masks(ctx)
     try:
@@ -300,3 +300,47 @@ def test_no_kernel_writes_outside_its_buffers(dtype):
     for raw, nb in arenas:
         bad += int((raw[:GUARD] != 0xA5).sum()) + int((raw[GUARD + nb:] != 0xA5).sum())
     assert bad == 0, "%d canary bytes overwritten across %d buffers" % (bad, len(arenas))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_packed_layout_equals_padded_layout(dtype):
+    """a ragged batch run PACKED (no pad-to-max: sum(lengths) rows through every GEMM / LayerNorm, attention
+    with per-utterance row offsets, whole query tiles of the short utterances never visited) must give what the reference's
+    padded layout gives -- logits on the valid frames, the three losses, every gradient -- and both must sit on the live oracle.
+    Lengths straddle the 128-row query tile and 64-key tile boundaries; the batch ends inside a 1600-sample chunk (42-filled tail)."""
+    cfg = O.make_cfg(n_enc=2, n_dec=1, rel_dist=100, alpha=0.3)
+    sd = O.synthetic_state_dict(cfg, 3)
+    batch = O.synthetic_batch(seed=21, ragged=[300, 129, 257, 64, 9], tgt_lens=[12, 7, 9, 5, 2])
+    res, grads, _ = O.loss_and_grads(sd, cfg, batch, True, 0)
+    lens = batch["lengths"]
+    runs = {}
+    for packed in (False, True):
+        eng = make_engine(dict(cfg, packed=packed), sd, dtype)
+        out_enc, out_dec, loss, loss_dec, loss_enc, G, ctx = run_step(eng, cfg, batch)
+        assert ctx.packed == packed and ctx.M == (sum(lens) if packed else len(lens) * max(lens))
+        runs[packed] = (out_enc, out_dec, loss_dec, loss_enc, G)
+        tol = 1e-4 if dtype == torch.float32 else 2e-2
+        assert _valid_frames_err(out_enc, res["out_enc"], lens) < tol
+        assert abs(loss_enc - float(res["loss_enc"])) < tol * abs(float(res["loss_enc"]))
+        assert abs(loss_dec - float(res["loss_dec"])) < tol * abs(float(res["loss_dec"]))
+    a, b = runs[False], runs[True]
+    same = 2e-5 if dtype == torch.float32 else 2e-2            # fp32: the same arithmetic on the same rows, only the reduction order of
+    assert _valid_frames_err(b[0], a[0], lens) < same          # the weight-gradient sums (fewer zero rows) differs
+    assert rel_err(b[1], a[1]) < same
+    assert abs(b[2] - a[2]) < same * abs(a[2]) and abs(b[3] - a[3]) < same * abs(a[3])
+    if dtype == torch.float32:
+        worst = max((float((b[4][n].double() - a[4][n].double()).norm() / a[4][n].double().norm().clamp_min(1e-30)), n) for n in a[4]
+                    if float(a[4][n].abs().max()) > 0)
+        assert worst[0] < 1e-4, worst
+    # the packed run against the live oracle, every tensor in relative L2 with the usual yardsticks (float64 truth, autocast-bf16)
+    bf16 = dtype == torch.bfloat16
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    b64 = dict(batch)
+    b64["raw_emg"] = [x.double() for x in batch["raw_emg"]]
+    _, g64, _ = O.loss_and_grads(sd64, cfg, b64, True, 0)
+    gbf = oracle_autocast_bf16_grads(sd, cfg, batch) if bf16 else None
+    names = sorted(grads)
+    flat = lambda d: {n: d[n].detach().double().cpu().reshape(-1).numpy() for n in names}      # noqa: E731
+    gmax = max(float(g.abs().max()) for g in grads.values())
+    rows = l2_rows(names, flat(b[4]), flat(grads), flat(g64), flat(gbf) if gbf is not None else None, gmax)
+    assert_l2_rows(rows, 2e-2 if bf16 else 1e-4, bf16, "packed %s" % dtype)
