@@ -452,6 +452,10 @@ def run_also(args, w, world, rank, dev, trainer, model, barrier, max_over_ranks)
             return outs
         run_resident(0)
         ms = device_ms(run_resident, 2)
+        eng.cfg["packed"] = False                                  # the reference's pad-to-max layout, for comparison
+        run_resident(0)
+        ms_padded = device_ms(run_resident, 2)
+        eng.cfg["packed"] = True
         run_e2e(0)
         barrier()
         t0 = time.perf_counter()
@@ -463,11 +467,65 @@ def run_also(args, w, world, rank, dev, trainer, model, barrier, max_over_ranks)
         return {"utterances": n_utt, "frames": tot_frames, "batches_per_rank": len(batches), "padded_frames_this_rank":
                 sum(len(idx) * max(lens[i] for i in idx) for idx in batches), "frames_this_rank": frames_mine,
                 "ms": round(ms, 3), "utterances_per_s": round(n_utt / (ms / 1e3), 1), "frames_per_s": round(tot_frames / (ms / 1e3), 1),
+                "ms_padded_layout": round(ms_padded, 3), "layout": "packed (sum(lengths) rows, attention by row offsets; SURVEY.md 8(f) N2)",
                 "e2e_ms": round(ms_e2e, 3), "e2e_utterances_per_s": round(n_utt / (ms_e2e / 1e3), 1),
                 "what": "eval-mode encoder forward (BN running statistics) + w_aux + CTC best-path decode (sst_ctc_greedy), lengths ~ "
                         "clip(lognormal(450, 0.5), 100, 1500) frames, length-sorted and dealt round-robin to the ranks, <= 64 000 frames "
                         "per batch; e2e = from pinned host buffers incl. the D2H of the decoded ids"}
     guarded("cfg5_inference", cfg5)
+
+    # ---- N2: a ragged TRAINING batch (lognormal lengths, one length bucket would be narrower), packed vs pad-to-max ---------------
+    def ragged_training():
+        lens = sorted(lognormal_lengths(400, seed=11 + rank))
+        lens = lens[100:100 + 110]                                 # a contiguous slice of the length-sorted corpus, ~ one batch
+        while sum(lens) > 64000:
+            lens.pop()
+        b = make_batch(lengths=lens, tgt_min=20, tgt_max=60, seed=9500 + rank)
+        d = trainer.to_device(trainer.prepare(b))
+        pristine = d["X"].clone()
+        chunks = world * d["X"].shape[0]
+        res = {"utterances": len(lens), "frames": sum(lens), "padded_frames": len(lens) * max(lens)}
+
+        def step(_):
+            d["X"].copy_(pristine)
+            trainer.step_device(d, global_chunks=chunks)
+        for packed in (True, False):
+            trainer.eng.cfg["packed"] = packed
+            step(0)
+            step(0)
+            ms = device_ms(step, 4)
+            res["ms_packed" if packed else "ms_padded"] = round(ms, 3)
+        trainer.eng.cfg["packed"] = True
+        res["frames_per_s_packed"] = round(world * sum(lens) / (res["ms_packed"] / 1e3), 1)
+        res["what"] = "one training step (fwd+bwd+loss+AdamW) on a ragged batch per rank; real frames / time"
+        return res
+    guarded("ragged_training", ragged_training)
+
+    # ---- N4: one beam-search decoder step (BeamSearch.py:111-114), 100 hypotheses of 30 tokens over a 1000-frame memory ----------
+    def beam_step():
+        from sst_b200.beam_search import BeamDecoder
+        model.eval()
+        b = make_batch(1, 1000, 10, 20, seed=8100 + rank)
+        X = prepare_batch(b)["X"].to(dev)
+        n_hyp, t = 100, 30
+        hist = torch.randint(0, 40, (n_hyp, t), device=dev, dtype=torch.int64)
+        hist[:, 0] = 41
+        with torch.no_grad():
+            memory, _ = model(b["lengths"], dev, mode='beam_search', part='encoder', x_raw=X)
+            dec = BeamDecoder(model, memory)
+
+            def shared(_):
+                dec.step_logits(hist)
+
+            def repeat(_):
+                model(b["lengths"], dev, mode='beam_search', part='decoder', y=hist, memory=memory.repeat(n_hyp, 1, 1))[:, -1, :-2]
+            shared(0); repeat(0)
+            ms_s, ms_r = device_ms(shared, 5), device_ms(repeat, 5)
+        model.train()
+        return {"hypotheses": n_hyp, "prefix_tokens": t, "memory_frames": 1000, "ms_shared_memory": round(ms_s, 3),
+                "ms_memory_repeat": round(ms_r, 3), "what": "BeamDecoder (memory projected once, k_off = 0) vs the reference call "
+                "pattern memory.repeat(n_hyp, 1, 1) through Model.forward(part='decoder'); identical logits"}
+    guarded("beam_decoder_step", beam_step)
 
     # ---- cfg3 (BASELINE.json configs[2]): 8 encoder + 4 decoder layers, alpha 0.7 -----------------------------------------------
     def cfg3():

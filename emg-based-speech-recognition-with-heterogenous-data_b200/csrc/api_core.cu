@@ -26,6 +26,15 @@ int check_launch(const char* what, int n_kernels) {
   return SST_OK;
 }
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SST_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 int num_sms() {
   static int n = 0;
   if (!n) {

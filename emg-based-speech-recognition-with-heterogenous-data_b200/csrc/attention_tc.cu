@@ -90,6 +90,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();                                     // set-up above overlaps the previous kernel's tail (sst_common.cuh)
+  pdl_trigger();
 
   if (w == NW) {
     // ============================================ issuer (one thread) ============================================
@@ -353,7 +355,8 @@ static int attn_fwd_tc_launch_n(const SstAttnDesc& d, const void* q, const void*
   }
   const long n_items = (long)cdiv(d.Lq, BM) * d.H * d.B;
   const int grid = (int)(n_items < num_sms() ? n_items : num_sms());       // persistent: one CTA per SM
-  attn_fwd_tc_kernel<DH, NSPLIT><<<grid, 128 * NSPLIT + 32, SMEM, st>>>(tmQ, tmK, tmV, tmE, p);
+  cudaError_t le = launch_pdl(attn_fwd_tc_kernel<DH, NSPLIT>, dim3(grid), dim3(128 * NSPLIT + 32), SMEM, st, tmQ, tmK, tmV, tmE, p);
+  SST_REQUIRE(le == cudaSuccess, SST_E_LAUNCH, "attn_fwd_tc launch: %s", cudaGetErrorString(le));
   return check_launch("attn_fwd_tc");
 }
 

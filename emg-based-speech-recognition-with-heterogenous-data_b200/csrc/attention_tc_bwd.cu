@@ -164,6 +164,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();                                     // dO comes from the kernel right in front of this one (sst_common.cuh)
+  pdl_trigger();
 
   int t_lo, t_hi, t_hi_full;
   key_tile_range(p, i0, t_lo, t_hi_full);
@@ -444,6 +446,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();                                     // the hand-off tiles come from the dQ kernel right in front of this one
+  pdl_trigger();
 
   // Packed layouts: key tiles beyond an entry's keys are not items at all, query tiles beyond its queries are not visited
   // (the dQ kernel wrote no hand-off tiles for them).  The issuer and the epilogue warps walk the same item sequence.
@@ -635,12 +639,14 @@ static int attn_bwd_tc_launch_n(const SstAttnDesc& d, const void* q, const void*
     SST_REQUIRE(e == cudaSuccess, SST_E_LAUNCH, "cudaFuncSetAttribute(attn_bwd_tc): %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  attn_bwd_dq_tc_kernel<DH, NSPLIT><<<dim3(cdiv(d.Lq, BM), d.H, d.B), 128 * NSPLIT + 32, SMEM_DQ, st>>>(
-      tmK, tmV, tmE, p, reinterpret_cast<const __nv_bfloat16*>(q));
+  cudaError_t le = launch_pdl(attn_bwd_dq_tc_kernel<DH, NSPLIT>, dim3(cdiv(d.Lq, BM), d.H, d.B), dim3(128 * NSPLIT + 32), SMEM_DQ, st,
+                              tmK, tmV, tmE, p, reinterpret_cast<const __nv_bfloat16*>(q));
+  SST_REQUIRE(le == cudaSuccess, SST_E_LAUNCH, "attn_bwd_dq_tc launch: %s", cudaGetErrorString(le));
   {
     const int n_kt = cdiv(d.Lk, BN), n_items = n_kt * d.H * d.B;
     const int grid = n_items < num_sms() ? n_items : num_sms();
-    attn_bwd_dkv_tc_kernel<DH><<<grid, 160, SMEM_DKV, st>>>(tmQ, tmDO, tmP, tmDS, p, n_kt, n_items);
+    le = launch_pdl(attn_bwd_dkv_tc_kernel<DH>, dim3(grid), dim3(160), SMEM_DKV, st, tmQ, tmDO, tmP, tmDS, p, n_kt, n_items);
+    SST_REQUIRE(le == cudaSuccess, SST_E_LAUNCH, "attn_bwd_dkv_tc launch: %s", cudaGetErrorString(le));
   }
   return check_launch("attn_bwd_tc", 2);
 }

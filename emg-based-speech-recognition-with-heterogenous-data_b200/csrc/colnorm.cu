@@ -55,6 +55,8 @@ template <typename T>
 __global__ void __launch_bounds__(512)
 colstats_kernel(const T* __restrict__ x, long rows, int C, long ld, double* __restrict__ stats, long rows_per_block, ColSmem sm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  pdl_wait();                 // launched with launch_pdl (sst_common.cuh): nothing of global memory is touched before this
+  pdl_trigger();
   double* dbuf = reinterpret_cast<double*>(smem_raw);
   constexpr int U = 2;
   const ColGeom cg = col_geom<T>(smem_raw + sm.red_bytes, U, sm.nt);
@@ -92,6 +94,8 @@ template <typename T>
 __global__ void __launch_bounds__(512)
 colsum_kernel(const T* __restrict__ x, long rows, int C, long ld, float* __restrict__ out, long rows_per_block, ColSmem sm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  pdl_wait();                 // launched with launch_pdl (sst_common.cuh): nothing of global memory is touched before this
+  pdl_trigger();
   float* fbuf = reinterpret_cast<float*>(smem_raw);
   constexpr int U = 2;
   const ColGeom cg = col_geom<T>(smem_raw + sm.red_bytes, U, sm.nt);
@@ -149,6 +153,8 @@ __global__ void __launch_bounds__(512)
 bn_apply_kernel(BnBranch a, BnBranch b, int has_b, int relu, T* __restrict__ out, long n_chunks, int Tlen, int C, int lead,
                 int trail, long prows_per_block, ColSmem sm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  pdl_wait();                 // launched with launch_pdl (sst_common.cuh): nothing of global memory is touched before this
+  pdl_trigger();
   constexpr int U = 1;
   const ColGeom cg = col_geom<T>(smem_raw, U, sm.nt);
   const int c = threadIdx.x * 8, TY = blockDim.y;
@@ -252,6 +258,8 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, long ld_dout, const T* __restri
                      int relu, BnBranch a, BnBranch b, int has_b, long n_chunks, int Tlen, int C,
                      double* __restrict__ red, long rows_per_block, ColSmem sm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  pdl_wait();                 // launched with launch_pdl (sst_common.cuh): nothing of global memory is touched before this
+  pdl_trigger();
   double* dbuf = reinterpret_cast<double*>(smem_raw);
   constexpr int U = 1;
   const ColGeom cg = col_geom<T>(smem_raw + sm.red_bytes + sm.sgn_bytes, U, sm.nt);
@@ -349,6 +357,8 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, long ld_dout, const T* __restric
                     int relu, BnBranch a, BnBranch b, int has_b, BnGradOut ga, BnGradOut gb, long n_chunks,
                     int Tlen, int C, const double* __restrict__ red, long rows_per_block, ColSmem sm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  pdl_wait();                 // launched with launch_pdl (sst_common.cuh): nothing of global memory is touched before this
+  pdl_trigger();
   constexpr int U = 1;
   const ColGeom cg = col_geom<T>(smem_raw + sm.sgn_bytes, U, sm.nt);
   const int c = threadIdx.x * 8, TY = blockDim.y;
@@ -499,7 +509,8 @@ using namespace sst;
   do {                                                                                     \
     int rc_ = opt_in_smem(KERNEL<T_>, cl.smem);                                            \
     if (rc_) return rc_;                                                                   \
-    KERNEL<T_><<<cl.grid, cl.block, cl.smem, st>>>(__VA_ARGS__);                           \
+    cudaError_t le_ = launch_pdl(KERNEL<T_>, dim3(cl.grid), dim3(cl.block), cl.smem, st, __VA_ARGS__);   \
+    SST_REQUIRE(le_ == cudaSuccess, SST_E_LAUNCH, #KERNEL " launch: %s", cudaGetErrorString(le_)); \
   } while (0)
 
 extern "C" {

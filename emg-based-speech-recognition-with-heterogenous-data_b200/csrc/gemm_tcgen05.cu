@@ -127,6 +127,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) SST_TRACE(1);                                  // barriers, TMEM, cluster sync done
+  pdl_wait();                 // everything above ran under the previous kernel's tail; from here on global memory is touched
+  pdl_trigger();              // the next kernel's CTAs may take this SM's resources as soon as this CTA leaves
 
   const int total_units = p.m_blks * p.n_blks * p.splits;
 
@@ -583,11 +585,13 @@ static int launch_bn(const SstGemmDesc& d, const void* A, const void* B, GemmKPa
   cfg.blockDim = dim3(G_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CTAS>, tmA, tmB, p);
   SST_REQUIRE(le == cudaSuccess, SST_E_LAUNCH, "gemm_tcgen05 launch: %s", cudaGetErrorString(le));
   return check_launch("gemm_tcgen05");

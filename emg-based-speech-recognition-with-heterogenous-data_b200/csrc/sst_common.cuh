@@ -20,6 +20,29 @@ int  check_launch(const char* what, int n_kernels = 1);   // counts launches; cu
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 int num_sms();
 
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// A step is ~440 back-to-back launches on one stream.  Kernels launched through launch_pdl() may be scheduled while the previous
+// kernel of the stream is still draining (its CTAs have all passed pdl_trigger() or exited): block scheduling, barrier / TMEM set-up
+// and tensor-map prefetch then run under the predecessor's tail instead of after it.  EVERY such kernel calls pdl_wait() before it
+// touches global memory (loads, stores, TMA): that returns once the predecessor has completed and its writes are visible -- by
+// induction everything earlier in the stream has, too.  Both instructions are no-ops in a kernel launched the ordinary way.
+// SST_PDL=0 turns the launch attribute off (bench.py measures both).
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- dtype helpers --------------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
