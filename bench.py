@@ -383,17 +383,49 @@ def run_also(args, w, world, rank, dev, trainer, model, barrier, max_over_ranks)
             for i, d in enumerate(hb):
                 d["X"].copy_(pristine[i])
                 trainer.step_device(d, global_chunks=world * chunks)
+
+        def cycle_graphed(_):
+            for i, d in enumerate(hb):
+                d["X"].copy_(pristine[i])
+                trainer.step_graphed(d, global_chunks=world * chunks)
         cycle(0)
         ms = device_ms(cycle, 2)
         n_opt = trainer.flat.step_count - steps_before
+        ms_graphed = None
+        if world == 1:                                             # CUDA-graph replay of the micro-steps (single process)
+            for _ in range(3):
+                cycle_graphed(0)                                   # two eager passes per signature, then the captures
+            ms_graphed = device_ms(cycle_graphed, 3)
         trainer.batch_size_grad = 1
         trainer.start_epoch()
         return {"reading": "batch_size_grad = 200 chunks x 1600 samples per GPU reached in 12 micro-batches of %d chunks (%d utt x %d "
                            "samples); summed gradients; all-reduce + AdamW on the 12th micro-step only; model = headline workload "
                            "(no conformer code in the reference)" % (chunks, utt, frames * 8),
                 "ms_per_cycle": round(ms, 3), "optimizer_steps": n_opt, "cycles_run": 3,
-                "frames_per_s": round(world * n_micro * utt * frames / (ms / 1e3), 1)}
+                "frames_per_s": round(world * n_micro * utt * frames / (ms / 1e3), 1),
+                "cuda_graphs": None if ms_graphed is None else {
+                    "ms_per_cycle": round(ms_graphed, 3), "frames_per_s": round(n_micro * utt * frames / (ms_graphed / 1e3), 1),
+                    "what": "Trainer.step_graphed: each of the 12 micro-batch signatures replayed as one CUDA graph (dropout salt, "
+                            "learning rate and Adam bias corrections through device memory); the eager cycle above is bound by the "
+                            "host's launch rate"}}
     guarded("cfg4_accumulation", cfg4)
+
+    # ---- cfg1 (BASELINE.json configs[0]): the reference's CPU-runnable batch, 4 utterances x 200 frames -- launch-bound on a B200 ---
+    def cfg1():
+        if world > 1:
+            return {"note": "single-process measurement"}
+        hb = [trainer.to_device(trainer.prepare(make_batch(4, 200, 28, 32, seed=7600 + i))) for i in range(2)]
+        hb = [dict(d) for d in hb]
+        res = {}
+        for name, fn in (("eager", trainer.step_device), ("cuda_graph", trainer.step_graphed)):
+            for i in range(6):
+                fn(hb[i % 2], global_chunks=hb[i % 2]["X"].shape[0])
+            ms = device_ms(lambda i: fn(hb[i % 2], global_chunks=hb[i % 2]["X"].shape[0]), 20)
+            res["ms_per_step_" + name] = round(ms, 3)
+        res["frames_per_s_cuda_graph"] = round(800 / (res["ms_per_step_cuda_graph"] / 1e3), 1)
+        res["what"] = "headline model, 4 utterances x 1600 samples per step (SURVEY.md 8(d) cfg1 shape), fwd+bwd+loss+AdamW every step"
+        return res
+    guarded("cfg1_small_batch", cfg1)
 
     # ---- N1: reference-semantics greedy attention decoding (greedy_search.py:7-53), latency per utterance ------------------------
     def greedy():

@@ -26,6 +26,9 @@ int check_launch(const char* what, int n_kernels) {
   return SST_OK;
 }
 
+static const unsigned long long* g_salt = nullptr;
+const unsigned long long* dropout_salt() { return g_salt; }
+
 bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -63,6 +66,11 @@ int sst_device_check(void) {
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   if (e != cudaSuccess) { sst::set_error("no CUDA device: %s", cudaGetErrorString(e)); return SST_E_ARCH; }
   if (major != 10) { sst::set_error("device is sm_%d0, libsst.so is built for sm_100a only", major); return SST_E_ARCH; }
+  return SST_OK;
+}
+
+int sst_set_dropout_salt(const uint64_t* salt_dev) {
+  sst::g_salt = reinterpret_cast<const unsigned long long*>(salt_dev);
   return SST_OK;
 }
 

@@ -12,6 +12,7 @@ struct AttnP {
   int causal, mask_q_rows, R;
   float scale;
   uint32_t thr; float dscale; unsigned long long seed;
+  const unsigned long long* salt;
   const int* q_lens; const int* k_lens;
   const uint8_t* q_pad; const uint8_t* k_pad;
   const long long* q_off; const long long* k_off;     // packed layouts (include/sst.h): first row of entry b, or null
@@ -98,7 +99,7 @@ attn_fwd_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __restr
   if (lane == 0) { lse[row_id] = mx; lse[nrows + row_id] = __logf(sum); }
   for (int jj = lane; jj < nk; jj += 32) {
     float pr = sc[jj] * inv;
-    if (p.thr) pr = philox_keep16(p.seed, (unsigned long long)row_id * p.Lkp + (lo + jj), p.thr) ? pr * p.dscale : 0.f;
+    if (p.thr) pr = philox_keep16(salted(p.seed, p.salt), (unsigned long long)row_id * p.Lkp + (lo + jj), p.thr) ? pr * p.dscale : 0.f;
     sc[jj] = pr;
   }
   __syncwarp();
@@ -154,7 +155,7 @@ attn_bwd_dq_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     const float s = make_logit(p, b, i, j, qk, qe, masked);
     const float pr = __expf((s - Lm) - Ll);
     float dp = dot_row(dos, v + (kb + j) * p.ldv + h * p.dh, p.dh);
-    if (p.thr) dp = philox_keep16(p.seed, (unsigned long long)row_id * p.Lkp + j, p.thr) ? dp * p.dscale : 0.f;
+    if (p.thr) dp = philox_keep16(salted(p.seed, p.salt), (unsigned long long)row_id * p.Lkp + j, p.thr) ? dp * p.dscale : 0.f;
     const float ds = pr * (dp - dl);
     dsq[jj] = masked ? 0.f : ds * p.scale;
     dsb[jj] = inband ? ds : 0.f;
@@ -219,7 +220,7 @@ attn_bwd_dkv_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __r
     const float pr = __expf((s - lse[rid]) - lse[(long)p.B * p.H * p.Lq + rid]);
     float dp = dot_row(vs, dO + tokq * p.ldo + h * p.dh, p.dh);
     float keep = 1.f;
-    if (p.thr) keep = philox_keep16(p.seed, (unsigned long long)rid * p.Lkp + j, p.thr) ? p.dscale : 0.f;
+    if (p.thr) keep = philox_keep16(salted(p.seed, p.salt), (unsigned long long)rid * p.Lkp + j, p.thr) ? p.dscale : 0.f;
     dp *= keep;
     const float ds = pr * (dp - delta[rid]);
     pw[ii] = pr * keep;
@@ -248,6 +249,7 @@ static AttnP make_params(const SstAttnDesc& d, const int* q_lens, const int* k_l
   p.thr = d.drop_p > 0.f ? drop_threshold16(d.drop_p) : 0u;
   p.dscale = d.drop_p < 1.f ? 1.f / (1.f - d.drop_p) : 0.f;
   p.seed = d.seed;
+  p.salt = dropout_salt();
   p.q_lens = q_lens; p.k_lens = k_lens;
   p.q_pad = d.q_pad; p.k_pad = d.k_pad;
   p.q_off = reinterpret_cast<const long long*>(d.q_off); p.k_off = reinterpret_cast<const long long*>(d.k_off);

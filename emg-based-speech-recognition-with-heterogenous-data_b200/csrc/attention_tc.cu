@@ -208,6 +208,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int q = w & 3, hf = w >> 2;
     const int li = 32 * q + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const unsigned long long seed = p.thr ? salted(p.seed, p.salt) : 0ull;
     uint32_t g = 0;                                 // running tile counter, in step with the issuer's
     // The O rows of a finished item are written out one tile late, from inside the NEXT item's first tile: the wait for the
     // item's last PV (~0.3 us of MMA latency with nothing else to do) then falls behind that tile's logits / exp work.
@@ -257,7 +258,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int x = 0; x < CW; ++x) { U[x] = __expf(U[x] - m_new); sum += U[x]; }   // exact subtraction first: m can be -1e8
         if (p.thr) {
           float keep[CW];
-          dropout_keep<NSPLIT>(p, rc, t * BN, hf, keep);
+          dropout_keep<NSPLIT>(p, seed, rc, t * BN, hf, keep);
 #pragma unroll
           for (int x = 0; x < CW; ++x) U[x] *= keep[x];
         }

@@ -30,6 +30,7 @@ struct AttnTcParams {
   int causal, mask_q_rows, R, band;
   float scale;
   uint32_t thr; float dscale; unsigned long long seed;   // thr: 16-bit keep threshold (0 = no dropout)
+  const unsigned long long* salt;                         // added to the seed when registered (sst_common.cuh)
   const int* q_lens; const int* k_lens;
   const uint8_t* q_pad; const uint8_t* k_pad;   // optional per-position padding masks (OR-ed with the length masks)
   const long long* q_off; const long long* k_off;   // packed layouts (include/sst.h): first row of entry b, or null = b*Lq / b*Lk
@@ -67,6 +68,7 @@ inline AttnTcParams make_tc_params(const SstAttnDesc& d, const int* q_lens, cons
   p.thr = d.drop_p > 0.f ? drop_threshold16(d.drop_p) : 0u;
   p.dscale = d.drop_p < 1.f ? 1.f / (1.f - d.drop_p) : 0.f;
   p.seed = d.seed;
+  p.salt = dropout_salt();
   p.q_lens = q_lens; p.k_lens = k_lens;
   p.q_pad = d.q_pad; p.k_pad = d.k_pad;
   p.q_off = reinterpret_cast<const long long*>(d.q_off); p.k_off = reinterpret_cast<const long long*>(d.k_off);
@@ -257,12 +259,13 @@ __device__ __forceinline__ bool tile_is_simple(const AttnTcParams& p, const RowC
 // keep factors (0 or 1/(1-pd)) of the thread's CW keys: counter = row_id * Lkp + j, eight keys per Philox block, the same
 // stream as the CUDA-core kernels of attention_simt.cu
 template <int NSPLIT>
-__device__ __forceinline__ void dropout_keep(const AttnTcParams& p, const RowCtx& rc, int j0, int hf, float (&keep)[Split<NSPLIT>::CW]) {
+__device__ __forceinline__ void dropout_keep(const AttnTcParams& p, unsigned long long seed, const RowCtx& rc, int j0, int hf,
+                                             float (&keep)[Split<NSPLIT>::CW]) {
   constexpr int CW = Split<NSPLIT>::CW;
   const unsigned long long base = ((unsigned long long)rc.row_id * p.Lkp + j0 + CW * hf) >> 3;
 #pragma unroll
   for (int g = 0; g < CW / 8; ++g) {
-    const Philox4 r = philox4x32(p.seed, base + g);
+    const Philox4 r = philox4x32(seed, base + g);
     const uint32_t thr_hi = p.thr << 16;
 #pragma unroll
     for (int e = 0; e < 8; ++e) keep[g * 8 + e] = philox_keep16_at(r, e, thr_hi) ? p.dscale : 0.f;

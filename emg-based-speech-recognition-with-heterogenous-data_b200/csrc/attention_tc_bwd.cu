@@ -52,7 +52,8 @@ __device__ __forceinline__ void issue_s_pb_dp(uint32_t tmem_s, uint32_t tmem_pb,
 // Per-row backward math of the thread's CW keys.  In: U = logits, (Lm, Ll) saved softmax statistics, delta.
 // Out: U[x] = dropped-out probability P~ (what multiplies dO in dV), W[x] = dS (gradient w.r.t. the logit).
 template <int NSPLIT>
-__device__ __forceinline__ void tile_backward_row(const AttnTcParams& p, const RowCtx& rc, uint32_t tDP /* incl. lane base */, int j0,
+__device__ __forceinline__ void tile_backward_row(const AttnTcParams& p, unsigned long long seed, const RowCtx& rc,
+                                                  uint32_t tDP /* incl. lane base */, int j0,
                                                   int hf, float Lm, float Ll, float delta, float (&U)[Split<NSPLIT>::WIN_LD],
                                                   float (&W)[Split<NSPLIT>::CW]) {
   constexpr int CW = Split<NSPLIT>::CW;
@@ -60,7 +61,7 @@ __device__ __forceinline__ void tile_backward_row(const AttnTcParams& p, const R
   // p = exp((s - max) - logsum): two subtractions in fp32 (max can be -1e8, where max + logsum would swallow logsum)
   if (p.thr) {
     float keep[CW];
-    dropout_keep<NSPLIT>(p, rc, j0, hf, keep);
+    dropout_keep<NSPLIT>(p, seed, rc, j0, hf, keep);
 #pragma unroll
     for (int x = 0; x < CW; ++x) {
       const float pr = __expf((U[x] - Lm) - Ll);
@@ -316,6 +317,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
   } else {
     // ============================================ compute warps ==================================================
     delta = sdelta[li];
+    const unsigned long long seed = p.thr ? salted(p.seed, p.salt) : 0ull;
     // shared-memory address of this thread's CW relative columns c = (127 - li + CW*hf) + x in the swizzled dS_rel tile
     uint32_t rel_addr[CW];
     {
@@ -348,7 +350,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_sfree);    // the issuer may overwrite S / PB / dP with the next tile
 
-      if (!skip) tile_backward_row<NSPLIT>(p, rc, 0xffffffffu, t * BN, hf, Lm, Ll, delta, U, W);
+      if (!skip) tile_backward_row<NSPLIT>(p, seed, rc, 0xffffffffu, t * BN, hf, Lm, Ll, delta, U, W);
       if (k > 0) ptx::mbar_wait(bar_dq, (uint32_t)((k - 1) & 1));     // dQ(t-1) has finished reading dS_rel / the dS tile
       if (!skip) {
         // bias term: dS at its relative column c = lj - li + 127 (zero outside the band); addresses are tile-independent

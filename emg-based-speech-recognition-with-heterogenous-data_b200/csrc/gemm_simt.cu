@@ -17,6 +17,7 @@ struct SimtParams {
   float alpha, mask_scale, drop_scale;
   uint32_t drop_thr;
   unsigned long long seed;
+  const unsigned long long* salt;
   const float* bias;
   const void* aux;
   int aux_dtype;
@@ -125,7 +126,7 @@ gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, const SimtPar
       if (p.epilogue & SST_EPI_BIAS) v += p.bias[n];
       if (p.epilogue & SST_EPI_RELU) v = fmaxf(v, 0.f);
       if (p.epilogue & SST_EPI_DROPOUT)
-        v = philox_keep16(p.seed, (unsigned long long)m * (unsigned long long)p.N + n, p.drop_thr) ? v * p.drop_scale : 0.f;
+        v = philox_keep16(salted(p.seed, p.salt), (unsigned long long)m * (unsigned long long)p.N + n, p.drop_thr) ? v * p.drop_scale : 0.f;
       if (p.epilogue & SST_EPI_MULMASK)
         v *= (ld_as_f32(p.aux, (long)m * p.ldaux + n, p.aux_dtype) > 0.f) ? p.mask_scale : 0.f;
       long ci = out_row * p.ldc + n;
@@ -164,6 +165,7 @@ int launch_gemm_simt(const SstGemmDesc& d, const void* A, const void* B, void* C
   p.drop_thr = drop_threshold16(d.drop_p);
   p.drop_scale = d.drop_p < 1.f ? 1.f / (1.f - d.drop_p) : 0.f;
   p.seed = d.seed;
+  p.salt = dropout_salt();
   p.bias = reinterpret_cast<const float*>(bias);
   p.aux = aux; p.aux_dtype = d.aux_dtype;
   p.C = C; p.out_dtype = d.out_dtype;

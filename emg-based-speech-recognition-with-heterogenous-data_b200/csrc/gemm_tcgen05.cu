@@ -40,6 +40,7 @@ struct GemmKParams {
   float alpha, mask_scale, drop_scale;
   uint32_t drop_thr;
   unsigned long long seed;
+  const unsigned long long* salt;
   const float* bias;
   const void* aux;
   long ldaux;
@@ -235,13 +236,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // main loop: the dropout keep bits (Philox, eight 16-bit lanes per block) and the ReLU/dropout mask bits of `aux`.
       constexpr int CPW = BN / 32 / G_CGROUPS;      // 32-column chunks per epilogue warp
       const uint32_t stg = ptx::smem_u32(staging) + (uint32_t)(warp - 2) * 2048;
+      const unsigned long long seed_eff = (p.epilogue & SST_EPI_DROPOUT) ? salted(p.seed, p.salt) : 0ull;
       Philox4 rnd[4];                               // 16-bit lane e of block i8 decides column i8 * 8 + e of a chunk
       uint32_t mask_bits[CPW];
       auto draw = [&](int lc) {                     // the four Philox blocks of chunk lc (kept in registers until used)
         const int nbase = n0 + (cg * CPW + lc) * 32;
         const unsigned long long e0 = (unsigned long long)m * (unsigned long long)p.N + (unsigned long long)nbase;
 #pragma unroll
-        for (int i8 = 0; i8 < 4; ++i8) rnd[i8] = philox4x32(p.seed, (e0 >> 3) + i8);
+        for (int i8 = 0; i8 < 4; ++i8) rnd[i8] = philox4x32(seed_eff, (e0 >> 3) + i8);
       };
       if (p.epilogue & SST_EPI_DROPOUT) draw(0);    // first chunk's bits are produced under the MMA main loop
       if (p.epilogue & SST_EPI_MULMASK) {
@@ -634,6 +636,7 @@ int launch_gemm_tcgen05(const SstGemmDesc& d, const void* A, const void* B, void
   p.drop_thr = drop_threshold16(d.drop_p);
   p.drop_scale = d.drop_p < 1.f ? 1.f / (1.f - d.drop_p) : 0.f;
   p.seed = d.seed;
+  p.salt = dropout_salt();
   p.bias = reinterpret_cast<const float*>(bias);
   p.aux = aux; p.ldaux = d.ldaux; p.aux_f32 = d.aux_dtype == SST_F32;
   p.C = C; p.ldc = d.ldc; p.out_f32 = d.out_dtype == SST_F32;

@@ -98,7 +98,9 @@ __global__ void scatter_rows_kernel(const T* __restrict__ dout, T* __restrict__ 
 // out[(b,s), :] = dropout( W[y[b,s], :] + pe[b, :] / D )
 template <typename T>
 __global__ void embed_posenc_kernel(const long* __restrict__ y, const float* __restrict__ W, const float* __restrict__ pe,
-                                    T* __restrict__ out, int B, int S, int D, uint32_t thr, float dscale, unsigned long long seed) {
+                                    T* __restrict__ out, int B, int S, int D, uint32_t thr, float dscale, unsigned long long seed,
+                                    const unsigned long long* __restrict__ salt) {
+  if (thr) seed = salted(seed, salt);
   const int dv = D / 8;
   const long total = (long)B * S * dv;
   const float invD = 1.f / (float)D;
@@ -124,7 +126,9 @@ __global__ void embed_posenc_kernel(const long* __restrict__ y, const float* __r
 // dW[y[row], :] += keep * dout[row, :]   (rows with y == pad_idx skipped: nn.Embedding padding_idx)
 template <typename T>
 __global__ void embed_bwd_kernel(const long* __restrict__ y, const T* __restrict__ dout, float* __restrict__ dW, int B, int S, int D,
-                                 int pad_idx, uint32_t thr, float dscale, unsigned long long seed) {
+                                 int pad_idx, uint32_t thr, float dscale, unsigned long long seed,
+                                 const unsigned long long* __restrict__ salt) {
+  if (thr) seed = salted(seed, salt);
   const int dv = D / 8;
   const long total = (long)B * S * dv;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -309,9 +313,12 @@ permute3_batch_kernel(const SstPermuteItem* __restrict__ items, int n_items) {
   }
 }
 
+// hyper != nullptr: (lr, bias correction 1, sqrt of bias correction 2) come from device memory -- the values a captured graph
+// replays must not be baked into it (sst_adamw_dev)
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
                              float lr, float beta1, float beta2, float eps, float wd, float bc1, float sqrt_bc2,
-                             __nv_bfloat16* __restrict__ p_bf16) {
+                             __nv_bfloat16* __restrict__ p_bf16, const float* __restrict__ hyper) {
+  if (hyper != nullptr) { lr = hyper[0]; bc1 = hyper[1]; sqrt_bc2 = hyper[2]; }
   for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long)gridDim.x * blockDim.x * 4) {
     if (i + 4 <= n) {
       float4 pp = *reinterpret_cast<float4*>(p + i), gg = *reinterpret_cast<const float4*>(g + i);
@@ -357,7 +364,8 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 template <typename T, bool BWD>
 __global__ void __launch_bounds__(256)
 gelu_dropout_kernel(const T* __restrict__ x, long ldx, const T* __restrict__ dy, long lddy, T* __restrict__ out, long ldo, long rows, int cols,
-                    uint32_t thr16, float dscale, unsigned long long seed) {
+                    uint32_t thr16, float dscale, unsigned long long seed, const unsigned long long* __restrict__ salt) {
+  if (thr16) seed = salted(seed, salt);
   const int vpr = cols >> 3;                                          // vectors per row
   const long total = rows * vpr;
   for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long)gridDim.x * blockDim.x) {
@@ -437,8 +445,8 @@ int sst_embed_posenc_fwd(int out_dtype, const int64_t* y, const float* W, const 
   const uint32_t thr = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
   const float ds = drop_p < 1.f ? 1.f / (1.f - drop_p) : 0.f;
   const int grid = ew_grid2((long)B * S * (D / 8), 256);
-  if (out_dtype == SST_F32) embed_posenc_kernel<float><<<grid, 256, 0, st>>>((const long*)y, W, pe, (float*)out, B, S, D, thr, ds, seed);
-  else embed_posenc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const long*)y, W, pe, (__nv_bfloat16*)out, B, S, D, thr, ds, seed);
+  if (out_dtype == SST_F32) embed_posenc_kernel<float><<<grid, 256, 0, st>>>((const long*)y, W, pe, (float*)out, B, S, D, thr, ds, seed, dropout_salt());
+  else embed_posenc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const long*)y, W, pe, (__nv_bfloat16*)out, B, S, D, thr, ds, seed, dropout_salt());
   return check_launch("embed_posenc_fwd");
 }
 
@@ -450,8 +458,8 @@ int sst_embed_bwd(int dtype, const int64_t* y, const void* dout, float* dW, int 
   const uint32_t thr = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
   const float ds = drop_p < 1.f ? 1.f / (1.f - drop_p) : 0.f;
   const int grid = ew_grid2((long)B * S * (D / 8), 256);
-  if (dtype == SST_F32) embed_bwd_kernel<float><<<grid, 256, 0, st>>>((const long*)y, (const float*)dout, dW, B, S, D, pad_idx, thr, ds, seed);
-  else embed_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const long*)y, (const __nv_bfloat16*)dout, dW, B, S, D, pad_idx, thr, ds, seed);
+  if (dtype == SST_F32) embed_bwd_kernel<float><<<grid, 256, 0, st>>>((const long*)y, (const float*)dout, dW, B, S, D, pad_idx, thr, ds, seed, dropout_salt());
+  else embed_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const long*)y, (const __nv_bfloat16*)dout, dW, B, S, D, pad_idx, thr, ds, seed, dropout_salt());
   return check_launch("embed_bwd");
 }
 
@@ -531,7 +539,7 @@ static int gelu_launch(bool bwd, int dtype, int64_t rows, int cols, const void* 
   const float dscale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const int grid = ew_grid2(rows * (cols / 8), 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define SST_GELU(T, B) gelu_dropout_kernel<T, B><<<grid, 256, 0, st>>>((const T*)x, ldx, (const T*)dy, lddy, (T*)out, ldo, rows, cols, thr, dscale, seed)
+#define SST_GELU(T, B) gelu_dropout_kernel<T, B><<<grid, 256, 0, st>>>((const T*)x, ldx, (const T*)dy, lddy, (T*)out, ldo, rows, cols, thr, dscale, seed, dropout_salt())
   if (dtype == SST_F32) { if (bwd) SST_GELU(float, true); else SST_GELU(float, false); }
   else { if (bwd) SST_GELU(__nv_bfloat16, true); else SST_GELU(__nv_bfloat16, false); }
 #undef SST_GELU
@@ -559,8 +567,37 @@ int sst_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr,
   const int grid = ew_grid2((n + 3) / 4, 256);
   SST_REQUIRE(p_bf16 == nullptr || ((uintptr_t)p_bf16 & 7) == 0, SST_E_ARG, "adamw: bf16 shadow must be 8-byte aligned");
   adamw_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, (float)bc1,
-                                                                         (float)sqrt(bc2), reinterpret_cast<__nv_bfloat16*>(p_bf16));
+                                                                         (float)sqrt(bc2), reinterpret_cast<__nv_bfloat16*>(p_bf16), nullptr);
   return check_launch("adamw");
+}
+
+int sst_adamw_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float beta1, float beta2, float eps,
+                  float wd, void* p_bf16, void* stream) {
+  SST_REQUIRE(hyper != nullptr, SST_E_ARG, "adamw_dev: hyper (device float[3]: lr, 1 - beta1^t, sqrt(1 - beta2^t)) required");
+  if (n <= 0) return SST_OK;
+  const int grid = ew_grid2((n + 3) / 4, 256);
+  SST_REQUIRE(p_bf16 == nullptr || ((uintptr_t)p_bf16 & 7) == 0, SST_E_ARG, "adamw: bf16 shadow must be 8-byte aligned");
+  adamw_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, 0.f, beta1, beta2, eps, wd, 1.f, 1.f,
+                                                                         reinterpret_cast<__nv_bfloat16*>(p_bf16), hyper);
+  return check_launch("adamw_dev");
+}
+
+// ---- by-value scalars into device memory: the per-step values (dropout salt, learning rate, bias corrections) a replayed CUDA
+//      graph reads.  The bytes travel as a kernel PARAMETER, i.e. they are captured when this call returns: no pinned staging buffer
+//      whose lifetime the caller would have to manage.
+struct ScalarBlob { unsigned int w[16]; };
+__global__ void write_scalars_kernel(unsigned int* __restrict__ dst, ScalarBlob b, int nwords) {
+  if ((int)threadIdx.x < nwords) dst[threadIdx.x] = b.w[threadIdx.x];
+}
+
+int sst_write_scalars(void* dst, const void* src_host, int nbytes, void* stream) {
+  SST_REQUIRE(dst != nullptr && src_host != nullptr && nbytes > 0 && nbytes <= 64 && nbytes % 4 == 0 && ((uintptr_t)dst & 3) == 0,
+              SST_E_ARG, "write_scalars: 4..64 bytes, a multiple of 4, 4-byte aligned destination");
+  ScalarBlob b;
+  memset(&b, 0, sizeof(b));
+  memcpy(&b, src_host, (size_t)nbytes);
+  write_scalars_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned int*>(dst), b, nbytes / 4);
+  return check_launch("write_scalars");
 }
 
 }  // extern "C"

@@ -32,10 +32,12 @@ template <typename T, int NV, bool EXACT>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ r, T* __restrict__ y, T* __restrict__ s_out,
               const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ mean_out,
-              float* __restrict__ rstd_out, long rows, int D, float eps, uint32_t thr, float dscale, unsigned long long seed) {
+              float* __restrict__ rstd_out, long rows, int D, float eps, uint32_t thr, float dscale, unsigned long long seed,
+              const unsigned long long* __restrict__ salt) {
   extern __shared__ __align__(16) uint8_t ln_smem[];
   pdl_wait();
   pdl_trigger();
+  if (thr != 0) seed = salted(seed, salt);
   const int lane = threadIdx.x & 31;
   const int warp = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
   const int nwarps = (int)(gridDim.x * (blockDim.x >> 5));
@@ -129,10 +131,11 @@ __global__ void __launch_bounds__(256, 2)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ s, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, const float* __restrict__ gamma, T* __restrict__ ds, T* __restrict__ dr,
               float* __restrict__ dgamma, float* __restrict__ dbeta, long rows, int D, uint32_t thr, float dscale,
-              unsigned long long seed) {
+              unsigned long long seed, const unsigned long long* __restrict__ salt) {
   extern __shared__ __align__(16) uint8_t ln_smem[];   // [2][D] floats of column partials, then the ring
   pdl_wait();
   pdl_trigger();
+  if (dr != nullptr) seed = salted(seed, salt);
   float* red = reinterpret_cast<float*>(ln_smem);
   const int lane = threadIdx.x & 31;
   const int warp = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
@@ -263,7 +266,7 @@ int sst_layernorm_fwd(int dtype, int64_t rows, int D, const void* x, const void*
     }                                                                                                                        \
     SST_REQUIRE(smem <= 227 * 1024, SST_E_ARG, "layernorm: D=%d needs %zu bytes of shared memory", D, smem);                  \
     launch_pdl(ln_fwd_kernel<T_, NV_, EX_>, dim3(grid), dim3(TH), smem, st, (const T_*)x, (const T_*)r, (T_*)y, (T_*)s_out, gamma, beta, \
-               mean, rstd, rows, D, eps, thr, dscale, (unsigned long long)seed);                                               \
+               mean, rstd, rows, D, eps, thr, dscale, (unsigned long long)seed, dropout_salt());                               \
   } while (0)
   if (dtype == SST_F32) { if (D == 768) SST_LN_FWD(float, 3, true); else SST_LN_FWD(float, LN_MAXV, false); }
   else { if (D == 768) SST_LN_FWD(__nv_bfloat16, 3, true); else SST_LN_FWD(__nv_bfloat16, LN_MAXV, false); }
@@ -297,7 +300,7 @@ int sst_layernorm_bwd(int dtype, int64_t rows, int D, const void* dy, const void
     }                                                                                                                        \
     SST_REQUIRE(smem <= 227 * 1024, SST_E_ARG, "layernorm: D=%d needs %zu bytes of shared memory", D, smem);                  \
     launch_pdl(ln_bwd_kernel<T_, NV_, EX_>, dim3(grid), dim3(TH), smem, st, (const T_*)dy, (const T_*)s, mean, rstd, gamma, (T_*)ds,  \
-               (T_*)dr, dgamma, dbeta, rows, D, thr, dscale, (unsigned long long)seed);                                        \
+               (T_*)dr, dgamma, dbeta, rows, D, thr, dscale, (unsigned long long)seed, dropout_salt());                        \
   } while (0)
   if (dtype == SST_F32) { if (D == 768) SST_LN_BWD(float, 3, true); else SST_LN_BWD(float, LN_MAXV, false); }
   else { if (D == 768) SST_LN_BWD(__nv_bfloat16, 3, true); else SST_LN_BWD(__nv_bfloat16, LN_MAXV, false); }

@@ -43,6 +43,15 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// ---- dropout salt -------------------------------------------------------------------------------------
+// Dropout seeds cross the C ABI by value, which a captured CUDA graph would replay unchanged.  Every kernel that draws from the
+// Philox stream therefore adds *salt (a device uint64 the caller registered with sst_set_dropout_salt, or nothing when there is
+// none) to its seed: a replayed graph sees a fresh value the caller wrote in front of the replay (sst_write_scalars).
+const unsigned long long* dropout_salt();       // host: the registered device pointer (may be null)
+__device__ __forceinline__ unsigned long long salted(unsigned long long seed, const unsigned long long* salt) {
+  return salt != nullptr ? seed + *salt : seed;
+}
+
 // ---- dtype helpers --------------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }

@@ -517,7 +517,16 @@ class Engine:
             self.n += 1
             return (self.base * 1000003 + self.n * 7919) & 0xFFFFFFFFFFFFFFFF
 
-    def encode(self, x_raw, lengths, training, seed=0, save=True, packed=False):
+    def batch_meta(self, lengths):
+        """Device copies of the per-utterance frame counts and first rows (int32 lengths, int64 offsets).  encode() makes them itself
+        unless they are handed in: a CUDA-graph capture cannot contain the host-to-device copy."""
+        offs = [0]
+        for l in lengths[:-1]:
+            offs.append(offs[-1] + l)
+        return (torch.tensor(lengths, dtype=torch.int32).to(self.dev, non_blocking=True),
+                torch.tensor(offs, dtype=torch.int64).to(self.dev, non_blocking=True))
+
+    def encode(self, x_raw, lengths, training, seed=0, save=True, packed=False, meta=None):
         """x_raw: (n, 1600, 8) fp32 CUDA (already shifted); lengths: list[int] frames per utterance.
         Returns (x_enc (B*Lmax, D), ctx).  packed=True: a ragged batch is NOT padded to (B, Lmax) -- the
         transformer runs on the sum(lengths) rows decollate_tensor (data_utils.py:176-185) yields, utterance b at rows
@@ -539,15 +548,11 @@ class Engine:
         xlin = self._linear_fwd(a3, rows3, "w_raw_in", bias=self.P["w_raw_in.bias"])
         B, Lmax, total = len(lengths), max(lengths), sum(lengths)
         assert total <= rows3, "lengths exceed the available frames (data_utils.py:182)"
-        lens_dev = torch.tensor(lengths, dtype=torch.int32).to(self.dev, non_blocking=True)
+        lens_dev, offs_dev = meta if meta is not None else self.batch_meta(lengths)
         ragged = not (all(l == Lmax for l in lengths) and total == rows3)
         packed = bool(packed and ragged and min(lengths) >= 1)
         M, off = B * Lmax, None
         if ragged:
-            offs = [0]
-            for l in lengths[:-1]:
-                offs.append(offs[-1] + l)
-            offs_dev = torch.tensor(offs, dtype=torch.int64).to(self.dev, non_blocking=True)
             ctx.offs = offs_dev
             if packed:
                 x, M, off = xlin[:total], total, offs_dev       # the decollated rows as they are
@@ -671,11 +676,12 @@ class Engine:
     def dec_head(self, x_dec, M):
         return self._linear_fwd(x_dec, M, "w_out", bias=self.P["w_out.bias"], out_dtype=torch.float32, ldc=self.LDH)
 
-    def forward(self, x_raw, lengths, y=None, tgt_lens=None, training=True, seed=0, ctc=None, packed=None):
+    def forward(self, x_raw, lengths, y=None, tgt_lens=None, training=True, seed=0, ctc=None, packed=None, meta=None):
         """Model.forward_training (architecture.py:101-139).  Returns (enc_logits (B*L, 64) fp32, dec_logits (B*S, 64) fp32 | None, ctx).
         `ctc` = (targets (B, Smax) int64, target lengths int32, coefficient): start the CTC loss + gradient on the side stream as
         soon as the encoder logits exist, so that its serial alpha/beta recursion runs under the decoder forward."""
-        x_enc, ctx = self.encode(x_raw, lengths, training, seed, packed=self.cfg.get("packed", True) if packed is None else packed)
+        x_enc, ctx = self.encode(x_raw, lengths, training, seed, packed=self.cfg.get("packed", True) if packed is None else packed,
+                                 meta=meta)
         B, Lmax = ctx.B, ctx.Lmax
         ctx.enc_logits = self.enc_head(x_enc, ctx.M, ctx)
         ctx.dec_logits = None

@@ -474,5 +474,32 @@ def adamw(p, g, m, v, n, lr, beta1, beta2, eps, wd, step, p_bf16=None):
                               ptr(p_bf16), stream()), "sst_adamw")
 
 
+def adamw_dev(p, g, m, v, n, hyper, beta1, beta2, eps, wd, p_bf16=None):
+    """AdamW step whose (lr, 1 - beta1^t, sqrt(1 - beta2^t)) are read from the device float[3] `hyper` (CUDA-graph replays)."""
+    with _scope("adamw", bytes=(28.0 + (2.0 if p_bf16 is not None else 0.0)) * n):
+        check(lib().sst_adamw_dev(ptr(p), ptr(g), ptr(m), ptr(v), _i64(n), ptr(hyper), _f(beta1), _f(beta2), _f(eps), _f(wd),
+                                  ptr(p_bf16), stream()), "sst_adamw_dev")
+
+
+_salt_tensor = None
+
+
+def set_dropout_salt(t):
+    """Register (None: unregister) a device uint64 (int64 tensor of one element) that every dropout kernel adds to its seed."""
+    global _salt_tensor
+    if t is not None:
+        assert t.is_cuda and t.dtype == torch.int64 and t.numel() == 1
+    _salt_tensor = t                              # libsst.so keeps the raw pointer: keep the tensor alive
+    check(lib().sst_set_dropout_salt(ptr(t)), "sst_set_dropout_salt")
+
+
+def write_scalars(dst, fmt, *values):
+    """struct.pack(fmt, *values) into the device tensor `dst` as a kernel parameter (captured by value at the call)."""
+    import struct
+    blob = struct.pack(fmt, *values)
+    assert len(blob) % 4 == 0 and len(blob) <= 64 and dst.numel() * dst.element_size() >= len(blob)
+    check(lib().sst_write_scalars(ptr(dst), blob, len(blob), stream()), "sst_write_scalars")
+
+
 def launch_count():
     return int(lib().sst_launch_count())

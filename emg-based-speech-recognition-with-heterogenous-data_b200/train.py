@@ -391,7 +391,7 @@ class Trainer:
         Returns the float32[3] device tensor (loss, loss_dec, loss_enc).  `global_chunks`: chunks of this micro-step summed
         over all ranks when the caller knows it (AccumulationGate)."""
         import random
-        model, eng, flat = self.model, self.eng, self.flat
+        model = self.model
         model.train()
         self.schedule_lr(self.batch_idx)
         X = dev_batch['X']
@@ -399,11 +399,21 @@ class Trainer:
         r = random.randrange(8) if shift_r is None else shift_r       # architecture.py:105
         if r > 0:
             L.shift_left(X, X.shape[0], X.shape[1], X.shape[2], r)
+        losses = self._micro_step(dev_batch, will_step, self.seed * 1000003 + self.batch_idx, None, None)
+        if will_step:
+            self.flat.step_count += 1
+            model._weights_version += 1
+        self.batch_idx += 1
+        return losses
+
+    def _micro_step(self, dev_batch, will_step, seed, meta, hyper):
+        """The device work of one micro-batch after the input shift (recognition_model.py:90-118).  `hyper`: device float[3]
+        (lr, 1 - beta1^t, sqrt(1 - beta2^t)) of the optimizer step instead of by-value scalars -- the form a CUDA graph replays."""
+        eng, flat = self.eng, self.flat
         has_dec = eng.n_dec > 0
-        _, _, ctx = eng.forward(X, dev_batch['lengths'], dev_batch['tgt_in'] if has_dec else None,
-                                dev_batch['tgt_lens'] if has_dec else None, training=True,
-                                seed=self.seed * 1000003 + self.batch_idx,
-                                ctc=(dev_batch['ctc_tgt'], dev_batch['ctc_lens'], self.alpha if has_dec else 1.0))
+        _, _, ctx = eng.forward(dev_batch['X'], dev_batch['lengths'], dev_batch['tgt_in'] if has_dec else None,
+                                dev_batch['tgt_lens'] if has_dec else None, training=True, seed=seed,
+                                ctc=(dev_batch['ctc_tgt'], dev_batch['ctc_lens'], self.alpha if has_dec else 1.0), meta=meta)
         losses = eng.losses(ctx, dev_batch['ctc_tgt'], dev_batch['ctc_lens'], dev_batch['tgt_out'] if has_dec else None,
                             dev_batch['n_valid'], self.alpha, self.eps_ls)
         if self.sync is not None and will_step:
@@ -413,13 +423,102 @@ class Trainer:
         else:
             eng.backward(ctx, flat.G_all)
         if will_step:                                               # recognition_model.py:115-118
-            flat.step_count += 1
-            L.adamw(flat.p, flat.g, flat.m, flat.v, flat.numel, self.lr, 0.9, 0.999, 1e-8, self.wd, flat.step_count, flat.pb)
+            if hyper is None:
+                L.adamw(flat.p, flat.g, flat.m, flat.v, flat.numel, self.lr, 0.9, 0.999, 1e-8, self.wd, flat.step_count + 1, flat.pb)
+            else:
+                L.adamw_dev(flat.p, flat.g, flat.m, flat.v, flat.numel, hyper, 0.9, 0.999, 1e-8, self.wd, flat.pb)
             flat.zero_grad()
             eng.pack()
-            model._weights_version += 1
-        self.batch_idx += 1
         return losses
+
+    # ---- CUDA-graph replay of the micro-step -------------------------------------------------------
+    def step_graphed(self, dev_batch, shift_r=None, global_chunks=None, warm=2):
+        """step_device with the ~440 launches of a micro-step replayed as ONE CUDA graph: for small batches the step is bound by
+        the host's launch rate (16 us per launch through ctypes against 5-10 us of device time), not by the device.  A graph
+        freezes shapes and by-value arguments, so
+          * one graph per batch SIGNATURE (chunks, utterance lengths, target shapes, number of unpadded targets, step-or-accumulate),
+            captured after `warm` ordinary steps of that signature and kept (least recently used of 16 dropped) -- a stream of
+            equally shaped batches (fixed-length buckets, the BASELINE.json configs) replays, any other batch simply runs eagerly;
+          * what changes from step to step travels through device memory, written in front of the replay (sst_write_scalars): the
+            dropout salt every Philox-drawing kernel adds to its seed, the learning rate of the warm-up schedule
+            (recognition_model.py:57-64) and Adam's bias corrections (sst_adamw_dev);
+          * the inputs are copied into the graph's own buffers; the random input shift (architecture.py:104-108, one
+            random.randrange(8) per step, as ever) is applied to that copy by an ordinary launch.
+        Single process only: the bucketed all-reduce of GradSync stays on the eager path.  Returns the float32[3] device losses
+        (overwritten by the next replay of the same graph)."""
+        import random
+        if self.sync is not None or self.dev.type != "cuda":
+            return self.step_device(dev_batch, shift_r, global_chunks)
+        X = dev_batch['X']
+        has_dec = self.eng.n_dec > 0
+        will_step_peek = self.gate.sum_batch_size + (int(global_chunks) if global_chunks is not None else int(X.shape[0])) >= self.gate.batch_size_grad
+        key = (tuple(X.shape), tuple(dev_batch['lengths']), tuple(dev_batch['tgt_in'].shape) if has_dec else None,
+               tuple(dev_batch['ctc_tgt'].shape), int(dev_batch['n_valid']), bool(will_step_peek), bool(self.eng.cfg.get("packed", True)))
+        st = self._graph_state()
+        ent = st["graphs"].get(key)
+        if ent is not None and ent["graph"] is not None and ent["plan"] is not getattr(self.eng, "_pack_plan", None):
+            ent = st["graphs"][key] = dict(seen=warm, graph=None)      # the packed GEMM operands moved: the recorded pointers are stale
+        if ent is None or ent["graph"] is None:
+            if ent is None:
+                ent = st["graphs"][key] = dict(seen=0, graph=None)
+            ent["seen"] += 1
+            if ent["seen"] <= warm:
+                return self.step_device(dev_batch, shift_r, global_chunks)      # also warms every lazily initialised piece of the path
+            self._capture(st, key, ent, dev_batch, will_step_peek)
+        ent["tick"] = st["tick"] = st["tick"] + 1
+        # ---- replay -------------------------------------------------------------------------------------------------------
+        self.model.train()
+        self.schedule_lr(self.batch_idx)
+        will_step = self.gate.add(X.shape[0], global_chunks)
+        assert will_step == will_step_peek
+        s = ent["static"]
+        for k in ("X", "tgt_in", "tgt_out", "tgt_lens", "ctc_tgt", "ctc_lens"):
+            if k in s and torch.is_tensor(s[k]):
+                s[k].copy_(dev_batch[k], non_blocking=True)
+        r = random.randrange(8) if shift_r is None else shift_r
+        if r > 0:
+            L.shift_left(s["X"], X.shape[0], X.shape[1], X.shape[2], r)
+        t = self.flat.step_count + 1
+        L.write_scalars(st["scalars"], "<qfff", (self.seed * 1000003 + self.batch_idx) * 0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF,
+                        float(self.lr), float(1.0 - 0.9 ** t), float((1.0 - 0.999 ** t) ** 0.5))
+        ent["graph"].replay()
+        if will_step:
+            self.flat.step_count += 1
+            self.model._weights_version += 1
+            self.eng._packed_version = None
+        self.batch_idx += 1
+        return ent["losses"]
+
+    def _graph_state(self):
+        st = getattr(self, "_graphs", None)
+        if st is None:
+            scalars = torch.zeros(8, dtype=torch.int32, device=self.dev)          # [salt (8 bytes) | lr, bc1, sqrt bc2 | pad]
+            st = self._graphs = dict(graphs={}, tick=0, scalars=scalars, salt=scalars[:2].view(torch.int64),
+                                     hyper=scalars[2:5].view(torch.float32), pool=None, stream=torch.cuda.Stream(device=self.dev))
+        return st
+
+    def _capture(self, st, key, ent, dev_batch, will_step):
+        live = [k for k, e in st["graphs"].items() if e["graph"] is not None]
+        if len(live) >= 16:                                                      # drop the least recently replayed graph
+            old = min(live, key=lambda k: st["graphs"][k]["tick"])
+            del st["graphs"][old]
+        static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in dev_batch.items()}
+        meta = self.eng.batch_meta(dev_batch['lengths'])
+        L.write_scalars(st["scalars"], "<qfff", 0, float(self.lr), 1.0, 1.0)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        L.set_dropout_salt(st["salt"])
+        # gradients accumulate in flat.g: the capture pass must not be counted -- it is not executed, only recorded
+        try:
+            with torch.cuda.graph(g, pool=st["pool"], stream=st["stream"]):
+                losses = self._micro_step(static, will_step, 0x5353, meta, st["hyper"])
+        finally:
+            L.set_dropout_salt(None)
+        if st["pool"] is None:
+            st["pool"] = g.pool()
+        # everything the recorded launches point at and the engine may replace later stays referenced by the entry
+        ent.update(graph=g, static=static, meta=meta, losses=losses, tick=st["tick"], plan=getattr(self.eng, "_pack_plan", None),
+                   ws=L._attn_ws.get(self.dev), pk=dict(self.eng.pk))
 
     def step(self, example):
         """Public entry: collate_raw dict on the host -> losses; one async D2H of float[3] replaces the three .item() calls."""

@@ -268,6 +268,17 @@ typedef struct SstPermuteItem {
 } SstPermuteItem;
 int sst_permute3_plan(SstPermuteItem* items_host, int n_items, int* total_blocks);
 int sst_permute3_cast_batch(const SstPermuteItem* items_dev, int n_items, int total_blocks, void* stream);
+/*  sst_set_dropout_salt : register (NULL: unregister) a device uint64 every dropout-drawing kernel launched afterwards adds to its
+ *                         seed.  Seeds, the learning rate and Adam's bias corrections cross this ABI by value, which a captured
+ *                         CUDA graph replays unchanged: with a salt registered, sst_write_scalars in front
+ *                         of each replay (salt) and sst_adamw_dev (lr, 1 - beta1^t, sqrt(1 - beta2^t) from a device float[3])
+ *                         make a replayed training step draw fresh masks and take the scheduled step.  Process-wide.
+ *  sst_write_scalars    : nbytes (4..64, multiple of 4) from HOST memory to device memory as a kernel parameter -- captured by
+ *                         value when the call returns, ordered on `stream` like any launch. */
+int sst_set_dropout_salt(const uint64_t* salt_dev);
+int sst_write_scalars(void* dst_dev, const void* src_host, int nbytes, void* stream);
+int sst_adamw_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper_dev, float beta1, float beta2,
+                  float eps, float wd, void* p_bf16, void* stream);
 int sst_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, float wd,
               int64_t step, void* p_bf16, void* stream);
 

@@ -177,3 +177,70 @@ def test_pipelined_run_gives_the_stepwise_losses():
     assert t2.batch_idx == 4 and t2.flat.step_count == 4
     scale = float(t1.flat.p.abs().max())
     assert float((t1.flat.p - t2.flat.p).abs().max()) < 1e-4 * scale
+
+
+def _graph_model(cfg, sd, dtype, dropout):
+    import sst_b200  # noqa: F401
+    from sst_b200 import architecture as A
+    A.configure(model_size=768, feed_forward_layer_size=3072, num_layers_encoder=cfg["n_enc"], num_layers_decoder=cfg["n_dec"],
+                n_heads_encoder=8, n_heads_decoder=8, relative_distance=cfg["rel_dist"], dropout_model=dropout, dropout_pos_emb=dropout,
+                sst_dtype=dtype)
+    model = A.Model(112, 44, 43, DEV).to(DEV)
+    model.load_state_dict(sd)
+    return model
+
+
+@pytest.mark.parametrize("accumulate_every", [1, 2])
+def test_graphed_steps_equal_eager_steps(accumulate_every):
+    """Trainer.step_graphed replays the micro-step as one CUDA graph (per batch signature, captured after two eager
+    steps).  Without dropout the graphed loop must BE the eager loop: same losses, and the same parameters after 8 steps through the
+    warm-up learning-rate schedule and Adam's bias corrections (those reach the replay through device memory) -- fp32 mode, compared
+    at 2e-5 (the weight-gradient GEMMs accumulate their split-K partials with atomics, in a different order run to run)."""
+    from sst_b200.train import Trainer
+    cfg = O.make_cfg(n_enc=1, n_dec=1, rel_dist=100, alpha=0.2)
+    sd0 = O.synthetic_state_dict(cfg, 7)
+    batches = [O.synthetic_batch(seed=40 + (k % 2), ragged=[70, 100, 30], tgt_lens=[9, 14, 5]) for k in range(8)]
+    out = {}
+    for mode in ("eager", "graphed"):
+        model = _graph_model(cfg, sd0, "fp32", 0.0)
+        tr = Trainer(model, alpha_loss=cfg["alpha"], batch_size_grad=accumulate_every, learning_rate_warmup=1500)
+        losses = []
+        for batch in batches:
+            dev = tr.to_device(tr.prepare(batch))
+            ls = tr.step_device(dev, shift_r=3) if mode == "eager" else tr.step_graphed(dev, shift_r=3)
+            tr.fetch_losses(ls)
+            losses.append(tr.wait_losses())
+        out[mode] = (losses, {n: p.detach().clone() for n, p in model.named_parameters()}, tr)
+    tr = out["graphed"][2]
+    live = [e for e in tr._graphs["graphs"].values() if e["graph"] is not None]
+    assert len(live) == (1 if accumulate_every == 1 else 2), "one graph per signature (accumulate / step) expected, got %d" % len(live)
+    assert tr.flat.step_count == out["eager"][2].flat.step_count == 8 // accumulate_every and tr.batch_idx == 8
+    for a, b in zip(out["eager"][0], out["graphed"][0]):
+        for x, y in zip(a, b):
+            assert abs(x - y) <= 2e-5 * abs(x), (out["eager"][0], out["graphed"][0])
+    for n, p in out["eager"][1].items():
+        upd = (p - sd0[n].to(DEV)).double()
+        d = (out["graphed"][1][n].double() - p.double()).abs().max()
+        assert float(d) <= 2e-2 * float(upd.abs().max()) + 1e-9, (n, float(d), float(upd.abs().max()))
+
+
+def test_graphed_replays_draw_fresh_dropout_masks():
+    """Dropout seeds cross the C ABI by value, so a replayed graph would repeat its masks: every Philox-drawing kernel adds the
+    registered device salt (sst_set_dropout_salt), rewritten in front of each replay.  The same batch replayed on frozen weights
+    (accumulation only, no optimizer step) must give DIFFERENT losses each time, all within the spread eager steps show."""
+    from sst_b200.train import Trainer
+    cfg = O.make_cfg(n_enc=1, n_dec=1, rel_dist=100, alpha=0.2)
+    sd0 = O.synthetic_state_dict(cfg, 9)
+    batch = O.synthetic_batch(seed=77, ragged=[70, 100, 30], tgt_lens=[9, 14, 5])
+    model = _graph_model(cfg, sd0, "bf16", 0.2)
+    tr = Trainer(model, alpha_loss=0.2, batch_size_grad=10 ** 9)
+    vals = []
+    for k in range(8):
+        dev = tr.to_device(tr.prepare(batch))
+        tr.fetch_losses(tr.step_graphed(dev, shift_r=0))
+        vals.append(tr.wait_losses()[0])
+    eager, replayed = vals[:2], vals[2:]
+    assert any(e["graph"] is not None for e in tr._graphs["graphs"].values())
+    assert len(set(round(v, 5) for v in replayed)) == len(replayed), replayed
+    mean = sum(vals) / len(vals)
+    assert all(abs(v - mean) < 0.25 * abs(mean) for v in vals), vals
