@@ -114,7 +114,14 @@ colsum_kernel(const T* __restrict__ x, long rows, int C, long ld, float* __restr
   reduce_over_ty(s, fbuf);
   if (threadIdx.y == 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) if (c + j < C) atomicAdd(out + c + j, s[j]);
+    for (int j = 0; j < 8; ++j) if (c + j >= C) s[j] = 0.f;
+    if (c + 8 <= C && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      red_add4(out + c, s[0], s[1], s[2], s[3]);
+      red_add4(out + c + 4, s[4], s[5], s[6], s[7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (c + j < C) atomicAdd(out + c + j, s[j]);
+    }
   }
 }
 

@@ -125,7 +125,9 @@ ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ r, T* __restrict__ 
 }
 
 // ds = rstd * (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat));  dr = ds * keep/(1-p);
-// dgamma += sum_rows dy*xhat, dbeta += sum_rows dy  (per-lane register partials -> smem -> one atomic per block/column)
+// dgamma += sum_rows dy*xhat, dbeta += sum_rows dy: per-lane register partials; at the end every warp parks its 2*D partials in the
+// (by then idle) ring, the block adds them up and issues one 16-byte reduction per four columns (no shared-memory atomics: eight
+// warps adding into the same 1536 shared words was most of the kernel's ~9 us floor on decoder-sized inputs)
 template <typename T, int NV, bool EXACT>
 __global__ void __launch_bounds__(256, 2)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ s, const float* __restrict__ mean_in,
@@ -136,14 +138,11 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ s, const float* __
   pdl_wait();
   pdl_trigger();
   if (dr != nullptr) seed = salted(seed, salt);
-  float* red = reinterpret_cast<float*>(ln_smem);
   const int lane = threadIdx.x & 31;
   const int warp = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
   const int nwarps = (int)(gridDim.x * (blockDim.x >> 5));
   uint32_t plane;
-  const uint32_t ring = ln_ring<T>(ln_smem + (size_t)2 * D * sizeof(float), plane);
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
+  const uint32_t ring = ln_ring<T>(ln_smem, plane);
   float ag[NV][8], ab[NV][8], gm[NV][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -208,18 +207,32 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ s, const float* __
       }
     }
       });
+  cp_async_wait<0>();
+  __syncthreads();                                   // every warp has left the ring: it now holds [warp][dgamma D | dbeta D] partials
+  float* part = reinterpret_cast<float*>(ln_smem);
+  const int nw = (int)(blockDim.x >> 5);
+  float* mine = part + (size_t)(threadIdx.x >> 5) * 2 * D;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 8;
     if (EXACT || c < D) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { atomicAdd(&red[c + j], ag[i][j]); atomicAdd(&red[D + c + j], ab[i][j]); }
+      *reinterpret_cast<float4*>(mine + c) = make_float4(ag[i][0], ag[i][1], ag[i][2], ag[i][3]);
+      *reinterpret_cast<float4*>(mine + c + 4) = make_float4(ag[i][4], ag[i][5], ag[i][6], ag[i][7]);
+      *reinterpret_cast<float4*>(mine + D + c) = make_float4(ab[i][0], ab[i][1], ab[i][2], ab[i][3]);
+      *reinterpret_cast<float4*>(mine + D + c + 4) = make_float4(ab[i][4], ab[i][5], ab[i][6], ab[i][7]);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    atomicAdd(dgamma + i, red[i]);
-    atomicAdd(dbeta + i, red[D + i]);
+  const bool vec = ((reinterpret_cast<uintptr_t>(dgamma) | reinterpret_cast<uintptr_t>(dbeta)) & 15) == 0;
+  for (int i = threadIdx.x * 4; i < 2 * D; i += blockDim.x * 4) {      // D % 8 == 0: a group of four never straddles dgamma | dbeta
+    float4 s = *reinterpret_cast<const float4*>(part + i);
+    for (int w = 1; w < nw; ++w) {
+      const float4 t = *reinterpret_cast<const float4*>(part + (size_t)w * 2 * D + i);
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    float* dst = i < D ? dgamma + i : dbeta + (i - D);
+    if (vec) red_add4(dst, s.x, s.y, s.z, s.w);                         // four columns per reduction (sst_common.cuh)
+    else { atomicAdd(dst, s.x); atomicAdd(dst + 1, s.y); atomicAdd(dst + 2, s.z); atomicAdd(dst + 3, s.w); }
   }
 }
 
@@ -291,7 +304,8 @@ int sst_layernorm_bwd(int dtype, int64_t rows, int D, const void* dy, const void
 #define SST_LN_BWD(T_, NV_, EX_)                                                                                             \
   do {                                                                                                                       \
     constexpr int TH = LnCfg<EX_>::THREADS;                                                                                  \
-    const size_t smem = (size_t)2 * D * sizeof(float) + (size_t)LnCfg<EX_>::STAGES * 2 * NV_ * TH * ColSlot<T_>::BYTES;        \
+    size_t smem = (size_t)LnCfg<EX_>::STAGES * 2 * NV_ * TH * ColSlot<T_>::BYTES;                                           \
+    if (smem < (size_t)(TH / 32) * 2 * D * sizeof(float)) smem = (size_t)(TH / 32) * 2 * D * sizeof(float);   /* tail partials */ \
     static bool attr = false;                                                                                                \
     if (!attr) {                                                                                                             \
       cudaError_t e = cudaFuncSetAttribute(ln_bwd_kernel<T_, NV_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \

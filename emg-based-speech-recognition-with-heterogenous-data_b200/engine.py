@@ -96,17 +96,18 @@ class Engine:
         self.pk[key + ".T"] = self._cast2d(self.pk[key] if self.pk[key] is not w2d and sh is not None and self.dtype == torch.bfloat16
                                            else w2d, transpose=True)
 
-    def _pack_heads_in(self, key, ws):
-        """ws: list of (H, D, dh) per-head projection weights -> W (len*H*dh, D) and its transpose."""
+    def _pack_heads_in(self, key, ws, W=None, WT=None):
+        """ws: list of (H, D, dh) per-head projection weights -> W (len*H*dh, D) and its transpose (D, len*H*dh); W / WT may be
+        views (row block / column block) of a wider operand several layers share."""
         H, D, dh = ws[0].shape
         HD = H * dh
         n = len(ws)
-        W = self.empty(n * HD, D)
+        W = self.empty(n * HD, D) if W is None else W
         for s, w in enumerate(ws):
             L.permute3_cast(w, W[s * HD:], (H, dh, D), (D * dh, 1, dh), (dh * D, D, 1))
-        WT = self.empty(D, n * HD)             # built from the masters too (no read of W: one unordered launch replays this)
+        WT = self.empty(D, n * HD) if WT is None else WT     # built from the masters too (no read of W: one unordered launch replays this)
         for s, w in enumerate(ws):
-            L.permute3_cast(w, WT[:, s * HD:], (H, D, dh), (D * dh, dh, 1), (dh, n * HD, 1))
+            L.permute3_cast(w, WT[:, s * HD:], (H, D, dh), (D * dh, dh, 1), (dh, WT.stride(0), 1))
         self.pk[key] = W
         self.pk[key + ".T"] = WT
 
@@ -176,6 +177,12 @@ class Engine:
             self.pk[a + ".E"] = self._cast2d(E.view(-1, self.dh))
             self._pack_linear(p + ".linear1", P[p + ".linear1.weight"], p + ".linear1.weight")
             self._pack_linear(p + ".linear2", P[p + ".linear2.weight"], p + ".linear2.weight")
+        # cross-attention key / value projections of ALL decoder layers side by side: the encoder memory is projected by one GEMM
+        # (N = n_dec * 2D) and its gradient collected by one (K = n_dec * 2D) instead of n_dec short ones that each re-read and
+        # re-write the (frames, D) accumulator; a layer's own operand is a row / column block of these
+        if self.n_dec > 0:
+            kv_all = self.empty(self.n_dec * 2 * D, D)
+            kv_all_T = self.empty(D, self.n_dec * 2 * D)
         for i in range(self.n_dec):
             p = "transformerDecoder.layers.%d" % i
             a = p + ".self_attn"
@@ -183,10 +190,13 @@ class Engine:
             self._pack_linear(a + ".o", P[a + ".w_o"].view(D, D), a + ".w_o")
             m = p + ".multihead_attn"
             self._pack_heads_in(m + ".q", [P[m + ".w_q"]])
-            self._pack_heads_in(m + ".kv", [P[m + ".w_k"], P[m + ".w_v"]])
+            self._pack_heads_in(m + ".kv", [P[m + ".w_k"], P[m + ".w_v"]], W=kv_all[i * 2 * D:(i + 1) * 2 * D],
+                                WT=kv_all_T[:, i * 2 * D:(i + 1) * 2 * D])
             self._pack_linear(m + ".o", P[m + ".w_o"].view(D, D), m + ".w_o")
             self._pack_linear(p + ".linear1", P[p + ".linear1.weight"], p + ".linear1.weight")
             self._pack_linear(p + ".linear2", P[p + ".linear2.weight"], p + ".linear2.weight")
+        if self.n_dec > 0:
+            self.pk["dec.kv_all"], self.pk["dec.kv_all.T"] = kv_all, kv_all_T
         self._pack_linear("w_aux", P["w_aux.weight"], "w_aux.weight")
         self._pack_linear("w_out", P["w_out.weight"], "w_out.weight")
 
@@ -463,7 +473,7 @@ class Engine:
         kv = cross_kv if cross_kv is not None else self._linear_fwd(mem, Mm, m + ".kv")
         o2 = self.empty(M, D)
         lse2 = self.empty(2 * B * self.Hd * S, dtype=torch.float32)
-        ad2 = self._attn_desc(B, S, Lm, D, 2 * D, 2 * D, False, False, 0, p, seeds(), dec=True, k_off=mem_off, k_rows=Mm)
+        ad2 = self._attn_desc(B, S, Lm, D, kv.stride(0), kv.stride(0), False, False, 0, p, seeds(), dec=True, k_off=mem_off, k_rows=Mm)
         L.attn_fwd(ad2, q, kv, kv[:, D:], None, None, mem_lens, o2, lse2)
         y2 = self._linear_fwd(o2, M, m + ".o.T")
         t2, ln2 = self._ln_fwd(t1, y2, M, pfx + ".norm2", p, seeds())
@@ -475,7 +485,9 @@ class Engine:
                 h=h, pre=pre, s_ffn=s_ffn, ln3=ln3, p=p)
         return t3, c
 
-    def _dec_layer_bwd(self, c, dt3, mem, dmem, B, S, Lm, tgt_lens, mem_lens, i, G, Mm=None):
+    def _dec_layer_bwd(self, c, dt3, mem, dmem, B, S, Lm, tgt_lens, mem_lens, i, G, Mm=None, dkv=None):
+        """dkv: this layer's (Mm, 2D) block of the shared key / value gradient buffer -- the caller then folds all layers into
+        the memory gradient with ONE GEMM (Engine.backward); without it the layer adds its own share to dmem."""
         D, M = self.D, B * S
         Mm = Mm if Mm is not None else B * Lm
         pfx = "transformerDecoder.layers.%d" % i
@@ -489,13 +501,18 @@ class Engine:
         dO2 = self.empty(M, D)
         self.gemm(dy2, self.pk[m + ".o"], dO2, M, D, D, D, D, D)
         dq = self.empty(M, D)
-        dkv = self.empty(Mm, 2 * D)
+        own = dkv is None
+        if own:
+            dkv = self.empty(Mm, c.kv.stride(0))[:, :2 * D]          # dk / dv are written with the pitches of k / v
+        assert dkv.stride(0) == c.kv.stride(0)
         delta = self.empty(B * self.Hd * S, dtype=torch.float32)
         L.attn_bwd(c.ad2, c.q, c.kv, c.kv[:, D:], None, None, mem_lens, c.o2, c.lse2, dO2, dq, dkv, dkv[:, D:], delta)
         self._qkv_wgrad(dq, c.t1, M, [m + ".w_q"], G, dec=True)
         self.gemm(dq, self.pk[m + ".q.T"], ds2, M, D, D, D, D, D, epilogue=L.EPI_ACCUM)
         self._qkv_wgrad(dkv, mem, Mm, [m + ".w_k", m + ".w_v"], G, dec=True)
-        self.gemm(dkv, self.pk[m + ".kv.T"], dmem, Mm, D, 2 * D, 2 * D, 2 * D, D, epilogue=L.EPI_ACCUM)
+        if own:
+            WT = self.pk[m + ".kv.T"]
+            self.gemm(dkv, WT, dmem, Mm, D, 2 * D, dkv.stride(0), WT.stride(0), D, epilogue=L.EPI_ACCUM)
         ds1, dy1 = self._ln_bwd(ds2, c.ln1, M, pfx + ".norm1", G)
         # self attention
         self.gemm(c.o1, dy1, G[a + ".w_o"], D, D, M, D, D, D, layout=L.GEMM_NT_MN, epilogue=L.EPI_ACCUM)
@@ -540,7 +557,8 @@ class Engine:
         ctx = Ctx(n=n, blocks=[], layers=[], training=training)
         a, T = x_raw, T0
         for i in range(3):
-            a, c = self._resblock_fwd(i, a, n, T, training, last=(i == 2))
+            with L.nvtx_range("conv%d.fwd" % i):
+                a, c = self._resblock_fwd(i, a, n, T, training, last=(i == 2))
             T //= 2
             ctx.blocks.append(c)
         rows3 = n * T
@@ -563,7 +581,8 @@ class Engine:
             x = xlin
         ctx.update(a3=a3, rows3=rows3, B=B, Lmax=Lmax, lens=lens_dev, ragged=ragged, lengths=list(lengths), packed=packed, M=M, off=off)
         for i in range(self.n_enc):
-            x, c = self._enc_layer_fwd(x, B, Lmax, lens_dev, i, training, seeds, M=M, off=off)
+            with L.nvtx_range("enc%d.fwd" % i):
+                x, c = self._enc_layer_fwd(x, B, Lmax, lens_dev, i, training, seeds, M=M, off=off)
             ctx.layers.append(c)
         ctx.x_enc = x
         ctx.seeds = seeds
@@ -661,9 +680,14 @@ class Engine:
         s_emb = seeds()
         L.embed_posenc_fwd(self.dt, y, self.P["embedding_tgt.weight"], self.Bf["pos_decoder.pe"], t, B, S, self.D, p_pos, s_emb)
         layers = []
+        if cross is None and self.n_dec > 0:
+            Mm_ = Mm if Mm is not None else B * Lm
+            kv_all = self._linear_fwd(mem, Mm_, "dec.kv_all")            # (Mm, n_dec * 2D): every layer's keys / values in one GEMM
+            cross = [kv_all[:, i * 2 * self.D:(i + 1) * 2 * self.D] for i in range(self.n_dec)]
         for i in range(self.n_dec):
-            t, c = self._dec_layer_fwd(t, mem, B, S, Lm, tgt_lens, mem_lens, i, training, seeds, tgt_pad, Mm=Mm, mem_off=mem_off,
-                                       cross_kv=cross[i] if cross is not None else None)
+            with L.nvtx_range("dec%d.fwd" % i):
+                t, c = self._dec_layer_fwd(t, mem, B, S, Lm, tgt_lens, mem_lens, i, training, seeds, tgt_pad, Mm=Mm, mem_off=mem_off,
+                                           cross_kv=cross[i] if cross is not None else None)
             layers.append(c)
         if ctx is not None:
             ctx.update(y=y, S=S, tgt_lens=tgt_lens, dec_layers=layers, p_pos=p_pos, s_emb=s_emb, x_dec=t)
@@ -763,13 +787,21 @@ class Engine:
             Md = B * S
             dt_ = self._linear_bwd(d_dec_logits, ctx.x_dec, Md, "w_out", G, "w_out.weight", "w_out.bias")
             on_stage("heads")
+            shared = self.n_dec > 0 and ctx.dec_layers[0].kv.stride(0) == self.n_dec * 2 * D
+            dkv_all = self.empty(M, self.n_dec * 2 * D) if shared else None
             for i in reversed(range(self.n_dec)):
-                dt_ = self._dec_layer_bwd(ctx.dec_layers[i], dt_, ctx.x_enc, dx, B, S, Lx, ctx.tgt_lens, ctx.lens, i, G, Mm=M)
+                with L.nvtx_range("dec%d.bwd" % i):
+                    dt_ = self._dec_layer_bwd(ctx.dec_layers[i], dt_, ctx.x_enc, dx, B, S, Lx, ctx.tgt_lens, ctx.lens, i, G, Mm=M,
+                                              dkv=dkv_all[:, i * 2 * D:(i + 1) * 2 * D] if shared else None)
                 on_stage("dec%d" % i)
+            if shared:       # gradient of the encoder memory through every layer's key / value projection: one K = n_dec * 2D GEMM
+                WT = self.pk["dec.kv_all.T"]
+                self.gemm(dkv_all, WT, dx, M, D, self.n_dec * 2 * D, dkv_all.stride(0), WT.stride(0), D, epilogue=L.EPI_ACCUM)
             L.embed_bwd(self.dt, ctx.y, dt_, G["embedding_tgt.weight"], B, S, D, PAD, ctx.p_pos, ctx.s_emb)
         on_stage("embed")
         for i in reversed(range(self.n_enc)):
-            dx = self._enc_layer_bwd(ctx.layers[i], dx, B, Lx, ctx.lens, i, G, M=M)
+            with L.nvtx_range("enc%d.bwd" % i):
+                dx = self._enc_layer_bwd(ctx.layers[i], dx, B, Lx, ctx.lens, i, G, M=M)
             on_stage("enc%d" % i)
         if ctx.packed:
             # dx already is the gradient of w_raw_in's first sum(lengths) output rows; the rest of the last chunk (the 42-filled
@@ -785,5 +817,6 @@ class Engine:
             da = self._linear_bwd(dxlin, ctx.a3, ctx.rows3, "w_raw_in", G, "w_raw_in.weight", "w_raw_in.bias")
         on_stage("w_raw_in")
         for c in reversed(ctx.blocks):
-            da = self._resblock_bwd(c, da, G)
+            with L.nvtx_range("conv%d.bwd" % c.i):
+                da = self._resblock_bwd(c, da, G)
             on_stage("conv%d" % c.i)

@@ -82,6 +82,24 @@ class Profiler:
 
 
 _profiler = None
+_NVTX = os.environ.get("SST_NVTX", "0") not in ("", "0")      # SST_NVTX=1: an NVTX range around every C-ABI launch (kernel family
+                                                               # name) and every engine stage (nvtx_range), for nsys / ncu --nvtx
+
+
+class nvtx_range:
+    """`with nvtx_range("enc3.fwd"):` -- a no-op unless SST_NVTX=1 (the tracing the reference lacks)."""
+    __slots__ = ("name",)
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
 
 
 class _scope:
@@ -91,11 +109,15 @@ class _scope:
         self.kind, self.flops, self.bytes, self.tag = kind, flops, bytes, tag
 
     def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.kind)
         if _profiler is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e0.record()
 
     def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
         if _profiler is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
