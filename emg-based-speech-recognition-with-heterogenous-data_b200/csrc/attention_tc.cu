@@ -232,7 +232,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
       float U[SP::WIN_LD];
       const bool skip = block_out_of_band<NSPLIT>(p, i0 + 32 * q, t * BN + CW * hf);
-      float* red = sred + (gt & 1) * NSPLIT * 128;
+      const uint32_t red = ptx::smem_u32(sred) + (uint32_t)((gt & 1) * NSPLIT * 128 + li) * 4;      // this row's slot of group 0
       float mt = NEG_BIG;
       if (!skip) {
         uint32_t mbits;
@@ -246,10 +246,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_sfree);    // the issuer may overwrite S / PB with the next tile
 
-      red[hf * 128 + li] = mt;
+      ptx::st_shared_f32(red + hf * 512, mt);
       ptx::named_bar_sync(1 + q, 32 * NSPLIT);       // the NSPLIT warps that share this lane quarter
 #pragma unroll
-      for (int g = 0; g < NSPLIT; ++g) mt = fmaxf(mt, red[g * 128 + li]);
+      for (int g = 0; g < NSPLIT; ++g) mt = fmaxf(mt, ptx::ld_shared_f32(red + g * 512));
       const float m_new = fmaxf(m_run, mt);
       const float alpha = __expf(m_run - m_new);
       float sum = 0.f;
@@ -297,12 +297,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // row sum = sum of the column groups' shares (third exchange buffer: the next item's first tile reuses the per-tile ones
     // while slower warps of this quarter may still be reading here)
     const int kl = t_hi - t_lo;
-    float* red = sred + 2 * NSPLIT * 128;
-    red[hf * 128 + li] = l_run;
+    const uint32_t red = ptx::smem_u32(sred) + (uint32_t)(2 * NSPLIT * 128 + li) * 4;
+    ptx::st_shared_f32(red + hf * 512, l_run);
     ptx::named_bar_sync(1 + q, 32 * NSPLIT);
     float l_tot = 0.f;
 #pragma unroll
-    for (int g = 0; g < NSPLIT; ++g) l_tot += red[g * 128 + li];
+    for (int g = 0; g < NSPLIT; ++g) l_tot += ptx::ld_shared_f32(red + g * 512);
 
     const bool valid = i < q_rows(p, b);
     o_pending = true; o_valid = valid; o_scale = 1.f / l_tot;
