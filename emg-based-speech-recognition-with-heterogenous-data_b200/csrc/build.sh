@@ -17,5 +17,5 @@ for f in *.cu; do
   fi
 done
 for p in $pids; do wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT $objs -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT $objs -lcudart -ldl
 echo "built $(realpath $OUT)"

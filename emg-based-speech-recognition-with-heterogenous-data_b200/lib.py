@@ -523,5 +523,48 @@ def write_scalars(dst, fmt, *values):
     check(lib().sst_write_scalars(ptr(dst), blob, len(blob), stream()), "sst_write_scalars")
 
 
+def nccl_lib_path():
+    """The libnccl.so.2 PyTorch itself uses (nvidia-nccl wheel), so that sst_comm_* and torch.distributed share one NCCL."""
+    env = os.environ.get("SST_NCCL_LIB")
+    if env:
+        return env
+    try:
+        import nvidia.nccl as _n
+        for base in list(getattr(_n, "__path__", [])) + ([os.path.dirname(_n.__file__)] if getattr(_n, "__file__", None) else []):
+            p = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.isfile(p):
+                return p
+    except Exception:
+        pass
+    return "libnccl.so.2"
+
+
+def comm_nccl_version():
+    return int(lib().sst_comm_nccl_version(nccl_lib_path().encode()))
+
+
+class Comm:
+    """sst_comm_* communicator (include/sst.h): `exchange(obj)` must return rank 0's `obj` on every rank (any host channel)."""
+
+    def __init__(self, rank, world, exchange):
+        path = nccl_lib_path().encode()
+        uid = C.create_string_buffer(128)
+        if rank == 0:
+            check(lib().sst_comm_unique_id(uid, path), "sst_comm_unique_id")
+        blob = exchange(bytes(uid.raw) if rank == 0 else None)
+        self.handle = C.c_void_p()
+        check(lib().sst_comm_init(blob, rank, world, path, C.byref(self.handle)), "sst_comm_init")
+        self.rank, self.world = rank, world
+
+    def allreduce(self, t, average=True):
+        """In place over the ranks, enqueued on the current stream."""
+        check(lib().sst_comm_allreduce_bucket(self.handle, ptr(t), _i64(t.numel()), dt(t), int(average), stream()), "sst_comm_allreduce_bucket")
+
+    def destroy(self):
+        if self.handle:
+            check(lib().sst_comm_destroy(self.handle), "sst_comm_destroy")
+            self.handle = C.c_void_p()
+
+
 def launch_count():
     return int(lib().sst_launch_count())

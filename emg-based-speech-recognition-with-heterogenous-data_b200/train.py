@@ -164,13 +164,26 @@ class AccumulationGate:
 
 
 class GradSync:
-    def __init__(self, flat, n_enc, n_dec, bucket_bytes=128 << 20, group=None):
+    def __init__(self, flat, n_enc, n_dec, bucket_bytes=128 << 20, group=None, native_comm=None):
+        """native_comm: reduce the buckets through libsst.so's own communicator (sst_comm_*, include/sst.h) instead of
+        torch.distributed.all_reduce; default from the environment variable SST_COMM=native.  torch.distributed stays the host
+        channel (the unique id travels through it) and the fallback."""
+        import os
         import torch.distributed as dist
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.flat = flat
         self.backend = dist.get_backend(group) if dist.is_initialized() else None
+        if native_comm is None:
+            native_comm = os.environ.get("SST_COMM", "") == "native"
+        self.comm = None
+        if native_comm and self.world > 1 and flat.g.is_cuda:
+            def exchange(blob):
+                box = [blob]
+                dist.broadcast_object_list(box, src=0, group=group)
+                return box[0]
+            self.comm = L.Comm(dist.get_rank(group), self.world, exchange)
         # buckets = contiguous ranges of the flat gradient buffer, closed at stage boundaries once they reach bucket_bytes
         self.buckets = []            # (start, end, stage after which the bucket is complete)
         start, cur_stage = 0, None
@@ -235,7 +248,9 @@ class GradSync:
             self.stream.wait_event(ev)
             with torch.cuda.stream(self.stream):
                 e0 = self._event(self.stream) if self.timeline is not None else None
-                if self.backend == "nccl":
+                if self.comm is not None:
+                    self.comm.allreduce(t, average=True)
+                elif self.backend == "nccl":
                     dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
                 else:
                     dist.all_reduce(t, group=self.group)

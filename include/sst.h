@@ -30,6 +30,7 @@ extern "C" {
 #define SST_E_ARCH (-2)     /* device is not sm_100 */
 #define SST_E_LAUNCH (-3)   /* CUDA launch / runtime failure */
 #define SST_E_UNSUPPORTED (-4)
+#define SST_E_COMM (-5)     /* NCCL could not be loaded / a collective failed */
 
 const char* sst_version(void);
 const char* sst_last_error(void);
@@ -268,6 +269,22 @@ typedef struct SstPermuteItem {
 } SstPermuteItem;
 int sst_permute3_plan(SstPermuteItem* items_host, int n_items, int* total_blocks);
 int sst_permute3_cast_batch(const SstPermuteItem* items_dev, int n_items, int total_blocks, void* stream);
+/* ------------------------------------------------------------------------------------------------------------
+ * Gradient exchange of the data-parallel path: replaces nn.DataParallel's gather (recognition_model.py:284).
+ * One process per GPU; rank 0 draws a 128-byte id (sst_comm_unique_id) and hands it to every rank over any host channel;
+ * sst_comm_init (collective, uses the calling thread's current device) returns an opaque communicator;
+ * sst_comm_allreduce_bucket reduces `count` elements of a gradient bucket IN PLACE across the ranks (sum, or mean when
+ * `average`) -- it only enqueues on `stream`, so the caller orders it after the backward stage that completes the bucket and
+ * before the optimizer (sst_b200/train.py GradSync).  NCCL is dlopen'ed at the first call: `lib_path` (or the environment
+ * variable SST_NCCL_LIB, or the loader's libnccl.so.2) names the library, normally the one the host framework already uses.
+ * sst_comm_nccl_version: e.g. 22809, or a negative SST_E_* when NCCL cannot be loaded.
+ * ---------------------------------------------------------------------------------------------------------- */
+int sst_comm_unique_id(void* id_out /* 128 bytes, host */, const char* lib_path);
+int sst_comm_init(const void* id /* 128 bytes, host */, int rank, int world, const char* lib_path, void** comm_out);
+int sst_comm_allreduce_bucket(void* comm, void* buf, int64_t count, int dtype, int average, void* stream);
+int sst_comm_destroy(void* comm);
+int sst_comm_nccl_version(const char* lib_path);
+
 /*  sst_set_dropout_salt : register (NULL: unregister) a device uint64 every dropout-drawing kernel launched afterwards adds to its
  *                         seed.  Seeds, the learning rate and Adam's bias corrections cross this ABI by value, which a captured
  *                         CUDA graph replays unchanged: with a salt registered, sst_write_scalars in front

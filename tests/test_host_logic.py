@@ -35,6 +35,17 @@ def test_cabi_library_exports_every_declared_symbol():
     assert lib.sst_launch_count() == 0  # nothing was launched by loading
 
 
+def test_comm_entry_points_load_nccl_and_report_errors():
+    """sst_comm_* (include/sst.h): NCCL is dlopen'ed at the first call, from the library PyTorch itself uses; no GPU is needed to
+    load it and ask for its version; a path that does not exist must come back as SST_E_COMM with a message, not crash."""
+    import ctypes as C
+    v = L.comm_nccl_version()
+    assert v >= 21000, v                                         # NCCL >= 2.10 (ncclAvg): 2.28.9 reports 22809
+    assert L.lib().sst_comm_allreduce_bucket(None, None, C.c_int64(0), 0, 1, None) == -1        # SST_E_ARG: null communicator
+    assert b"bad arguments" in L.lib().sst_last_error()
+    assert L.lib().sst_comm_destroy(None) == 0
+
+
 def test_missing_device_fails_loudly():
     if torch.cuda.is_available():
         pytest.skip("GPU present")

@@ -40,16 +40,18 @@ def _batch(rank):
     return O.synthetic_batch(seed=90 + rank, ragged=[[70, 100, 30], [100, 55, 44]][rank], tgt_lens=[[9, 14, 5], [12, 6, 8]][rank])
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, native):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    if native:
+        os.environ["SST_COMM"] = "native"          # buckets through libsst.so's own communicator (sst_comm_*, include/sst.h)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     cfg = O.make_cfg(n_enc=1, n_dec=1, rel_dist=100, alpha=0.2)
     sd0 = O.synthetic_state_dict(cfg, 7)
     tr = _make_trainer(cfg, sd0, dev, True)
-    from sst_b200.train import prepare_batch
+    assert (tr.sync.comm is not None) == bool(native)
     d = tr.to_device(tr.prepare(_batch(rank)))
     tr.step_device(d, shift_r=0)
     torch.cuda.synchronize()
@@ -60,13 +62,14 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_allreduced_gradient_is_the_mean_of_the_per_rank_gradients():
+@pytest.mark.parametrize("native", [False, True], ids=["torch_distributed", "sst_comm"])
+def test_allreduced_gradient_is_the_mean_of_the_per_rank_gradients(native):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
     world = 2
     out_dir = tempfile.mkdtemp()
-    mp.spawn(_worker, args=(world, _free_port(), out_dir), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out_dir, native), nprocs=world, join=True)
     res = [torch.load(os.path.join(out_dir, "rank%d.pt" % r)) for r in range(world)]
     assert torch.equal(res[0]["p"], res[1]["p"]) and torch.equal(res[0]["g"], res[1]["g"])       # replicas stay identical
     # single-process gradients of each rank's batch from the same initial weights
