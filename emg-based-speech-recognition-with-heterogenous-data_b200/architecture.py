@@ -39,6 +39,8 @@ try:
     _define("string", "sst_dtype", "fp32", "compute dtype of the B200 path: fp32 (parity) or bf16 (tensor cores)")
     _define("string", "sst_ffn_activation", "relu", "feed-forward activation: relu (the reference as shipped, transformer.py:45,61) or gelu "
             "(exact erf; the variant of its logs_to_save/GELU_* runs)")
+    _define("boolean", "sst_packed", True, "run ragged batches packed (sum(lengths) rows, attention by row offsets) instead of padding "
+            "every utterance to the longest (data_utils.py:176-185 + pad_sequence, architecture.py:116-117)")
 except ImportError:                                               # pragma: no cover
     FLAGS = None
 
@@ -196,7 +198,7 @@ class Model(nn.Module):
         self.cfg = dict(d_model=D, d_ff=Fd, n_enc=_flag("num_layers_encoder", 6), n_dec=_flag("num_layers_decoder", 6),
                         n_heads=_flag("n_heads_encoder", 8), n_heads_dec=_flag("n_heads_decoder", 8), rel_dist=R,
                         dropout=_flag("dropout_model", .2), dropout_pos=_flag("dropout_pos_emb", .2),
-                        activation=str(_flag("sst_ffn_activation", "relu")).lower())
+                        activation=str(_flag("sst_ffn_activation", "relu")).lower(), packed=bool(_flag("sst_packed", True)))
         self.pad = _flag("pad", PAD)
         self.conv_blocks = nn.Sequential(ResBlock(8, D, 2), ResBlock(D, D, 2), ResBlock(D, D, 2))
         self.w_raw_in = nn.Linear(D, D)

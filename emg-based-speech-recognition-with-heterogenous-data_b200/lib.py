@@ -478,7 +478,8 @@ class PermutePlan:
         return self.table is not None and all(a.data_ptr() == pa and b.data_ptr() == pb for a, pa, b, pb in self.ptrs)
 
     def replay(self):
-        check(lib().sst_permute3_cast_batch(ptr(self.table), self.n, self.blocks, stream()), "sst_permute3_cast_batch")
+        with _scope("weight_repack"):
+            check(lib().sst_permute3_cast_batch(ptr(self.table), self.n, self.blocks, stream()), "sst_permute3_cast_batch")
 
 
 def permute3_cast(inp, out, dims, in_strides, out_strides, accumulate=False):
