@@ -215,13 +215,24 @@ def test_graphed_steps_equal_eager_steps(accumulate_every):
     live = [e for e in tr._graphs["graphs"].values() if e["graph"] is not None]
     assert len(live) == (1 if accumulate_every == 1 else 2), "one graph per signature (accumulate / step) expected, got %d" % len(live)
     assert tr.flat.step_count == out["eager"][2].flat.step_count == 8 // accumulate_every and tr.batch_idx == 8
+    # Two runs of the SAME eager loop already differ a little: the weight-gradient GEMMs add their split-K partials with atomics, and
+    # AdamW's first steps move a weight by ~lr * sign(g), so an entry whose gradient is ~0 can go the other way.  Yardsticks that
+    # ignore those few entries but catch a replay that used a stale learning rate / bias correction / input: the loss of every step
+    # to 1e-3 (a stale lr would be off by up to 8/3 at step 8), and each tensor's total update in relative L2.
     for a, b in zip(out["eager"][0], out["graphed"][0]):
         for x, y in zip(a, b):
-            assert abs(x - y) <= 2e-5 * abs(x), (out["eager"][0], out["graphed"][0])
+            assert abs(x - y) <= 1e-3 * abs(x), (out["eager"][0], out["graphed"][0])
+    worst = (0.0, None)
     for n, p in out["eager"][1].items():
         upd = (p - sd0[n].to(DEV)).double()
-        d = (out["graphed"][1][n].double() - p.double()).abs().max()
-        assert float(d) <= 2e-2 * float(upd.abs().max()) + 1e-9, (n, float(d), float(upd.abs().max()))
+        if float(upd.norm()) == 0.0:
+            assert torch.equal(out["graphed"][1][n], p)
+            continue
+        if n.startswith("conv_blocks.") and n.endswith(".bias") and ".bn" not in n and "res_norm" not in n:
+            continue      # conv biases in front of BatchNorm: true gradient 0, AdamW amplifies pure rounding noise
+        e = float((out["graphed"][1][n].double() - p.double()).norm() / upd.norm())
+        worst = max(worst, (e, n))
+    assert worst[0] < 0.1, worst
 
 
 def test_graphed_replays_draw_fresh_dropout_masks():
