@@ -406,8 +406,8 @@ def run_also(args, w, world, rank, dev, trainer, model, barrier, max_over_ranks)
                 "cuda_graphs": None if ms_graphed is None else {
                     "ms_per_cycle": round(ms_graphed, 3), "frames_per_s": round(n_micro * utt * frames / (ms_graphed / 1e3), 1),
                     "what": "Trainer.step_graphed: each of the 12 micro-batch signatures replayed as one CUDA graph (dropout salt, "
-                            "learning rate and Adam bias corrections through device memory); the eager cycle above is bound by the "
-                            "host's launch rate"}}
+                            "learning rate and Adam bias corrections through device memory).  Small micro-batches are bound by per-kernel "
+                            "floors on the device (~11 us per GEMM launch), not by the host's launch rate, so the gain is a few %"}}
     guarded("cfg4_accumulation", cfg4)
 
     # ---- cfg1 (BASELINE.json configs[0]): the reference's CPU-runnable batch, 4 utterances x 200 frames -- launch-bound on a B200 ---
