@@ -225,8 +225,13 @@ __device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
+// Arrive on a barrier of ANOTHER CTA of the cluster.  Default semantics (.release at .cta scope), NOT .release.cluster: a cluster-scope
+// release compiles to MEMBAR.ALL.GPU + ERRBAR, i.e. the arriving thread first waits until every global store it has issued (the GEMM
+// epilogue's output tile!) is visible GPU-wide -- 11 % of the stall samples of the epilogue-bound GEMMs (ncu, round 2).  What the
+// arrival publishes here is "my tcgen05.ld of the accumulator has completed", which tcgen05.wait::ld + tcgen05.fence::before_thread_sync
+// already order; no global data is handed to the peer.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into THIS CTA's shared memory whose bytes are counted on an mbarrier of the pair's leader CTA
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar, int32_t x, int32_t y) {
