@@ -316,25 +316,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::tc_fence_after();
       if (warp == 2 && lane == 0) SST_TRACE(8 + 2 * ((u - unit0) / unit_stride));       // tile's accumulator ready
       bool row_ok = m < p.M;
-      long out_row = m;
+      int out_row = m;                               // output rows stay far below 2^31 (checked at launch): 32-bit bookkeeping
       if (p.remap_P > 0) {
         int chunk = m / p.remap_P;
         int t = m - chunk * p.remap_P - p.remap_j0;
         row_ok = row_ok && t >= 0 && t < p.remap_T;
-        out_row = (long)chunk * p.remap_T + t;
+        out_row = chunk * p.remap_T + t;
       }
       // Coalesced bf16 stores: the warp's (32 rows x 32 columns) chunk is transposed through shared memory so that one store
       // instruction writes 8 rows x 64 contiguous bytes (full sectors) instead of 32 rows x 16 bytes.  Lane l stores the
       // 16-byte piece (l & 3) of rows it*8 + (l >> 2); the row bookkeeping of those rows comes from their owner lanes.
       const bool staged = !p.atomic_out && !p.out_f32 && !(p.epilogue & SST_EPI_ACCUM) && (p.ldc & 7) == 0 && p.out_seg_cols == 0;
-      long st_row[4];
-      bool st_ok[4];
+      int st_row[4];                                 // output row, or -1 when the owner lane's row is not stored
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int src = it * 8 + (lane >> 2);
-        st_row[it] = __shfl_sync(0xffffffffu, out_row, src);
-        st_ok[it] = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, src) != 0;
-      }
+      for (int it = 0; it < 4; ++it) st_row[it] = __shfl_sync(0xffffffffu, row_ok ? out_row : -1, it * 8 + (lane >> 2));
 #pragma unroll
       for (int lc0 = 0; lc0 < CPW; ++lc0) {
         const int c = cg * CPW + lc0;
@@ -387,11 +382,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int i = 0; i < 32; ++i) v[i] = ((mb >> i) & 1u) ? v[i] * p.mask_scale : 0.f;
             }
           }
-          long cb = out_row * p.ldc + nbase;
+          long cb = (long)out_row * p.ldc + nbase;
           if (p.out_seg_cols > 0) {             // the 32-column chunk never straddles a segment (segments are multiples of 32)
             const int grp = nbase / p.out_grp_cols, nin = nbase - grp * p.out_grp_cols;
             const int seg = nin / p.out_seg_cols;
-            cb = p.out_grp_off[grp] + (long)seg * p.out_seg_stride + out_row * p.ldc + (nin - seg * p.out_seg_cols);
+            cb = p.out_grp_off[grp] + (long)seg * p.out_seg_stride + (long)out_row * p.ldc + (nin - seg * p.out_seg_cols);
           }
           if (chunk_staged) {
 #pragma unroll
@@ -411,8 +406,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               uint4 o;
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
                            : "r"(stg + rl * 64 + ((uint32_t)(piece ^ ((rl >> 1) & 3)) << 4)));
-              if (st_ok[it])
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + st_row[it] * p.ldc + nbase + piece * 8) = o;
+              if (st_row[it] >= 0)
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (long)st_row[it] * p.ldc + nbase + piece * 8) = o;
             }
             __syncwarp();
           } else if (!row_ok) {
