@@ -330,13 +330,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int st_row[4];                                 // output row, or -1 when the owner lane's row is not stored
 #pragma unroll
       for (int it = 0; it < 4; ++it) st_row[it] = __shfl_sync(0xffffffffu, row_ok ? out_row : -1, it * 8 + (lane >> 2));
+      // The accumulator chunk of the NEXT column block is requested while this block's staged tile leaves through shared memory
+      // (its registers are free by then), so that only the tile's first TMEM load is waited for with nothing else to do.
+      uint32_t r[32];
+      const uint32_t taddr0 = tmem_base + (uint32_t)(acc * BN + cg * CPW * 32) + ((uint32_t)(q * 32) << 16);
+      ptx::tmem_ld_32x32b_x32(taddr0, r);
 #pragma unroll
       for (int lc0 = 0; lc0 < CPW; ++lc0) {
         const int c = cg * CPW + lc0;
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + (uint32_t)(acc * BN + c * 32) + ((uint32_t)(q * 32) << 16);
-        ptx::tmem_ld_32x32b_x32(taddr, r);
         ptx::tmem_ld_wait();
+        bool next_requested = false;
         const int nbase = n0 + c * 32;
         const bool chunk_staged = staged && nbase + 32 <= p.N;          // warp-uniform
         if ((row_ok || chunk_staged) && nbase < p.N) {
@@ -400,6 +403,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               ptx::st_shared_v4(stg + lane * 64 + ((uint32_t)(j ^ ((lane >> 1) & 3)) << 4), w4[0], w4[1], w4[2], w4[3]);
             }
             __syncwarp();
+            if (lc0 + 1 < CPW) {                    // warp-uniform branch (chunk_staged is)
+              ptx::tmem_ld_32x32b_x32(taddr0 + (uint32_t)((lc0 + 1) * 32), r);
+              next_requested = true;
+            }
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
               const int rl = it * 8 + (lane >> 2), piece = lane & 3;
@@ -466,6 +473,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
+        if (!next_requested && lc0 + 1 < CPW) ptx::tmem_ld_32x32b_x32(taddr0 + (uint32_t)((lc0 + 1) * 32), r);
       }
       ptx::tc_fence_before();
       __syncwarp();
