@@ -406,6 +406,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (lc0 + 1 < CPW) {                    // warp-uniform branch (chunk_staged is)
               ptx::tmem_ld_32x32b_x32(taddr0 + (uint32_t)((lc0 + 1) * 32), r);
               next_requested = true;
+              __syncwarp();                         // keeps the request in FRONT of the loads / stores below (ptxas sinks it otherwise)
             }
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
