@@ -707,15 +707,23 @@ class Engine:
         x_enc, ctx = self.encode(x_raw, lengths, training, seed, packed=self.cfg.get("packed", True) if packed is None else packed,
                                  meta=meta)
         B, Lmax = ctx.B, ctx.Lmax
+        has_dec = y is not None and y.numel() > 0
+        cross = None
+        if has_dec and self.n_dec > 0:
+            # the one big GEMM of the decoder (every layer's cross-attention keys / values) goes BEFORE the CTC kernels are put on
+            # the side stream: their 64 blocks hold 176 KB of shared memory each, and a persistent GEMM that shares the machine
+            # with them runs on the remaining SMs only -- the small per-layer decoder kernels are the better company
+            kv_all = self._linear_fwd(x_enc, ctx.M, "dec.kv_all")
+            cross = [kv_all[:, i * 2 * self.D:(i + 1) * 2 * self.D] for i in range(self.n_dec)]
         ctx.enc_logits = self.enc_head(x_enc, ctx.M, ctx)
         ctx.dec_logits = None
         ctx.loss_out = torch.zeros(3, dtype=torch.float32, device=self.dev)
         if ctc is not None:
             self._ctc_async(ctx, *ctc)
-        if y is not None and self.n_dec >= 0 and y.numel() > 0:
+        if has_dec:
             if tgt_lens is None:
                 tgt_lens = (y != PAD).sum(1).to(torch.int32)
-            x_dec = self.decode(y, tgt_lens, x_enc, ctx.lens, B, Lmax, training, ctx.seeds, ctx, Mm=ctx.M, mem_off=ctx.off)
+            x_dec = self.decode(y, tgt_lens, x_enc, ctx.lens, B, Lmax, training, ctx.seeds, ctx, Mm=ctx.M, mem_off=ctx.off, cross=cross)
             ctx.dec_logits = self.dec_head(x_dec, B * y.shape[1])
         return ctx.enc_logits, ctx.dec_logits, ctx
 
