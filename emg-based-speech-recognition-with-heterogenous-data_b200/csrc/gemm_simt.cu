@@ -164,6 +164,7 @@ int launch_gemm_simt(const SstGemmDesc& d, const void* A, const void* B, void* C
   p.alpha = d.alpha; p.mask_scale = d.mask_scale;
   p.drop_thr = drop_threshold16(d.drop_p);
   p.drop_scale = d.drop_p < 1.f ? 1.f / (1.f - d.drop_p) : 0.f;
+  SST_REQUIRE(d.col_acc == nullptr || d.col_acc_mode == 0, SST_E_UNSUPPORTED, "col_acc is a tensor-core epilogue feature: use sst_colsum_accum / sst_colstats");
   p.seed = d.seed;
   p.salt = dropout_salt();
   p.bias = reinterpret_cast<const float*>(bias);

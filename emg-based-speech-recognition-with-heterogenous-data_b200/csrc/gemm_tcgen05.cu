@@ -52,6 +52,7 @@ struct GemmKParams {
   int remap_P, remap_T, remap_j0;
   int out_seg_cols, out_grp_cols;       // segmented output columns (SstGemmDesc), 0 = plain
   long out_seg_stride, out_grp_off[3];
+  void* col_acc; int col_mode, col_grp; // fused column sums (1: float) / BatchNorm statistics (2: double, groups of col_grp columns)
 };
 
 // Debug timeline (-DSST_GEMM_TRACE, tools/gemm_trace.py): CTA 0 stamps %globaltimer at its pipeline events.
@@ -408,14 +409,56 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               next_requested = true;
               __syncwarp();                         // keeps the request in FRONT of the loads / stores below (ptxas sinks it otherwise)
             }
+            float cs[8], cq[8];                     // this lane's share of the chunk's column sums (/ sums of squares)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
               const int rl = it * 8 + (lane >> 2), piece = lane & 3;
               uint4 o;
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
                            : "r"(stg + rl * 64 + ((uint32_t)(piece ^ ((rl >> 1) & 3)) << 4)));
-              if (st_row[it] >= 0)
+              if (st_row[it] >= 0) {
                 *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (long)st_row[it] * p.ldc + nbase + piece * 8) = o;
+                if (p.col_mode != 0) {              // warp-uniform; the values exactly as stored
+                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&o);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(h2[j]);
+                    cs[2 * j] += f.x; cs[2 * j + 1] += f.y;
+                    if (p.col_mode == 2) { cq[2 * j] = fmaf(f.x, f.x, cq[2 * j]); cq[2 * j + 1] = fmaf(f.y, f.y, cq[2 * j + 1]); }
+                  }
+                }
+              }
+            }
+            if (p.col_mode != 0) {
+              // the 8 lanes that hold the same 8 columns (lane & 3 == piece) add up: afterwards lanes 0..3 own 8 columns each
+#pragma unroll
+              for (int sh = 4; sh < 32; sh <<= 1) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], sh);
+                  if (p.col_mode == 2) cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], sh);
+                }
+              }
+              if (lane < 4) {
+                const int n = nbase + lane * 8;
+                if (p.col_mode == 1) {
+                  float* dst = reinterpret_cast<float*>(p.col_acc) + n;
+                  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                    red_add4(dst, cs[0], cs[1], cs[2], cs[3]);
+                    red_add4(dst + 4, cs[4], cs[5], cs[6], cs[7]);
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) atomicAdd(dst + j, cs[j]);
+                  }
+                } else {
+                  const int G = p.col_grp, g = n / G;
+                  double* dst = reinterpret_cast<double*>(p.col_acc) + (long)g * 2 * G + (n - g * G);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) { atomicAdd(dst + j, (double)cs[j]); atomicAdd(dst + G + j, (double)cq[j]); }
+                }
+              }
             }
             __syncwarp();
           } else if (!row_ok) {
@@ -645,6 +688,17 @@ int launch_gemm_tcgen05(const SstGemmDesc& d, const void* A, const void* B, void
   p.aux = aux; p.ldaux = d.ldaux; p.aux_f32 = d.aux_dtype == SST_F32;
   p.C = C; p.ldc = d.ldc; p.out_f32 = d.out_dtype == SST_F32;
   p.remap_P = d.remap_P; p.remap_T = d.remap_T; p.remap_j0 = d.remap_j0;
+  p.col_acc = d.col_acc; p.col_mode = d.col_acc != nullptr ? d.col_acc_mode : 0;
+  p.col_grp = d.col_acc_grp > 0 ? d.col_acc_grp : (int)d.N;
+  if (p.col_mode != 0) {
+    SST_REQUIRE((p.col_mode == 1 || p.col_mode == 2) && !p.mode_mn && d.out_dtype == SST_BF16 && !(d.epilogue & SST_EPI_ACCUM) &&
+                d.N % 32 == 0 && d.ldc % 8 == 0 && d.out_seg_cols == 0 && p.col_grp % 8 == 0 && d.N % p.col_grp == 0, SST_E_ARG,
+                "col_acc needs a bf16 TN result without ACCUM / segments, N %% 32 == 0, ldc %% 8 == 0 and groups of whole 8-column pieces");
+    if (p.col_mode == 2) {
+      cudaError_t e = cudaMemsetAsync(d.col_acc, 0, sizeof(double) * 2 * (size_t)d.N, st);
+      SST_REQUIRE(e == cudaSuccess, SST_E_LAUNCH, "memset: %s", cudaGetErrorString(e));
+    }
+  }
   p.out_seg_cols = (int)d.out_seg_cols; p.out_grp_cols = (int)d.out_grp_cols; p.out_seg_stride = d.out_seg_stride;
   for (int s = 0; s < 3; ++s) p.out_grp_off[s] = d.out_grp_off[s];
   if (d.out_seg_cols > 0)

@@ -218,9 +218,17 @@ class Engine:
                   layout=L.GEMM_TN_BMN if w_kn else L.GEMM_TN)
         return out
 
+    def _fused_cols(self):
+        """Column sums / BatchNorm statistics ride in the tensor-core GEMM epilogue (SstGemmDesc.col_acc); the fp32 parity mode and
+        the CUDA-core cross-check keep the separate passes."""
+        import os
+        return self.dtype == torch.bfloat16 and not self.force_simt and os.environ.get("SST_FUSED_COLS", "1") != "0"   # =0: A/B switch
+
     def _linear_bwd(self, dy, x, M, key, G, wname, bname=None, dx_out=None, accum_dx=False, aux=None, mask_scale=1.0,
-                    need_dx=True, K_dy=None):
-        """dW (+)= dy^T x into G[wname] (reference layout (N,K)); db += colsum(dy); dx (+)= dy W (optional relu/dropout mask)."""
+                    need_dx=True, K_dy=None, dx_colsum=None):
+        """dW (+)= dy^T x into G[wname] (reference layout (N,K)); db += colsum(dy); dx (+)= dy W (optional relu/dropout mask).
+        dx_colsum: fp32 accumulator that receives the column sums of dx from the same GEMM's epilogue (the bias gradient of the
+        layer below)."""
         W = self.pk[key]
         N, K = W.shape
         if G is not None:
@@ -235,7 +243,7 @@ class Engine:
             dx_out = self.empty(M, K)
         epi = (L.EPI_ACCUM if accum_dx else 0) | (L.EPI_MULMASK if aux is not None else 0)
         self.gemm(dy, WT, dx_out, M, K, N, dy.stride(0), WT.stride(0), dx_out.stride(0), aux=aux, ldaux=aux.stride(0) if aux is not None else 0,
-                  epilogue=epi, mask_scale=mask_scale, a_cols=N)
+                  epilogue=epi, mask_scale=mask_scale, a_cols=N, col_acc=dx_colsum, col_acc_mode=1 if dx_colsum is not None else 0)
         return dx_out
 
     def _ffn1_fwd(self, x, M, pfx, p, seed):
@@ -252,10 +260,14 @@ class Engine:
         """gradient w.r.t. linear1's output: (dy W2) masked by the activation derivative and the dropout keep factors."""
         if not self.gelu:
             keep_scale = 1.0 / (1.0 - p) if p > 0 else 1.0
-            return self._linear_bwd(dy, h, M, pfx + ".linear2", G, pfx + ".linear2.weight", pfx + ".linear2.bias", aux=h, mask_scale=keep_scale)
+            # the masked input gradient IS linear1's output gradient: its column sums (linear1.bias) leave from the same epilogue
+            fused = self._fused_cols() and self.F % 32 == 0
+            dh = self._linear_bwd(dy, h, M, pfx + ".linear2", G, pfx + ".linear2.weight", pfx + ".linear2.bias", aux=h, mask_scale=keep_scale,
+                                  dx_colsum=G[pfx + ".linear1.bias"] if fused else None)
+            return dh, fused
         dh = self._linear_bwd(dy, h, M, pfx + ".linear2", G, pfx + ".linear2.weight", pfx + ".linear2.bias")
         L.gelu_dropout_bwd(self.dt, M, self.F, dh, self.F, pre, self.F, p, seed, dh, self.F)
-        return dh
+        return dh, False
 
     def _ln_fwd(self, x, r, M, prefix, p, seed):
         """returns y; r's buffer is overwritten with the pre-norm sum s (saved for backward)."""
@@ -281,14 +293,16 @@ class Engine:
                            q_off=q_off, k_off=k_off, q_rows_total=q_rows, k_rows_total=k_rows)
 
     # ------------------------------------------------------------------------------------------------ conv front-end
-    def _bn_stats(self, x, rows, ld, prefix, training):
+    def _bn_stats(self, x, rows, ld, prefix, training, stats=None):
+        """stats: float64 [2*C] batch sums / sums of squares the producing GEMM's epilogue already accumulated (SstGemmDesc.col_acc)."""
         C = self.D
         mean = self.empty(C, dtype=torch.float32)
         invstd = self.empty(C, dtype=torch.float32)
         rm, rv = self.Bf[prefix + ".running_mean"], self.Bf[prefix + ".running_var"]
         if training:
-            stats = self._bn_scratch
-            L.colstats(self.dt, x, rows, C, ld, stats)
+            if stats is None:
+                stats = self._bn_scratch
+                L.colstats(self.dt, x, rows, C, ld, stats)
             L.bn_finalize(stats, rows, C, 1e-5, 0.1, mean, invstd, rm, rv, True)
             self.Bf[prefix + ".num_batches_tracked"] += 1
         else:
@@ -301,31 +315,41 @@ class Engine:
         rows = n * T
         pfx = "conv_blocks.%d" % i
         c = Ctx(i=i, n=n, T_in=T_in, T=T, inp=inp)
+        # training-mode BatchNorm statistics of the three conv outputs come out of the conv GEMMs' epilogues (col_acc mode 2)
+        fuse = training and self._fused_cols()
+        st = (lambda k: self.empty(2 * k * C, dtype=torch.float64)) if fuse else (lambda k: None)
+        mode = 2 if fuse else 0
         if i == 0:
             col = self.empty(rows, 32)
             L.im2col_first(self.dt, inp, col, n, T_in)
             ycat = self.empty(rows, 2 * C)
-            self.gemm(col, self.pk["first.W"], ycat, rows, 2 * C, 32, 32, 32, 2 * C, bias=self.pk["first.b"], epilogue=L.EPI_BIAS)
+            st_cat = st(2)                               # [bn1: sums C | squares C][res_norm: sums C | squares C]
+            self.gemm(col, self.pk["first.W"], ycat, rows, 2 * C, 32, 32, 32, 2 * C, bias=self.pk["first.b"], epilogue=L.EPI_BIAS,
+                      col_acc=st_cat, col_acc_mode=mode, col_acc_grp=C)
             yc1, ld1, yr, ldr = ycat, 2 * C, ycat[:, C:], 2 * C
+            st1, str_ = (st_cat[:2 * C], st_cat[2 * C:]) if fuse else (None, None)
             c.col = col
         else:
             P = T + 1                                    # pair-rows per chunk of the (T_in + 2)-row padded input
             yc1 = self.empty(rows, C)
+            st1, str_ = st(1), st(1)
             self.gemm(inp, self.pk[pfx + ".conv1"], yc1, n * P, C, 3 * C, 2 * C, 3 * C, C, n_seg=3, a_row_shift=(0, 0, 1),
                       a_col0=(0, C, 0), a_rows=n * P, a_cols=2 * C, remap=(P, T, 0), bias=self.P[pfx + ".conv1.bias"],
-                      epilogue=L.EPI_BIAS)
+                      epilogue=L.EPI_BIAS, col_acc=st1, col_acc_mode=mode)
             yr = self.empty(rows, C)
             self.gemm(inp, self.pk[pfx + ".res"], yr, n * P, C, C, 2 * C, C, C, a_col0=(C, 0, 0), a_rows=n * P, a_cols=2 * C,
-                      remap=(P, T, 0), bias=self.P[pfx + ".residual_path.bias"], epilogue=L.EPI_BIAS)
+                      remap=(P, T, 0), bias=self.P[pfx + ".residual_path.bias"], epilogue=L.EPI_BIAS, col_acc=str_, col_acc_mode=mode)
             ld1, ldr = C, C
-        bn1 = self._bn_stats(yc1, rows, ld1, pfx + ".bn1", training)
+        bn1 = self._bn_stats(yc1, rows, ld1, pfx + ".bn1", training, st1)
         h1p = self.empty(n, T + 2, C)
         L.bn_apply(self.dt, n, T, C, yc1, ld1, bn1, None, 0, None, True, h1p, 1, 1)
         yc2 = self.empty(rows, C)
+        st2 = st(1)
         self.gemm(h1p, self.pk[pfx + ".conv2"], yc2, n * (T + 2), C, 3 * C, C, 3 * C, C, n_seg=3, a_row_shift=(-1, 0, 1),
-                  a_rows=n * (T + 2), a_cols=C, remap=(T + 2, T, 1), bias=self.P[pfx + ".conv2.bias"], epilogue=L.EPI_BIAS)
-        bn2 = self._bn_stats(yc2, rows, C, pfx + ".bn2", training)
-        bnr = self._bn_stats(yr, rows, ldr, pfx + ".res_norm", training)
+                  a_rows=n * (T + 2), a_cols=C, remap=(T + 2, T, 1), bias=self.P[pfx + ".conv2.bias"], epilogue=L.EPI_BIAS,
+                  col_acc=st2, col_acc_mode=mode)
+        bn2 = self._bn_stats(yc2, rows, C, pfx + ".bn2", training, st2)
+        bnr = self._bn_stats(yr, rows, ldr, pfx + ".res_norm", training, str_)
         lead = 0 if last else 1
         out = self.empty(n, T + 2 * lead, C)
         L.bn_apply(self.dt, n, T, C, yc2, C, bn2, yr, ldr, bnr, True, out, lead, lead)
@@ -420,9 +444,10 @@ class Engine:
         pfx = "transformerEncoder.layers.%d" % i
         a = pfx + ".self_attn"
         ds2, dy2 = self._ln_bwd(dx2, c.ln2, M, pfx + ".norm2", G)
-        dh = self._ffn2_bwd(dy2, c.h, c.pre, M, pfx, G, c.p, c.s_ffn)
+        dh, b1_done = self._ffn2_bwd(dy2, c.h, c.pre, M, pfx, G, c.p, c.s_ffn)
         # dx1 = ds2 + dh W1   (accumulated in place into ds2)
-        self._linear_bwd(dh, c.x1, M, pfx + ".linear1", G, pfx + ".linear1.weight", pfx + ".linear1.bias", dx_out=ds2, accum_dx=True)
+        self._linear_bwd(dh, c.x1, M, pfx + ".linear1", G, pfx + ".linear1.weight", None if b1_done else pfx + ".linear1.bias",
+                         dx_out=ds2, accum_dx=True)
         ds1, dy = self._ln_bwd(ds2, c.ln1, M, pfx + ".norm1", G)
         # out-projection y = o W_o^T-form: packed key ".o" holds (H*dh, D) = w_o itself, ".o.T" holds (D, H*dh)
         # weight gradient directly in the parameter layout: d w_o (H*dh, D) = o^T dy
@@ -493,8 +518,9 @@ class Engine:
         pfx = "transformerDecoder.layers.%d" % i
         a, m = pfx + ".self_attn", pfx + ".multihead_attn"
         ds3, dy3 = self._ln_bwd(dt3, c.ln3, M, pfx + ".norm3", G)
-        dh = self._ffn2_bwd(dy3, c.h, c.pre, M, pfx, G, c.p, c.s_ffn)
-        self._linear_bwd(dh, c.t2, M, pfx + ".linear1", G, pfx + ".linear1.weight", pfx + ".linear1.bias", dx_out=ds3, accum_dx=True)
+        dh, b1_done = self._ffn2_bwd(dy3, c.h, c.pre, M, pfx, G, c.p, c.s_ffn)
+        self._linear_bwd(dh, c.t2, M, pfx + ".linear1", G, pfx + ".linear1.weight", None if b1_done else pfx + ".linear1.bias",
+                         dx_out=ds3, accum_dx=True)
         ds2, dy2 = self._ln_bwd(ds3, c.ln2, M, pfx + ".norm2", G)
         # cross attention
         self.gemm(c.o2, dy2, G[m + ".w_o"], D, D, M, D, D, D, layout=L.GEMM_NT_MN, epilogue=L.EPI_ACCUM)

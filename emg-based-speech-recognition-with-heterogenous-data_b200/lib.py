@@ -26,7 +26,8 @@ class GemmDesc(C.Structure):
                 ("epilogue", C.c_int32), ("alpha", C.c_float), ("mask_scale", C.c_float), ("drop_p", C.c_float),
                 ("seed", C.c_uint64), ("remap_P", C.c_int32), ("remap_T", C.c_int32), ("remap_j0", C.c_int32),
                 ("force_simt", C.c_int32),
-                ("out_seg_cols", C.c_int64), ("out_seg_stride", C.c_int64), ("out_grp_cols", C.c_int64), ("out_grp_off", C.c_int64 * 3)]
+                ("out_seg_cols", C.c_int64), ("out_seg_stride", C.c_int64), ("out_grp_cols", C.c_int64), ("out_grp_off", C.c_int64 * 3),
+                ("col_acc", C.c_void_p), ("col_acc_mode", C.c_int32), ("col_acc_grp", C.c_int32)]
 
 
 _lib = None
@@ -147,7 +148,9 @@ def require_device():
 def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, layout=GEMM_TN, bias=None, aux=None, ldaux=0, epilogue=0, alpha=1.0,
          mask_scale=1.0, drop_p=0.0, seed=0, n_seg=1, a_row_shift=(0, 0, 0), a_col0=(0, 0, 0),
          b_row_shift=(0, 0, 0), b_col0=(0, 0, 0), a_rows=None, a_cols=None, b_rows=None, b_cols=None,
-         remap=(0, 0, 0), force_simt=False, out_seg=None):
+         remap=(0, 0, 0), force_simt=False, out_seg=None, col_acc=None, col_acc_mode=0, col_acc_grp=0):
+    """col_acc / col_acc_mode / col_acc_grp: column sums (1, float32 accumulator) or BatchNorm statistics (2, float64 [2*N], zeroed
+    by the call) of the stored bf16 result, fused into the tensor-core epilogue (include/sst.h)."""
     d = GemmDesc()
     d.dtype, d.out_dtype, d.layout = dt(A), dt(Cout), layout
     d.aux_dtype = dt(aux) if aux is not None else F32
@@ -174,6 +177,8 @@ def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, layout=GEMM_TN, bias=None, aux=None
     d.epilogue, d.alpha, d.mask_scale, d.drop_p, d.seed = epilogue, alpha, mask_scale, drop_p, seed
     d.remap_P, d.remap_T, d.remap_j0 = remap
     d.force_simt = 1 if force_simt else 0
+    if col_acc is not None:
+        d.col_acc, d.col_acc_mode, d.col_acc_grp = col_acc.data_ptr(), int(col_acc_mode), int(col_acc_grp)
     if out_seg is not None:                     # (seg_cols, seg_stride, grp_cols, (grp_off0, grp_off1, grp_off2)), element units
         d.out_seg_cols, d.out_seg_stride, d.out_grp_cols = out_seg[0], out_seg[1], out_seg[2]
         for i, o in enumerate(out_seg[3]):

@@ -98,6 +98,16 @@ typedef struct SstGemmDesc {
    * w_q / w_k / w_v (transformer.py:146-149), one group per tensor -- no packed temporary, no permute.
    * out_seg_cols and out_grp_cols must be multiples of 32, N a multiple of 32. */
   int64_t out_seg_cols, out_seg_stride, out_grp_cols, out_grp_off[3];
+  /* Column accumulators fused into the epilogue (tensor-core path, bf16 C stored through the staged path: layout TN / TN_BMN,
+   * N % 32 == 0, ldc % 8 == 0, no ACCUM, no segmented output).  Over the rows that are actually stored, of the values AS
+   * STORED (rounded to bf16) -- what a separate pass over C would read:
+   *   col_acc_mode 1:  ((float*)col_acc)[n] += sum_m C[m,n]            the bias gradient of the layer whose output gradient C is
+   *                    (replaces sst_colsum_accum over C: linear1.bias, transformer.py:61)
+   *   col_acc_mode 2:  ((double*)col_acc)[g*2G + n%G] += sum_m C[m,n],  [g*2G + G + n%G] += sum_m C[m,n]^2,  g = n / G,
+   *                    G = col_acc_grp (0: N): BatchNorm batch statistics of a conv output in sst_colstats' layout per group of G
+   *                    channels (architecture.py:27,29,33); the call zeroes the 2*N doubles first. */
+  void* col_acc;
+  int32_t col_acc_mode, col_acc_grp;
 } SstGemmDesc;
 
 int sst_gemm(const SstGemmDesc* d, const void* A, const void* B, void* C, const void* bias /*fp32[N]*/,

@@ -213,3 +213,46 @@ def test_argument_errors_are_reported(L):
         L.gemm(A[:, :68], B[:, :68], C, 128, 128, 68, 68, 68, 128)
     with pytest.raises(L.SstError):
         L.gemm(A, B, C, 128, 128, 72, 72, 72, 128, epilogue=L.EPI_BIAS)      # BIAS without a bias pointer
+
+
+@pytest.mark.parametrize("M,N,K,grp", [(800, 768, 768, 0), (4100, 3072, 768, 0), (7744, 1536, 64, 768), (333, 256, 136, 128)])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_fused_column_accumulators(L, M, N, K, grp, mode):
+    """SstGemmDesc.col_acc: the bias gradient (mode 1: float column sums, ACCUMULATED) / the BatchNorm batch statistics (mode 2: double
+    sums and sums of squares per group of `grp` channels, zeroed by the call) of the stored bf16 result leave from the GEMM's
+    epilogue -- they must be what a separate pass over the stored C gives.  Also with a masked epilogue and with a row remap that
+    drops halo rows (the dropped rows must not be counted)."""
+    g = torch.Generator(device=DEV).manual_seed(M + N)
+    A = (torch.randn(M, K, device=DEV, generator=g) * 0.5).bfloat16()
+    B = (torch.randn(N, K, device=DEV, generator=g) * 0.1).bfloat16()
+    bias = torch.randn(N, device=DEV, generator=g)
+    for remap in ((0, 0, 0), (10, 8, 1)):
+        if remap[0] and M % remap[0]:
+            continue
+        rows_out = M if not remap[0] else M // remap[0] * remap[1]
+        C = torch.full((rows_out, N), 7.0, device=DEV, dtype=torch.bfloat16)
+        if mode == 1:
+            acc = torch.full((N,), 3.0, device=DEV)                    # accumulated on top of what is there
+        else:
+            acc = torch.full((2 * N,), 123.0, device=DEV, dtype=torch.float64)      # zeroed by the call
+        L.gemm(A, B, C, M, N, K, K, K, N, bias=bias, epilogue=L.EPI_BIAS, remap=remap, col_acc=acc, col_acc_mode=mode, col_acc_grp=grp)
+        torch.cuda.synchronize()
+        stored = C.double()
+        assert not bool((C == 7.0).all(dim=1).any())                   # every output row was written
+        if mode == 1:
+            want = 3.0 + stored.sum(0)
+            assert float((acc.double() - want).abs().max()) <= 1e-5 * float(stored.abs().sum(0).max()) + 1e-3
+        else:
+            G = grp if grp else N
+            got = acc.view(N // G, 2, G)
+            s, q = stored.sum(0).view(N // G, G), (stored * stored).sum(0).view(N // G, G)
+            assert float((got[:, 0] - s).abs().max()) <= 1e-5 * float(stored.abs().sum(0).max()) + 1e-3
+            assert float((got[:, 1] - q).abs().max()) <= 1e-5 * float(q.max()) + 1e-3
+
+
+def test_fused_column_accumulators_need_the_tensor_core_path(L):
+    A = torch.randn(64, 64, device=DEV)
+    C = torch.empty(64, 64, device=DEV)
+    acc = torch.zeros(64, device=DEV)
+    with pytest.raises(L.SstError):
+        L.gemm(A, A, C, 64, 64, 64, 64, 64, 64, col_acc=acc, col_acc_mode=1)
