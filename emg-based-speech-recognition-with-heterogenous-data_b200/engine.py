@@ -218,11 +218,17 @@ class Engine:
                   layout=L.GEMM_TN_BMN if w_kn else L.GEMM_TN)
         return out
 
-    def _fused_cols(self):
-        """Column sums / BatchNorm statistics ride in the tensor-core GEMM epilogue (SstGemmDesc.col_acc); the fp32 parity mode and
-        the CUDA-core cross-check keep the separate passes."""
+    def _fused_cols(self, what="ffn"):
+        """Which column reductions ride in the tensor-core GEMM epilogue (SstGemmDesc.col_acc) instead of a separate pass.
+        Measured on cfg2 (one box, back to back, ms/step): none 51.19 | linear1.bias only 50.49 | BatchNorm statistics only 51.42 |
+        both 51.17.  The bias gradient pays (the 64000 x 3072 colsum pass costs 0.52 ms, the epilogue 0.17); the BatchNorm
+        statistics do NOT: one epilogue warp only sees 32 rows, so every channel receives rows/32 = 8000 double-precision atomics
+        per conv output (+1.9 ms of GEMM time against 0.55 ms of colstats, whose blocks reduce thousands of rows first).  Default
+        therefore 'ffn'; SST_FUSED_COLS = 0 | ffn | bn | 1 selects for experiments.  The fp32 parity mode and the CUDA-core
+        cross-check always keep the separate passes."""
         import os
-        return self.dtype == torch.bfloat16 and not self.force_simt and os.environ.get("SST_FUSED_COLS", "1") != "0"   # =0: A/B switch
+        sel = os.environ.get("SST_FUSED_COLS", "ffn")
+        return self.dtype == torch.bfloat16 and not self.force_simt and sel in ("1", what)
 
     def _linear_bwd(self, dy, x, M, key, G, wname, bname=None, dx_out=None, accum_dx=False, aux=None, mask_scale=1.0,
                     need_dx=True, K_dy=None, dx_colsum=None):
@@ -316,7 +322,7 @@ class Engine:
         pfx = "conv_blocks.%d" % i
         c = Ctx(i=i, n=n, T_in=T_in, T=T, inp=inp)
         # training-mode BatchNorm statistics of the three conv outputs come out of the conv GEMMs' epilogues (col_acc mode 2)
-        fuse = training and self._fused_cols()
+        fuse = training and self._fused_cols("bn")
         st = (lambda k: self.empty(2 * k * C, dtype=torch.float64)) if fuse else (lambda k: None)
         mode = 2 if fuse else 0
         if i == 0:
