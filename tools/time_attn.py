@@ -26,8 +26,6 @@ lse = torch.empty(2 * B * H * Lx, device="cuda")
 dqkv = torch.empty_like(qkv)
 delta = torch.empty(B * H * Lx, device="cuda")
 d = L.attn_desc(L.BF16, B, H, Lx, Lk, dh, 3 * D, 3 * D, 3 * D, D, causal, Lx == Lk, R, 1 / math.sqrt(dh), p, 1234)
-if os.environ.get("SST_KEEP_BITS") == "1":
-    L.attn_attach_keep_bits(d, "cuda")          # forward stores its dropout decisions, backward reads them
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 def run(fn):
     for _ in range(3):
